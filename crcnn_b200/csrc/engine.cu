@@ -1,0 +1,890 @@
+// C ABI implementation (include/crcnn_b200.h): contexts, device tensors, plaintext packs,
+// evaluation keys, the layer forwards and the evaluator-level operations, all on top of the
+// kernels in kernels.cu.  Host code only orchestrates; every arithmetic step runs on the GPU.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/crcnn_b200.h"
+#include "kernels.cuh"
+#include "params.h"
+
+using namespace crcnn;
+
+namespace {
+
+enum KernelClass {
+    KC_NTT_FWD = 0, KC_NTT_INV, KC_MAC, KC_PLAIN_EXPAND, KC_POOL, KC_BN, KC_PLAIN_OP,
+    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_COUNT
+};
+const char *kClassNames[KC_COUNT] = {"ntt_forward", "ntt_inverse", "weighted_sum_mac", "plain_expand_ntt", "pool_sum",
+                                     "batch_norm", "plain_op", "behz_lift", "square_tensor", "behz_floor_sk",
+                                     "relinearize", "imad_probe"};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct crcnn_tensor {
+    long count;
+    int size;
+    int ntt;  // 0 coefficient form, 1 NTT form
+    uint64_t *d;
+};
+
+struct crcnn_plain {
+    long count;
+    std::vector<uint32_t> off, idx;  // host copy of the sparse form
+    std::vector<uint64_t> val;
+    uint32_t *d_off = nullptr, *d_idx = nullptr;
+    uint64_t *d_val = nullptr;
+    uint64_t *ntt_mul = nullptr;   // [count][K][n] NTT(lift)            (multiplicative use)
+    uint64_t *ntt_add = nullptr;   // [count][K][n] NTT(Delta-scaled)    (additive use, NTT-form data)
+    uint64_t *coef_add = nullptr;  // [count][K][n] Delta-scaled         (additive use, coefficient-form data)
+};
+
+struct crcnn_evk {
+    uint64_t *d = nullptr;
+    long key_off[MAXK];
+    int digits[MAXK];
+    int dbc;
+};
+
+struct crcnn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    HostParams hp;
+    DeviceParams *dP = nullptr;
+    std::vector<void *> owned;  // table buffers
+    int n = 0, logn = 0, K = 0, S = 0;
+    int chunk_terms = 1 << 30;
+    size_t weight_cache_bytes = 24ull << 30;
+    std::string err;
+    std::map<std::vector<int>, int *> index_cache;
+    // profiling
+    bool prof_on = false;
+    long launches[KC_COUNT] = {0};
+    double ms[KC_COUNT] = {0};
+    struct Pending { int cls; cudaEvent_t a, b; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+int fail(crcnn_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? CRCNN_ERR_OUT_OF_MEMORY : CRCNN_ERR_CUDA; \
+            return fail(ctx, code__, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+        }                                                                                              \
+    } while (0)
+
+#define REQUIRE(cond, msg) \
+    do { if (!(cond)) return fail(ctx, CRCNN_ERR_INVALID_ARGUMENT, msg); } while (0)
+
+struct ProfScope {
+    crcnn_ctx *c; int cls; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(crcnn_ctx *ctx, int k) : c(ctx), cls(k) {
+        c->launches[cls]++;
+        if (!c->prof_on) return;
+        auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->pending.push_back({cls, a, b});
+    }
+};
+
+void prof_collect(crcnn_ctx *c) {
+    for (auto &p : c->pending) {
+        cudaEventSynchronize(p.b);
+        float t = 0;
+        cudaEventElapsedTime(&t, p.a, p.b);
+        c->ms[p.cls] += t;
+        c->event_pool.push_back(p.a);
+        c->event_pool.push_back(p.b);
+    }
+    c->pending.clear();
+}
+
+inline size_t poly_words(const crcnn_ctx *c) { return (size_t)c->K * c->n; }
+
+int dev_alloc(crcnn_ctx *ctx, size_t bytes, void **out) {
+    *out = nullptr;
+    if (bytes == 0) return CRCNN_OK;
+    CU(cudaMallocAsync(out, bytes, ctx->stream));
+    return CRCNN_OK;
+}
+void dev_free(crcnn_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
+
+int new_tensor(crcnn_ctx *ctx, long count, int size, int ntt, crcnn_tensor **out) {
+    auto *t = new crcnn_tensor{count, size, ntt, nullptr};
+    int rc = dev_alloc(ctx, (size_t)count * size * poly_words(ctx) * 8, (void **)&t->d);
+    if (rc) { delete t; return rc; }
+    *out = t;
+    return CRCNN_OK;
+}
+
+int ntt_inplace(crcnn_ctx *ctx, uint64_t *d, long npolys, int slot_base, int slot_count, bool inverse) {
+    ProfScope ps(ctx, inverse ? KC_NTT_INV : KC_NTT_FWD);
+    CU(launch_ntt(ctx->dP, ctx->logn, d, npolys, slot_base, slot_count, inverse, ctx->stream));
+    return CRCNN_OK;
+}
+
+int ensure_domain(crcnn_ctx *ctx, crcnn_tensor *t, int want_ntt) {
+    if (t->ntt == want_ntt) return CRCNN_OK;
+    int rc = ntt_inplace(ctx, t->d, t->count * t->size * ctx->K, 0, ctx->K, !want_ntt);
+    if (rc) return rc;
+    t->ntt = want_ntt;
+    return CRCNN_OK;
+}
+
+enum PlainForm { PF_NTT_MUL, PF_NTT_ADD, PF_COEF_ADD };
+
+int expand_range(crcnn_ctx *ctx, crcnn_plain *p, long first, long count, PlainForm f, uint64_t *dst) {
+    ProfScope ps(ctx, KC_PLAIN_EXPAND);
+    CU(launch_plain_expand(ctx->dP, ctx->logn, ctx->K, p->d_off, p->d_idx, p->d_val, first, count,
+                           f == PF_NTT_MUL ? 0 : 1, f != PF_COEF_ADD, dst, ctx->stream));
+    return CRCNN_OK;
+}
+
+// Materialise (and keep) a dense form of the whole pack.
+int ensure_form(crcnn_ctx *ctx, crcnn_plain *p, PlainForm f) {
+    uint64_t **slot = f == PF_NTT_MUL ? &p->ntt_mul : (f == PF_NTT_ADD ? &p->ntt_add : &p->coef_add);
+    if (*slot) return CRCNN_OK;
+    int rc = dev_alloc(ctx, (size_t)p->count * poly_words(ctx) * 8, (void **)slot);
+    if (rc) return rc;
+    return expand_range(ctx, p, 0, p->count, f, *slot);
+}
+
+int make_plain(crcnn_ctx *ctx, std::vector<uint32_t> &&off, std::vector<uint32_t> &&idx, std::vector<uint64_t> &&val,
+               crcnn_plain **out) {
+    auto *p = new crcnn_plain();
+    p->count = (long)off.size() - 1;
+    p->off = std::move(off); p->idx = std::move(idx); p->val = std::move(val);
+    int rc = dev_alloc(ctx, p->off.size() * 4, (void **)&p->d_off);
+    if (!rc) rc = dev_alloc(ctx, std::max<size_t>(p->idx.size(), 1) * 4, (void **)&p->d_idx);
+    if (!rc) rc = dev_alloc(ctx, std::max<size_t>(p->val.size(), 1) * 8, (void **)&p->d_val);
+    if (rc) { delete p; return rc; }
+    CU(cudaMemcpyAsync(p->d_off, p->off.data(), p->off.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    if (!p->idx.empty()) {
+        CU(cudaMemcpyAsync(p->d_idx, p->idx.data(), p->idx.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(p->d_val, p->val.data(), p->val.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));  // host vectors are pageable; make the staging explicit
+    *out = p;
+    return CRCNN_OK;
+}
+
+// Device copy of an index table, cached by content key.
+int get_index_table(crcnn_ctx *ctx, const std::vector<int> &key, const std::vector<int> &table, const int **out) {
+    auto it = ctx->index_cache.find(key);
+    if (it != ctx->index_cache.end()) { *out = it->second; return CRCNN_OK; }
+    int *d = nullptr;
+    CU(cudaMalloc((void **)&d, std::max<size_t>(table.size(), 1) * sizeof(int)));
+    CU(cudaMemcpyAsync(d, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->index_cache[key] = d;
+    *out = d;
+    return CRCNN_OK;
+}
+
+// Layer::computeBoundaries (CrCNN/src/layer.cpp:12-26)
+void boundaries(int xd, int yd, int xs, int ys, int xf, int yf, int *xl, int *yl) {
+    *xl = (xf > xs) ? xd - xf + 1 : xd - xs + 1;
+    *yl = (yf > ys) ? yd - yf + 1 : yd - ys + 1;
+}
+
+// Weighted-sum driver shared by conv and fc: M output channels [m_first, m_first+M) of Mall.
+int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
+                     int Npos, int Pimg, int Mall, int m_first, int M, crcnn_tensor *out) {
+    int rc = ensure_domain(ctx, in, 1);
+    if (rc) return rc;
+    rc = ensure_form(ctx, b, PF_NTT_ADD);
+    if (rc) return rc;
+    MacArgs a{};
+    a.x = in->d; a.in_index = d_index; a.out = out->d;
+    a.R = R; a.Npos = Npos; a.Pimg = Pimg; a.Mtotal = M; a.K = ctx->K; a.n = ctx->n;
+    a.chunk_terms = ctx->chunk_terms;
+    const size_t pw = poly_words(ctx);
+    const size_t all_bytes = (size_t)w->count * pw * 8;
+    if (w->ntt_mul || all_bytes <= ctx->weight_cache_bytes) {
+        rc = ensure_form(ctx, w, PF_NTT_MUL);  // first forward pays the transform, like the reference's lazy transform_kernel_to_ntt
+        if (rc) return rc;
+        a.w = w->ntt_mul + (size_t)m_first * R * pw;
+        a.bias = b->ntt_add + (size_t)m_first * pw;
+        a.M = M; a.m0 = 0;
+        ProfScope ps(ctx, KC_MAC);
+        CU(launch_mac(ctx->dP, a, ctx->stream));
+        return CRCNN_OK;
+    }
+    // weights do not fit: expand `rows` output rows at a time into a scratch buffer
+    long rows = (long)std::max<size_t>(1, ctx->weight_cache_bytes / ((size_t)R * pw * 8));
+    rows = std::min<long>(rows, M);
+    uint64_t *scratch = nullptr;
+    rc = dev_alloc(ctx, (size_t)rows * R * pw * 8, (void **)&scratch);
+    if (rc) return rc;
+    for (long m0 = 0; m0 < M; m0 += rows) {
+        long cur = std::min<long>(rows, M - m0);
+        rc = expand_range(ctx, w, (long)(m_first + m0) * R, cur * R, PF_NTT_MUL, scratch);
+        if (rc) break;
+        a.w = scratch; a.bias = b->ntt_add + (size_t)(m_first + m0) * pw;
+        a.M = (int)cur; a.m0 = (int)m0;
+        ProfScope ps(ctx, KC_MAC);
+        cudaError_t e = launch_mac(ctx->dP, a, ctx->stream);
+        if (e != cudaSuccess) { rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); break; }
+    }
+    dev_free(ctx, scratch);
+    return rc;
+}
+
+}  // namespace
+
+// ======================================================================================= C ABI
+extern "C" {
+
+const char *crcnn_last_error(const crcnn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, crcnn_ctx **out) {
+    crcnn_ctx *ctx = nullptr;  // errors before the context exists go to the thread-local slot
+    if (!out || !q) return fail(nullptr, CRCNN_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, CRCNN_ERR_NO_DEVICE, "no CUDA device: crcnn_b200 has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, CRCNN_ERR_INVALID_ARGUMENT, "bad device ordinal");
+    HostParams hp;
+    try {
+        hp = derive_params(n, K, q, t);
+    } catch (const std::exception &e) {
+        return fail(nullptr, CRCNN_ERR_INVALID_ARGUMENT, e.what());
+    }
+    CU(cudaSetDevice(device));
+    auto *c = new crcnn_ctx();
+    c->device = device; c->n = n; c->K = K; c->S = hp.d.S; c->logn = hp.d.logn;
+    int maxbits = 0;
+    for (int i = 0; i < K; i++) { int b = 0; for (uint64_t v = q[i]; v; v >>= 1) b++; maxbits = std::max(maxbits, b); }
+    int spare = 128 - 2 * maxbits;
+    c->chunk_terms = spare >= 30 ? (1 << 30) : (1 << spare);
+    // stream-ordered allocator: keep freed blocks cached
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    // upload tables
+    int slots = K + hp.d.S;
+    auto up = [&](const std::vector<uint64_t> &v, const uint64_t **dst) -> cudaError_t {
+        void *d = nullptr;
+        cudaError_t e = cudaMalloc(&d, v.size() * 8);
+        if (e != cudaSuccess) return e;
+        c->owned.push_back(d);
+        *dst = (const uint64_t *)d;
+        return cudaMemcpy(d, v.data(), v.size() * 8, cudaMemcpyHostToDevice);
+    };
+    cudaError_t e = cudaSuccess;
+    for (int s = 0; s < slots && e == cudaSuccess; s++) {
+        e = up(hp.w[s], &hp.d.tab[s].w);
+        if (e == cudaSuccess) e = up(hp.wp[s], &hp.d.tab[s].wp);
+        if (e == cudaSuccess) e = up(hp.iw[s], &hp.d.tab[s].iw);
+        if (e == cudaSuccess) e = up(hp.iwp[s], &hp.d.tab[s].iwp);
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->dP, sizeof(DeviceParams));
+    if (e == cudaSuccess) e = cudaMemcpy(c->dP, &hp.d, sizeof(DeviceParams), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        std::string m = cudaGetErrorString(e);
+        for (void *p : c->owned) cudaFree(p);
+        if (c->dP) cudaFree(c->dP);
+        delete c;
+        return fail(nullptr, CRCNN_ERR_CUDA, "context setup: " + m);
+    }
+    c->hp = std::move(hp);
+    *out = c;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_destroy(crcnn_ctx *ctx) {
+    if (!ctx) return CRCNN_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prof_collect(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
+    for (auto &kv : ctx->index_cache) cudaFree(kv.second);
+    for (void *p : ctx->owned) cudaFree(p);
+    cudaFree(ctx->dP);
+    delete ctx;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_set_stream(crcnn_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_sync(crcnn_ctx *ctx) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    CU(cudaStreamSynchronize(ctx->stream));
+    prof_collect(ctx);
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    ctx->weight_cache_bytes = bytes;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_ntt_table(const crcnn_ctx *ctx_c, int slot, int which, uint64_t *out) {
+    crcnn_ctx *ctx = const_cast<crcnn_ctx *>(ctx_c);
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(out && slot >= 0 && slot < ctx->K + ctx->S && which >= 0 && which < 4, "bad table selector");
+    const auto &v = which == 0 ? ctx->hp.w[slot] : which == 1 ? ctx->hp.wp[slot] : which == 2 ? ctx->hp.iw[slot] : ctx->hp.iwp[slot];
+    memcpy(out, v.data(), v.size() * 8);
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_bsk_count(const crcnn_ctx *ctx) { return ctx ? ctx->S : CRCNN_ERR_INVALID_ARGUMENT; }
+
+// ---------------------------------------------------------------------------- tensors
+int crcnn_tensor_upload_ex(crcnn_ctx *ctx, const uint64_t *host, long count, int size, int ntt_form, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(host && out && count >= 0 && size >= 2 && size <= 3, "bad tensor upload arguments");
+    CU(cudaSetDevice(ctx->device));
+    crcnn_tensor *t = nullptr;
+    int rc = new_tensor(ctx, count, size, ntt_form ? 1 : 0, &t);
+    if (rc) return rc;
+    const size_t n = ctx->n, rows = (size_t)count * size * ctx->K;
+    if (rows) CU(cudaMemcpy2DAsync(t->d, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, ctx->stream));
+    *out = t;
+    return CRCNN_OK;
+}
+int crcnn_tensor_upload(crcnn_ctx *ctx, const uint64_t *host, long count, int size, crcnn_tensor **out) {
+    return crcnn_tensor_upload_ex(ctx, host, count, size, 0, out);
+}
+
+int crcnn_tensor_download_ex(crcnn_ctx *ctx, crcnn_tensor *t, int want_ntt, uint64_t *host) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t && host, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n, rows = (size_t)t->count * t->size * ctx->K;
+    const uint64_t *src = t->d;
+    uint64_t *tmp = nullptr;
+    if ((t->ntt != 0) != (want_ntt != 0)) {  // convert a copy; the tensor itself keeps its domain
+        int rc = dev_alloc(ctx, rows * n * 8, (void **)&tmp);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(tmp, t->d, rows * n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        rc = ntt_inplace(ctx, tmp, (long)rows, 0, ctx->K, want_ntt == 0);
+        if (rc) return rc;
+        src = tmp;
+    }
+    if (rows) CU(cudaMemcpy2DAsync(host, (n + 1) * 8, src, n * 8, n * 8, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, tmp);
+    for (size_t r = 0; r < rows; r++) host[r * (n + 1) + n] = 0;  // SEAL's pad word
+    prof_collect(ctx);
+    return CRCNN_OK;
+}
+int crcnn_tensor_download(crcnn_ctx *ctx, crcnn_tensor *t, uint64_t *host) { return crcnn_tensor_download_ex(ctx, t, 0, host); }
+
+int crcnn_tensor_free(crcnn_ctx *ctx, crcnn_tensor *t) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (!t) return CRCNN_OK;
+    dev_free(ctx, t->d);
+    delete t;
+    return CRCNN_OK;
+}
+long crcnn_tensor_count(const crcnn_tensor *t) { return t ? t->count : -1; }
+int crcnn_tensor_ct_size(const crcnn_tensor *t) { return t ? t->size : -1; }
+
+int crcnn_tensor_slice(crcnn_ctx *ctx, crcnn_tensor *t, long first, long count, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t && out && first >= 0 && count >= 0 && first + count <= t->count, "slice out of range");
+    crcnn_tensor *s = nullptr;
+    int rc = new_tensor(ctx, count, t->size, t->ntt, &s);
+    if (rc) return rc;
+    size_t ctw = (size_t)t->size * poly_words(ctx);
+    if (count) CU(cudaMemcpyAsync(s->d, t->d + first * ctw, count * ctw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    *out = s;
+    return CRCNN_OK;
+}
+
+int crcnn_tensor_device_ptr(crcnn_tensor *t, void **dev_ptr, int *ntt_form) {
+    if (!t || !dev_ptr) return CRCNN_ERR_INVALID_ARGUMENT;
+    *dev_ptr = t->d;
+    if (ntt_form) *ntt_form = t->ntt;
+    return CRCNN_OK;
+}
+
+int crcnn_tensor_wrap_alloc(crcnn_ctx *ctx, long count, int size, int ntt_form, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(out && count >= 0 && size >= 2 && size <= 3, "bad tensor shape");
+    return new_tensor(ctx, count, size, ntt_form ? 1 : 0, out);
+}
+
+// ---------------------------------------------------------------------------- plaintext packs
+int crcnn_plain_upload(crcnn_ctx *ctx, const uint64_t *host, long count, int coeff_count, long stride, crcnn_plain **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(host && out && count >= 0 && coeff_count >= 0 && stride >= coeff_count, "bad plaintext upload arguments");
+    // SEAL rejects coeff_count > n+1, or == n+1 with a non-zero top coefficient (evaluator.cpp:1156-1159)
+    REQUIRE(coeff_count <= ctx->n + 1, "plain is not valid for encryption parameters");
+    std::vector<uint32_t> off(count + 1, 0), idx;
+    std::vector<uint64_t> val;
+    for (long i = 0; i < count; i++) {
+        const uint64_t *p = host + i * stride;
+        for (int c = 0; c < coeff_count; c++)
+            if (p[c]) {
+                REQUIRE(c < ctx->n, "plain is not valid for encryption parameters");
+                REQUIRE(p[c] < ctx->hp.d.t, "plaintext coefficient not below the plain modulus");
+                idx.push_back((uint32_t)c); val.push_back(p[c]);
+            }
+        off[i + 1] = (uint32_t)idx.size();
+    }
+    return make_plain(ctx, std::move(off), std::move(idx), std::move(val), out);
+}
+
+int crcnn_plain_upload_sparse(crcnn_ctx *ctx, const uint32_t *idx, const uint64_t *val, const uint32_t *offsets, long count,
+                              crcnn_plain **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(offsets && out && count >= 0, "bad sparse plaintext arguments");
+    std::vector<uint32_t> off(offsets, offsets + count + 1);
+    size_t nnz = off[count];
+    REQUIRE(nnz == 0 || (idx && val), "null sparse arrays");
+    std::vector<uint32_t> vi(idx, idx + nnz);
+    std::vector<uint64_t> vv(val, val + nnz);
+    for (size_t e = 0; e < nnz; e++) {
+        REQUIRE(vi[e] < (uint32_t)ctx->n, "plain is not valid for encryption parameters");
+        REQUIRE(vv[e] < ctx->hp.d.t, "plaintext coefficient not below the plain modulus");
+    }
+    return make_plain(ctx, std::move(off), std::move(vi), std::move(vv), out);
+}
+
+int crcnn_plain_encode(crcnn_ctx *ctx, const float *values, long count, crcnn_plain **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(values && out && count >= 0, "bad encode arguments");
+    std::vector<uint32_t> off(count + 1, 0), idx;
+    std::vector<uint64_t> val;
+    idx.reserve(count * 24); val.reserve(count * 24);
+    for (long i = 0; i < count; i++) {
+        encode_fractional_sparse((double)values[i], ctx->n, ctx->hp.d.t, idx, val);
+        off[i + 1] = (uint32_t)idx.size();
+    }
+    return make_plain(ctx, std::move(off), std::move(idx), std::move(val), out);
+}
+
+int crcnn_plain_get(crcnn_ctx *ctx, const crcnn_plain *p, long index, uint64_t *out_words) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(p && out_words && index >= 0 && index < p->count, "plaintext index out of range");
+    memset(out_words, 0, (size_t)(ctx->n + 1) * 8);
+    for (uint32_t e = p->off[index]; e < p->off[index + 1]; e++) out_words[p->idx[e]] = p->val[e];
+    return CRCNN_OK;
+}
+
+int crcnn_plain_get_ntt(crcnn_ctx *ctx, crcnn_plain *p, long index, uint64_t *out_words) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(p && out_words && index >= 0 && index < p->count, "plaintext index out of range");
+    uint64_t *tmp = nullptr;
+    int rc = dev_alloc(ctx, poly_words(ctx) * 8, (void **)&tmp);
+    if (rc) return rc;
+    rc = expand_range(ctx, p, index, 1, PF_NTT_MUL, tmp);
+    if (rc) return rc;
+    const size_t n = ctx->n;
+    CU(cudaMemcpy2DAsync(out_words, (n + 1) * 8, tmp, n * 8, n * 8, ctx->K, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, tmp);
+    for (int j = 0; j < ctx->K; j++) out_words[j * (n + 1) + n] = 0;
+    return CRCNN_OK;
+}
+
+int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (!p) return CRCNN_OK;
+    dev_free(ctx, p->d_off); dev_free(ctx, p->d_idx); dev_free(ctx, p->d_val);
+    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add);
+    delete p;
+    return CRCNN_OK;
+}
+long crcnn_plain_count(const crcnn_plain *p) { return p ? p->count : -1; }
+
+// ---------------------------------------------------------------------------- evaluation keys
+int crcnn_evk_upload(crcnn_ctx *ctx, const uint64_t *host, int dbc, const int *sizes, crcnn_evk **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(host && sizes && out && dbc >= 1 && dbc <= 60, "bad evaluation key arguments");
+    auto *k = new crcnn_evk();
+    k->dbc = dbc;
+    long polys = 0;
+    const size_t pw = poly_words(ctx);
+    for (int i = 0; i < MAXK; i++) { k->key_off[i] = 0; k->digits[i] = 0; }
+    for (int i = 0; i < ctx->K; i++) {
+        if (sizes[i] < 2 || (sizes[i] & 1)) { delete k; return fail(ctx, CRCNN_ERR_INVALID_ARGUMENT, "evaluation key sizes must be even and >= 2"); }
+        k->key_off[i] = polys * (long)pw;
+        k->digits[i] = sizes[i] / 2;
+        polys += sizes[i];
+    }
+    int rc = dev_alloc(ctx, (size_t)polys * pw * 8, (void **)&k->d);
+    if (rc) { delete k; return rc; }
+    const size_t n = ctx->n, rows = (size_t)polys * ctx->K;
+    CU(cudaMemcpy2DAsync(k->d, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_canonicalize(ctx->dP, k->d, (long)(rows * n), ctx->stream));
+    *out = k;
+    return CRCNN_OK;
+}
+int crcnn_evk_free(crcnn_ctx *ctx, crcnn_evk *k) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (!k) return CRCNN_OK;
+    dev_free(ctx, k->d);
+    delete k;
+    return CRCNN_OK;
+}
+
+// ---------------------------------------------------------------------------- layers
+int crcnn_conv_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd,
+                             int zd, int xs, int ys, int xf, int yf, int nf, int k0, int kc, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && w && b && out, "null argument");
+    REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && nf > 0 && xf <= xd && yf <= yd,
+            "bad convolution geometry");
+    REQUIRE(k0 >= 0 && kc > 0 && k0 + kc <= nf, "bad output-channel shard");
+    REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
+    const int R = zd * xf * yf;
+    REQUIRE(w->count == (long)nf * R && b->count == nf, "kernel/bias count does not match the layer geometry");  // convolutionalLayer.cpp:57-59
+    CU(cudaSetDevice(ctx->device));
+    const int xo = (xd - xf) / xs + 1, yo = (yd - yf) / ys + 1;  // convolutionalLayer.cpp:24
+    int xl, yl;
+    boundaries(xd, yd, xs, ys, xf, yf, &xl, &yl);
+    if ((xl + xs - 1) / xs != xo || (yl + ys - 1) / ys != yo)
+        return fail(ctx, CRCNN_ERR_UNSUPPORTED, "stride larger than the filter leaves outputs the reference never computes");
+    const int P = xo * yo, Npos = batch * P, nin = zd * xd * yd;
+    std::vector<int> key = {1, batch, xd, yd, zd, xs, ys, xf, yf};
+    const int *d_index = nullptr;
+    if (ctx->index_cache.find(key) == ctx->index_cache.end()) {
+        std::vector<int> table((size_t)Npos * R);
+        for (int bi = 0; bi < batch; bi++)
+            for (int i = 0; i < xo; i++)
+                for (int j = 0; j < yo; j++) {
+                    int *row = &table[((size_t)bi * P + i * yo + j) * R];
+                    int r = 0;
+                    for (int z = 0; z < zd; z++)
+                        for (int kx = 0; kx < xf; kx++)
+                            for (int ky = 0; ky < yf; ky++) row[r++] = bi * nin + (z * xd + i * xs + kx) * yd + j * ys + ky;
+                }
+        int rc = get_index_table(ctx, key, table, &d_index);
+        if (rc) return rc;
+    } else {
+        d_index = ctx->index_cache[key];
+    }
+    crcnn_tensor *o = nullptr;
+    int rc = new_tensor(ctx, (long)batch * kc * P, 2, 1, &o);
+    if (rc) return rc;
+    rc = run_weighted_sum(ctx, in, w, b, d_index, R, Npos, P, nf, k0, kc, o);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+    *out = o;
+    return CRCNN_OK;
+}
+
+int crcnn_conv_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
+                       int xs, int ys, int xf, int yf, int nf, crcnn_tensor **out) {
+    return crcnn_conv_forward_shard(ctx, in, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, 0, nf, out);
+}
+
+int crcnn_fc_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int in_dim,
+                           int out_dim, int o0, int oc, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && w && b && out, "null argument");
+    REQUIRE(batch > 0 && in_dim > 0 && out_dim > 0, "bad fully-connected geometry");
+    REQUIRE(o0 >= 0 && oc > 0 && o0 + oc <= out_dim, "bad output-row shard");
+    REQUIRE(in->size == 2 && in->count == (long)batch * in_dim, "input tensor does not match the layer geometry");
+    REQUIRE(w->count == (long)out_dim * in_dim && b->count == out_dim, "weight/bias count does not match the layer geometry");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int> key = {2, batch, in_dim};
+    const int *d_index = nullptr;
+    if (ctx->index_cache.find(key) == ctx->index_cache.end()) {
+        std::vector<int> table((size_t)batch * in_dim);
+        for (size_t i = 0; i < table.size(); i++) table[i] = (int)i;
+        int rc = get_index_table(ctx, key, table, &d_index);
+        if (rc) return rc;
+    } else {
+        d_index = ctx->index_cache[key];
+    }
+    crcnn_tensor *o = nullptr;
+    int rc = new_tensor(ctx, (long)batch * oc, 2, 1, &o);
+    if (rc) return rc;
+    rc = run_weighted_sum(ctx, in, w, b, d_index, in_dim, batch, 1, out_dim, o0, oc, o);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+    *out = o;
+    return CRCNN_OK;
+}
+
+int crcnn_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int in_dim, int out_dim,
+                     crcnn_tensor **out) {
+    return crcnn_fc_forward_shard(ctx, in, w, b, batch, in_dim, out_dim, 0, out_dim, out);
+}
+
+int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
+                       crcnn_plain *scale, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && out, "null argument");
+    REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && xf <= xd && yf <= yd, "bad pooling geometry");
+    REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
+    REQUIRE(!scale || scale->count >= 1, "empty scale pack");
+    CU(cudaSetDevice(ctx->device));
+    const int xo = (xd - xf) / xs + 1, yo = (yd - yf) / ys + 1;  // poolingLayer.cpp:18
+    int xl, yl;
+    boundaries(xd, yd, xs, ys, xf, yf, &xl, &yl);
+    if ((xl + xs - 1) / xs != xo || (yl + ys - 1) / ys != yo)
+        return fail(ctx, CRCNN_ERR_UNSUPPORTED, "stride larger than the window leaves outputs the reference never computes");
+    const int R = xf * yf, Nout = batch * zd * xo * yo;
+    std::vector<int> key = {3, batch, xd, yd, zd, xs, ys, xf, yf};
+    const int *d_index = nullptr;
+    if (ctx->index_cache.find(key) == ctx->index_cache.end()) {
+        std::vector<int> table((size_t)Nout * R);
+        size_t o = 0;
+        for (int bz = 0; bz < batch * zd; bz++)
+            for (int i = 0; i < xo; i++)
+                for (int j = 0; j < yo; j++)
+                    for (int kx = 0; kx < xf; kx++)
+                        for (int ky = 0; ky < yf; ky++) table[o++] = (bz * xd + i * xs + kx) * yd + j * ys + ky;
+        int rc = get_index_table(ctx, key, table, &d_index);
+        if (rc) return rc;
+    } else {
+        d_index = ctx->index_cache[key];
+    }
+    int rc = CRCNN_OK;
+    if (scale) {
+        rc = ensure_domain(ctx, in, 1);
+        if (!rc) rc = ensure_form(ctx, scale, PF_NTT_MUL);
+        if (rc) return rc;
+    }
+    crcnn_tensor *o = nullptr;
+    rc = new_tensor(ctx, Nout, 2, in->ntt, &o);
+    if (rc) return rc;
+    {
+        ProfScope ps(ctx, KC_POOL);
+        cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nout, R, scale ? scale->ntt_mul : nullptr, o->d, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = o;
+    return CRCNN_OK;
+}
+
+int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd, int yd, crcnn_plain *mean,
+                     crcnn_plain *invstd, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && mean && invstd && out, "null argument");
+    REQUIRE(batch > 0 && zd > 0 && xd > 0 && yd > 0, "bad batch-norm geometry");
+    REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
+    REQUIRE(mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_domain(ctx, in, 1);
+    if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
+    if (!rc) rc = ensure_form(ctx, invstd, PF_NTT_MUL);
+    if (rc) return rc;
+    crcnn_tensor *o = nullptr;
+    rc = new_tensor(ctx, in->count, 2, 1, &o);
+    if (rc) return rc;
+    {
+        ProfScope ps(ctx, KC_BN);
+        cudaError_t e = launch_bn(ctx->dP, ctx->n, ctx->K, in->d, in->count, xd * yd, zd, mean->ntt_add, invstd->ntt_mul, o->d, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = o;
+    return CRCNN_OK;
+}
+
+int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && out3, "null argument");
+    REQUIRE(in->size == 2, "square expects size-2 ciphertexts");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_domain(ctx, in, 0);
+    if (rc) return rc;
+    crcnn_tensor *o = nullptr;
+    rc = new_tensor(ctx, in->count, 3, 0, &o);
+    if (rc) return rc;
+    const int KS = ctx->K + ctx->S;
+    const size_t n = ctx->n, pw = poly_words(ctx);
+    // bound the scratch: chunks of at most `step` ciphertexts
+    const long step = std::max<long>(1, std::min<long>(in->count, (long)((2ull << 30) / (5 * (size_t)KS * n * 8))));
+    uint64_t *ext = nullptr, *prod = nullptr;
+    rc = dev_alloc(ctx, (size_t)step * 2 * KS * n * 8, (void **)&ext);
+    if (!rc) rc = dev_alloc(ctx, (size_t)step * 3 * KS * n * 8, (void **)&prod);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+    for (long c0 = 0; c0 < in->count && !rc; c0 += step) {
+        const long cur = std::min<long>(step, in->count - c0);
+        cudaError_t e;
+        { ProfScope ps(ctx, KC_BEHZ_LIFT); e = launch_behz_lift(ctx->dP, ctx->n, in->d + c0 * 2 * pw, cur, ext, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_FWD); e = launch_ntt(ctx->dP, ctx->logn, ext, cur * 2 * KS, 0, KS, false, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_SQ_TENSOR); e = launch_square_tensor(ctx->dP, ctx->n, KS, ext, cur, prod, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV); e = launch_ntt(ctx->dP, ctx->logn, prod, cur * 3 * KS, 0, KS, true, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_FLOOR); e = launch_behz_floor(ctx->dP, ctx->n, prod, cur, o->d + c0 * 3 * pw, ctx->stream); }
+        if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
+    }
+    dev_free(ctx, ext); dev_free(ctx, prod);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+    *out3 = o;
+    return CRCNN_OK;
+}
+
+int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_tensor **out2) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in3 && evk && out2, "null argument");
+    REQUIRE(in3->size == 3, "relinearize expects size-3 ciphertexts");
+    int total_digits = 0;
+    for (int i = 0; i < ctx->K; i++) {
+        int bits = 0; for (uint64_t v = ctx->hp.d.tab[i].mod.q; v; v >>= 1) bits++;
+        REQUIRE(evk->digits[i] * evk->dbc >= bits, "not enough evaluation keys");
+        total_digits += evk->digits[i];
+    }
+    REQUIRE(total_digits <= 63, "too many key digits for 128-bit lazy accumulation");  // evaluator.cpp:972-976
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_domain(ctx, in3, 0);
+    if (rc) return rc;
+    crcnn_tensor *o = nullptr;
+    rc = new_tensor(ctx, in3->count, 2, 0, &o);
+    if (rc) return rc;
+    RelinArgs a{};
+    a.in3 = in3->d; a.evk = evk->d; a.dbc = evk->dbc; a.out = o->d; a.count = in3->count;
+    for (int i = 0; i < MAXK; i++) { a.key_off[i] = evk->key_off[i]; a.digits[i] = evk->digits[i]; }
+    {
+        ProfScope ps(ctx, KC_RELIN);
+        cudaError_t e = launch_relin(ctx->dP, ctx->logn, ctx->K, a, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out2 = o;
+    return CRCNN_OK;
+}
+
+int crcnn_square_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_evk *evk, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    crcnn_tensor *t3 = nullptr;
+    int rc = crcnn_square(ctx, in, &t3);
+    if (rc) return rc;
+    rc = crcnn_relinearize(ctx, t3, evk, out);
+    crcnn_tensor_free(ctx, t3);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------- evaluator-level ops
+int crcnn_transform_to_ntt(crcnn_ctx *ctx, crcnn_tensor *t) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t, "null argument");
+    REQUIRE(!t->ntt, "tensor is already in NTT form");
+    CU(cudaSetDevice(ctx->device));
+    return ensure_domain(ctx, t, 1);
+}
+int crcnn_transform_from_ntt(crcnn_ctx *ctx, crcnn_tensor *t) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t, "null argument");
+    REQUIRE(t->ntt, "tensor is not in NTT form");
+    CU(cudaSetDevice(ctx->device));
+    return ensure_domain(ctx, t, 0);
+}
+
+int crcnn_plain_op(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_plain *p, long index, int op) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t && p && index >= 0 && index < p->count && op >= 0 && op <= 2, "bad plain_op arguments");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const uint64_t *pl;
+    if (op == 0) {
+        rc = ensure_domain(ctx, t, 1);
+        if (!rc) rc = ensure_form(ctx, p, PF_NTT_MUL);
+        if (rc) return rc;
+        pl = p->ntt_mul + index * poly_words(ctx);
+    } else {
+        rc = ensure_form(ctx, p, t->ntt ? PF_NTT_ADD : PF_COEF_ADD);
+        if (rc) return rc;
+        pl = (t->ntt ? p->ntt_add : p->coef_add) + index * poly_words(ctx);
+    }
+    ProfScope ps(ctx, KC_PLAIN_OP);
+    CU(launch_plain_op(ctx->dP, ctx->n, ctx->K, t->d, t->count, t->size, pl, op, ctx->stream));
+    return CRCNN_OK;
+}
+
+int crcnn_add_many(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t && out, "null argument");
+    REQUIRE(t->count >= 1, "encrypteds cannot be empty");  // evaluator.cpp:298-301
+    REQUIRE(t->size == 2, "add_many is implemented for size-2 ciphertexts");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<int> key = {4, (int)t->count};
+    const int *d_index = nullptr;
+    if (ctx->index_cache.find(key) == ctx->index_cache.end()) {
+        std::vector<int> table(t->count);
+        for (long i = 0; i < t->count; i++) table[i] = (int)i;
+        int rc = get_index_table(ctx, key, table, &d_index);
+        if (rc) return rc;
+    } else {
+        d_index = ctx->index_cache[key];
+    }
+    crcnn_tensor *o = nullptr;
+    int rc = new_tensor(ctx, 1, 2, t->ntt, &o);
+    if (rc) return rc;
+    ProfScope ps(ctx, KC_POOL);
+    cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, t->d, d_index, 1, (int)t->count, nullptr, o->d, ctx->stream);
+    if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = o;
+    return CRCNN_OK;
+}
+
+// ---------------------------------------------------------------------------- measurement
+int crcnn_prof_enable(crcnn_ctx *ctx, int on) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    ctx->prof_on = on != 0;
+    return CRCNN_OK;
+}
+int crcnn_prof_reset(crcnn_ctx *ctx) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    prof_collect(ctx);
+    for (int i = 0; i < KC_COUNT; i++) { ctx->launches[i] = 0; ctx->ms[i] = 0; }
+    return CRCNN_OK;
+}
+int crcnn_prof_count(crcnn_ctx *ctx) { return ctx ? KC_COUNT : CRCNN_ERR_INVALID_ARGUMENT; }
+int crcnn_prof_get(crcnn_ctx *ctx, int cls, char *name, long *launches, double *ms) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(cls >= 0 && cls < KC_COUNT, "bad kernel class");
+    prof_collect(ctx);
+    if (name) { strncpy(name, kClassNames[cls], 31); name[31] = 0; }
+    if (launches) *launches = ctx->launches[cls];
+    if (ms) *ms = ctx->ms[cls];
+    return CRCNN_OK;
+}
+
+int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && ms, "bad probe arguments");
+    CU(cudaSetDevice(ctx->device));
+    uint64_t *sink = nullptr;
+    int rc = dev_alloc(ctx, 8, (void **)&sink);
+    if (rc) return rc;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    ctx->launches[KC_PROBE]++;
+    CU(cudaEventRecord(a, ctx->stream));
+    CU(launch_imad_probe(blocks, threads, iters, sink, ctx->stream));
+    CU(cudaEventRecord(b, ctx->stream));
+    CU(cudaEventSynchronize(b));
+    float t = 0;
+    cudaEventElapsedTime(&t, a, b);
+    *ms = t;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    dev_free(ctx, sink);
+    return CRCNN_OK;
+}
+
+}  // extern "C"

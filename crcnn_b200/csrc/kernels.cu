@@ -1,0 +1,580 @@
+// Device kernels of the encrypted-forward hot path (sm_100a).  See kernels.cuh for the contracts.
+#include "kernels.cuh"
+#include "ntt.cuh"
+
+namespace crcnn {
+
+// =====================================================================================
+// NTT / inverse NTT of dense limb-polynomials
+// =====================================================================================
+template <int LOGN>
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS)
+ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count) {
+    extern __shared__ uint64_t sm[];
+    const long p = blockIdx.x;
+    const NttTable tb = P->tab[slot_base + (int)(p % slot_count)];
+    uint64_t *poly = data + p * (1L << LOGN);
+    ntt_forward_to_smem<LOGN>(sm, poly, tb);
+    smem_store_poly_canonical<LOGN>(sm, poly, tb.mod.q);
+}
+
+template <int LOGN>
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS)
+ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count) {
+    extern __shared__ uint64_t sm[];
+    const long p = blockIdx.x;
+    const NttTable tb = P->tab[slot_base + (int)(p % slot_count)];
+    uint64_t *poly = data + p * (1L << LOGN);
+    smem_load_poly<LOGN>(sm, poly);
+    __syncthreads();
+    ntt_inverse_from_smem<LOGN>(sm, poly, tb);
+}
+
+template <int LOGN>
+static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npolys, int slot_base, int slot_count,
+                                bool inverse, cudaStream_t stream) {
+    using Pl = NttPlan<LOGN>;
+    size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
+    auto kf = ntt_fwd_kernel<LOGN>;
+    auto ki = ntt_inv_kernel<LOGN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    if (npolys <= 0) return cudaSuccess;
+    if (inverse) ki<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count);
+    else kf<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
+                       bool inverse, cudaStream_t stream) {
+    switch (logn) {
+        case 10: return launch_ntt_t<10>(P, data, npolys, slot_base, slot_count, inverse, stream);
+        case 11: return launch_ntt_t<11>(P, data, npolys, slot_base, slot_count, inverse, stream);
+        case 12: return launch_ntt_t<12>(P, data, npolys, slot_base, slot_count, inverse, stream);
+        case 13: return launch_ntt_t<13>(P, data, npolys, slot_base, slot_count, inverse, stream);
+        case 14: return launch_ntt_t<14>(P, data, npolys, slot_base, slot_count, inverse, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// =====================================================================================
+// plaintext expansion: sparse (index, value<t) -> dense residues, optionally NTT form
+// =====================================================================================
+template <int LOGN>
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS)
+plain_expand_kernel(const DeviceParams *__restrict__ P, int K, const uint32_t *__restrict__ offsets,
+                    const uint32_t *__restrict__ idx, const uint64_t *__restrict__ val, long first, int mode,
+                    int to_ntt, uint64_t *__restrict__ out) {
+    extern __shared__ uint64_t sm[];
+    constexpr int N = 1 << LOGN;
+    const long b = blockIdx.x;
+    const long pi = b / K;
+    const int j = (int)(b % K);
+    const NttTable tb = P->tab[j];
+    const uint64_t half = P->half;
+    for (int i = threadIdx.x; i < NttPlan<LOGN>::SMEM_WORDS; i += blockDim.x) sm[i] = 0;
+    __syncthreads();
+    const uint32_t lo = offsets[first + pi], hi = offsets[first + pi + 1];
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+        uint64_t c = val[e], v;
+        if (mode == 0) {
+            v = c >= half ? c + P->lift_inc[j] : c;  // evaluator.cpp:1475-1484
+        } else {                                     // evaluator.cpp:1171-1190
+            U128 z = mul128(P->delta[j], c);
+            if (c >= half) add128_64(z, P->rho[j]);
+            v = barrett128(z, tb.mod);
+        }
+        sm[ntt_pad((int)idx[e])] = v;
+    }
+    __syncthreads();
+    uint64_t *dst = out + b * N;
+    if (to_ntt) {
+        ntt_forward_in_smem<LOGN>(sm, tb);
+        smem_store_poly_canonical<LOGN>(sm, dst, tb.mod.q);
+    } else {
+        for (int i = threadIdx.x; i < N; i += blockDim.x) dst[i] = sm[ntt_pad(i)];
+    }
+}
+
+template <int LOGN>
+static cudaError_t launch_plain_expand_t(const DeviceParams *P, int K, const uint32_t *offsets, const uint32_t *idx,
+                                         const uint64_t *val, long first, long count, int mode, bool to_ntt,
+                                         uint64_t *out, cudaStream_t stream) {
+    using Pl = NttPlan<LOGN>;
+    size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
+    auto k = plain_expand_kernel<LOGN>;
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    if (count <= 0) return cudaSuccess;
+    k<<<(unsigned)(count * K), Pl::THREADS, smem, stream>>>(P, K, offsets, idx, val, first, mode, to_ntt ? 1 : 0, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plain_expand(const DeviceParams *P, int logn, int K, const uint32_t *offsets, const uint32_t *idx,
+                                const uint64_t *val, long first, long count, int mode, bool to_ntt, uint64_t *out,
+                                cudaStream_t stream) {
+    switch (logn) {
+        case 10: return launch_plain_expand_t<10>(P, K, offsets, idx, val, first, count, mode, to_ntt, out, stream);
+        case 11: return launch_plain_expand_t<11>(P, K, offsets, idx, val, first, count, mode, to_ntt, out, stream);
+        case 12: return launch_plain_expand_t<12>(P, K, offsets, idx, val, first, count, mode, to_ntt, out, stream);
+        case 13: return launch_plain_expand_t<13>(P, K, offsets, idx, val, first, count, mode, to_ntt, out, stream);
+        case 14: return launch_plain_expand_t<14>(P, K, offsets, idx, val, first, count, mode, to_ntt, out, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// =====================================================================================
+// fused weighted sum: out[m][p] = sum_r x[in_index[p][r]] (.) w[m][r]  (+ bias[m] on poly 0)
+// One thread owns one residue column (limb j, coefficient c) of a TM x TN tile of outputs and
+// keeps 2*TM*TN 128-bit accumulators in registers; Barrett happens once per output (or once per
+// chunk_terms when the fan-in could overflow 128 bits).  Grid: x = output tiles (fastest, so the
+// CTAs resident together share one narrow coefficient slice of every input and weight -> L2 reuse),
+// y = coefficient slices of 128 residues.
+// =====================================================================================
+constexpr int MAC_THREADS = 128;
+
+template <int TM, int TN>
+__global__ void __launch_bounds__(MAC_THREADS)
+mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
+    extern __shared__ int s_idx[];  // [TN][R]
+    const int n = a.n, K = a.K, R = a.R;
+    const int slices_per_limb = n / MAC_THREADS;
+    const int j = blockIdx.y / slices_per_limb;
+    const int c = (blockIdx.y % slices_per_limb) * MAC_THREADS + threadIdx.x;
+    const int tiles_m = (a.M + TM - 1) / TM;
+    const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+    const int m_base = tm * TM, p_base = tn * TN;
+    const Mod mod = P->tab[j].mod;
+    const long limb_off = (long)j * n + c;
+    const long poly_words = (long)K * n;
+
+    for (int i = threadIdx.x; i < TN * R; i += MAC_THREADS) {
+        int t = i / R, r = i - t * R;
+        int p = min(p_base + t, a.Npos - 1);
+        s_idx[i] = a.in_index[(long)p * R + r];
+    }
+    __syncthreads();
+
+    U128 acc[TM][TN][2];
+#pragma unroll
+    for (int m = 0; m < TM; m++)
+#pragma unroll
+        for (int t = 0; t < TN; t++) { acc[m][t][0] = U128{0, 0}; acc[m][t][1] = U128{0, 0}; }
+
+    const uint64_t *wrow[TM];
+#pragma unroll
+    for (int m = 0; m < TM; m++) wrow[m] = a.w + (long)min(m_base + m, a.M - 1) * R * poly_words + limb_off;
+
+    for (int r0 = 0; r0 < R; r0 += a.chunk_terms) {
+        const int r1 = min(R, r0 + a.chunk_terms);
+#pragma unroll 2
+        for (int r = r0; r < r1; r++) {
+            uint64_t W[TM], X[TN][2];
+#pragma unroll
+            for (int m = 0; m < TM; m++) W[m] = __ldg(wrow[m] + (long)r * poly_words);
+#pragma unroll
+            for (int t = 0; t < TN; t++) {
+                const uint64_t *xp = a.x + (long)s_idx[t * R + r] * 2 * poly_words + limb_off;
+                X[t][0] = __ldg(xp);
+                X[t][1] = __ldg(xp + poly_words);
+            }
+#pragma unroll
+            for (int m = 0; m < TM; m++)
+#pragma unroll
+                for (int t = 0; t < TN; t++) {
+                    mac128(acc[m][t][0], X[t][0], W[m]);
+                    mac128(acc[m][t][1], X[t][1], W[m]);
+                }
+        }
+        if (r1 < R) {
+#pragma unroll
+            for (int m = 0; m < TM; m++)
+#pragma unroll
+                for (int t = 0; t < TN; t++) {
+                    acc[m][t][0] = U128{barrett128(acc[m][t][0], mod), 0};
+                    acc[m][t][1] = U128{barrett128(acc[m][t][1], mod), 0};
+                }
+        }
+    }
+
+#pragma unroll
+    for (int m = 0; m < TM; m++) {
+        if (m_base + m >= a.M) continue;
+#pragma unroll
+        for (int t = 0; t < TN; t++) {
+            const int p = p_base + t;
+            if (p >= a.Npos) continue;
+            uint64_t v0 = barrett128(acc[m][t][0], mod), v1 = barrett128(acc[m][t][1], mod);
+            if (a.bias) v0 = addmod(v0, __ldg(a.bias + (long)(m_base + m) * poly_words + limb_off), mod.q);
+            long oct = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + (long)(a.m0 + m_base + m) * a.Pimg + p % a.Pimg;
+            uint64_t *op = a.out + oct * 2 * poly_words + limb_off;
+            op[0] = v0;
+            op[poly_words] = v1;
+        }
+    }
+}
+
+template <int TM, int TN>
+static cudaError_t launch_mac_t(const DeviceParams *P, const MacArgs &a, cudaStream_t stream) {
+    dim3 grid(((a.M + TM - 1) / TM) * ((a.Npos + TN - 1) / TN), a.K * (a.n / MAC_THREADS));
+    size_t smem = (size_t)TN * a.R * sizeof(int);
+    auto k = mac_kernel<TM, TN>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, MAC_THREADS, smem, stream>>>(P, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t stream) {
+    if (a.M <= 0 || a.Npos <= 0) return cudaSuccess;
+    if (a.Npos == 1) return launch_mac_t<8, 1>(P, a, stream);
+    return launch_mac_t<4, 2>(P, a, stream);
+}
+
+// =====================================================================================
+// pooling (window sums, optional NTT-domain scale)
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, const int *__restrict__ in_index,
+            int R, const uint64_t *__restrict__ scale, uint64_t *__restrict__ out) {
+    const int n = P->n, K = P->K;
+    const long ctw = 2L * K * n;
+    const long o = blockIdx.x;
+    const long word = (long)blockIdx.y * 256 + threadIdx.x;  // within the ciphertext
+    const int j = (int)((word / n) % K);
+    const Mod mod = P->tab[j].mod;
+    U128 s{0, 0};
+    for (int r = 0; r < R; r++) add128_64(s, __ldg(in + (long)__ldg(in_index + o * R + r) * ctw + word));
+    uint64_t v = barrett128(s, mod);
+    if (scale) v = mulmod(v, __ldg(scale + (long)j * n + word % n), mod);
+    out[o * ctw + word] = v;
+}
+
+// =====================================================================================
+// batch-norm and evaluator-level plaintext ops
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+bn_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, int per_channel, int channels,
+          const uint64_t *__restrict__ mean, const uint64_t *__restrict__ invstd, uint64_t *__restrict__ out) {
+    const int n = P->n, K = P->K;
+    const long pw = (long)K * n, ctw = 2 * pw;
+    const long ct = blockIdx.x;
+    const long word = (long)blockIdx.y * 256 + threadIdx.x;
+    const int poly = (int)(word / pw);
+    const long lw = word - poly * pw;  // j*n + c
+    const int j = (int)(lw / n);
+    const int z = (int)((ct / per_channel) % channels);
+    const Mod mod = P->tab[j].mod;
+    uint64_t x = __ldg(in + ct * ctw + word);
+    if (poly == 0) x = submod(x, __ldg(mean + z * pw + lw), mod.q);
+    out[ct * ctw + word] = mulmod(x, __ldg(invstd + z * pw + lw), mod);
+}
+
+__global__ void __launch_bounds__(256)
+plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data, int size, const uint64_t *__restrict__ pl, int op) {
+    const int n = P->n, K = P->K;
+    const long pw = (long)K * n, ctw = size * pw;
+    const long ct = blockIdx.x;
+    const long word = (long)blockIdx.y * 256 + threadIdx.x;
+    if (word >= ctw) return;
+    const int poly = (int)(word / pw);
+    const long lw = word - poly * pw;
+    const int j = (int)(lw / n);
+    const Mod mod = P->tab[j].mod;
+    uint64_t *x = data + ct * ctw + word;
+    if (op == 0) *x = mulmod(*x, __ldg(pl + lw), mod);
+    else if (poly == 0) *x = (op == 1) ? addmod(*x, __ldg(pl + lw), mod.q) : submod(*x, __ldg(pl + lw), mod.q);
+}
+
+// =====================================================================================
+// BEHZ square pieces
+// =====================================================================================
+// q -> Bsk U {m_tilde} fast conversion followed by the Montgomery-style q-overflow removal
+// (baseconverter.cpp:663-742 then :581-622), one thread per coefficient.
+__global__ void __launch_bounds__(128)
+behz_lift_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, uint64_t *__restrict__ ext) {
+    const int n = P->n, K = P->K, S = P->S;
+    const int per = n / 128;
+    const long poly = blockIdx.x / per;  // ct*2 + p
+    const int c = (blockIdx.x % per) * 128 + threadIdx.x;
+    const uint64_t *src = in + poly * K * n + c;
+    uint64_t *dst = ext + poly * (K + S) * n + c;
+    uint64_t y[MAXK];
+    uint32_t zmt = 0;
+#pragma unroll
+    for (int i = 0; i < MAXK; i++) {
+        if (i < K) {
+            uint64_t x = __ldg(src + (long)i * n);
+            dst[(long)i * n] = x;
+            y[i] = mulmod(x, P->mt_inv_qhat[i], P->tab[i].mod);
+            zmt += (uint32_t)y[i] * (uint32_t)P->qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
+        }
+    }
+    const uint32_t r = zmt * (uint32_t)P->neg_inv_q_mod_mt;  // (-(z * q^-1)) mod 2^32, in [0, 2^32)
+    for (int k = 0; k < S; k++) {
+        const Mod mod = P->tab[K + k].mod;
+        U128 acc{0, 0};
+#pragma unroll
+        for (int i = 0; i < MAXK; i++)
+            if (i < K) mac128(acc, y[i], P->qhat_mod_bsk[k][i]);
+        uint64_t z = barrett128(acc, mod);
+        U128 t2 = mul128(P->q_mod_bsk[k], (uint64_t)r);
+        add128_64(t2, z);
+        uint64_t v = barrett128(t2, mod);
+        dst[(long)(K + k) * n] = mulmod(v, P->inv_mt_mod_bsk[k], mod);
+    }
+}
+
+// NTT-domain tensor square in both bases (evaluator.cpp:783-834)
+__global__ void __launch_bounds__(256)
+square_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ ext, uint64_t *__restrict__ prod) {
+    const int n = P->n, KS = P->K + P->S;
+    const long pw = (long)KS * n;
+    const long ct = blockIdx.x;
+    const long lw = (long)blockIdx.y * 256 + threadIdx.x;
+    if (lw >= pw) return;
+    const Mod mod = P->tab[lw / n].mod;
+    const uint64_t a = __ldg(ext + ct * 2 * pw + lw), b = __ldg(ext + ct * 2 * pw + pw + lw);
+    uint64_t *o = prod + ct * 3 * pw + lw;
+    o[0] = mulmod(a, a, mod);
+    uint64_t ab = mulmod(a, b, mod);
+    o[pw] = addmod(ab, ab, mod.q);
+    o[2 * pw] = mulmod(b, b, mod);
+}
+
+// multiply by t, fast_floor (q U Bsk -> Bsk), fastbconv_sk (Bsk -> q)
+// (evaluator.cpp:852-883, baseconverter.cpp:624-661, :448-579), one thread per coefficient.
+__global__ void __launch_bounds__(128)
+behz_floor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ prod, uint64_t *__restrict__ out) {
+    const int n = P->n, K = P->K, S = P->S, L = P->L;
+    const int per = n / 128;
+    const long poly = blockIdx.x / per;  // ct*3 + p
+    const int c = (blockIdx.x % per) * 128 + threadIdx.x;
+    const uint64_t *src = prod + poly * (K + S) * n + c;
+    uint64_t *dst = out + poly * K * n + c;
+    uint64_t u[MAXK], g[MAXS];
+#pragma unroll
+    for (int i = 0; i < MAXK; i++)
+        if (i < K) {
+            const Mod mod = P->tab[i].mod;
+            uint64_t xt = mulmod(__ldg(src + (long)i * n), P->t_mod[i], mod);
+            u[i] = mulmod(xt, P->inv_qhat[i], mod);
+        }
+    uint64_t f_sk = 0;
+#pragma unroll
+    for (int k = 0; k < MAXS; k++)
+        if (k < S) {
+            const Mod mod = P->tab[K + k].mod;
+            U128 acc{0, 0};
+#pragma unroll
+            for (int i = 0; i < MAXK; i++)
+                if (i < K) mac128(acc, u[i], P->qhat_mod_bsk[k][i]);
+            uint64_t v = barrett128(acc, mod);
+            uint64_t xt = mulmod(__ldg(src + (long)(K + k) * n), P->t_mod[K + k], mod);
+            uint64_t f = mulmod(xt + mod.q - v, P->inv_q_mod_bsk[k], mod);
+            if (k < L) g[k] = mulmod(f, P->inv_Mhat[k], mod); else f_sk = f;
+        }
+    const Mod msk = P->tab[K + L].mod;
+    U128 acc{0, 0};
+#pragma unroll
+    for (int i = 0; i < MAXS; i++)
+        if (i < L) mac128(acc, g[i], P->Mhat_mod_msk[i]);
+    uint64_t s = barrett128(acc, msk);
+    uint64_t alpha = mulmod(s + (msk.q - f_sk), P->inv_M_mod_msk, msk);
+    const bool centered_neg = alpha > (msk.q >> 1);
+    for (int j = 0; j < K; j++) {
+        const Mod mod = P->tab[j].mod;
+        U128 e{0, 0};
+#pragma unroll
+        for (int i = 0; i < MAXS; i++)
+            if (i < L) mac128(e, g[i], P->Mhat_mod_q[j][i]);
+        uint64_t ev = barrett128(e, mod);
+        U128 corr = centered_neg ? mul128(P->M_mod_q[j], msk.q - alpha) : mul128(P->neg_M_mod_q[j], alpha);
+        add128_64(corr, ev);
+        dst[(long)j * n] = barrett128(corr, mod);
+    }
+}
+
+// =====================================================================================
+// relinearize: digit decomposition x NTT-form keys, accumulated in registers
+// One CTA per (ciphertext, output limb j, output poly).  For every (prime i, digit k) the digit
+// polynomial is built in shared memory, transformed mod q_j there, and multiplied into 128-bit
+// register accumulators against the key polynomial; then one Barrett, one inverse NTT in shared
+// memory and the addition to c0 / c1.
+// =====================================================================================
+template <int LOGN, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+relin_kernel(const DeviceParams *__restrict__ P, RelinArgs a) {
+    extern __shared__ uint64_t sm[];
+    constexpr int N = 1 << LOGN;
+    constexpr int EPT = N / THREADS;
+    const int K = P->K;
+    const long ct = blockIdx.x;
+    const int j = blockIdx.y, poly = blockIdx.z;
+    const NttTable tb = P->tab[j];
+    const long pw = (long)K * N;
+    const uint64_t *c2 = a.in3 + (ct * 3 + 2) * pw;
+    const uint64_t mask = (1ULL << a.dbc) - 1;
+
+    U128 acc[EPT];
+#pragma unroll
+    for (int u = 0; u < EPT; u++) acc[u] = U128{0, 0};
+
+    for (int i = 0; i < K; i++) {
+        const Mod mi = P->tab[i].mod;
+        const uint64_t inv = P->inv_qhat[i];
+        for (int k = 0; k < a.digits[i]; k++) {
+            const int shift = a.dbc * k;
+#pragma unroll
+            for (int u = 0; u < EPT; u++) {
+                int e = threadIdx.x + u * THREADS;
+                uint64_t d = mulmod(__ldg(c2 + (long)i * N + e), inv, mi);  // evaluator.cpp:984-985
+                sm[ntt_pad(e)] = (d >> shift) & mask;                       // evaluator.cpp:997-1001
+            }
+            __syncthreads();
+            ntt_forward_in_smem<LOGN>(sm, tb);  // lazy [0,4q), ends with a barrier
+            const uint64_t *key = a.evk + a.key_off[i] + (long)(2 * k + poly) * pw + (long)j * N;
+#pragma unroll
+            for (int u = 0; u < EPT; u++) {
+                int e = threadIdx.x + u * THREADS;
+                mac128(acc[u], sm[ntt_pad(e)], __ldg(key + e));
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EPT; u++) sm[ntt_pad(threadIdx.x + u * THREADS)] = barrett128(acc[u], tb.mod);
+    __syncthreads();
+    ntt_inverse_in_smem<LOGN>(sm, tb);  // [0,2q), ends with a barrier
+    const uint64_t *cin = a.in3 + (ct * 3 + poly) * pw + (long)j * N;
+    uint64_t *cout = a.out + (ct * 2 + poly) * pw + (long)j * N;
+#pragma unroll
+    for (int u = 0; u < EPT; u++) {
+        int e = threadIdx.x + u * THREADS;
+        uint64_t v = sm[ntt_pad(e)];
+        v = v >= tb.mod.q ? v - tb.mod.q : v;
+        cout[e] = addmod(__ldg(cin + e), v, tb.mod.q);
+    }
+}
+
+template <int LOGN, int THREADS>
+static cudaError_t launch_relin_t(const DeviceParams *P, const RelinArgs &a, int K, cudaStream_t stream) {
+    size_t smem = NttPlan<LOGN>::SMEM_WORDS * sizeof(uint64_t);
+    auto k = relin_kernel<LOGN, THREADS>;
+    static bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    if (a.count <= 0) return cudaSuccess;
+    dim3 grid((unsigned)a.count, K, 2);
+    k<<<grid, THREADS, smem, stream>>>(P, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relin(const DeviceParams *P, int logn, int K, const RelinArgs &a, cudaStream_t stream) {
+    switch (logn) {
+        case 10: return launch_relin_t<10, 128>(P, a, K, stream);
+        case 11: return launch_relin_t<11, 256>(P, a, K, stream);
+        case 12: return launch_relin_t<12, 512>(P, a, K, stream);
+        case 13: return launch_relin_t<13, 1024>(P, a, K, stream);
+        case 14: return launch_relin_t<14, 1024>(P, a, K, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// =====================================================================================
+// simple launch wrappers
+// =====================================================================================
+cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout,
+                           int R, const uint64_t *scale_ntt, uint64_t *out, cudaStream_t stream) {
+    if (Nout <= 0) return cudaSuccess;
+    dim3 grid(Nout, (unsigned)(2L * K * n / 256));
+    pool_kernel<<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, long count, int per_channel,
+                         int channels, const uint64_t *mean_ntt, const uint64_t *invstd_ntt, uint64_t *out,
+                         cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    dim3 grid((unsigned)count, (unsigned)(2L * K * n / 256));
+    bn_kernel<<<grid, 256, 0, stream>>>(P, in, per_channel, channels, mean_ntt, invstd_ntt, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data, long count, int size,
+                               const uint64_t *pl, int op, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    dim3 grid((unsigned)count, (unsigned)(((long)size * K * n + 255) / 256));
+    plain_op_kernel<<<grid, 256, 0, stream>>>(P, data, size, pl, op);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_behz_lift(const DeviceParams *P, int n, const uint64_t *in, long count, uint64_t *ext,
+                                cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    behz_lift_kernel<<<(unsigned)(count * 2 * (n / 128)), 128, 0, stream>>>(P, in, ext);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uint64_t *ext, long count,
+                                    uint64_t *prod, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    dim3 grid((unsigned)count, (unsigned)(((long)KS * n + 255) / 256));
+    square_tensor_kernel<<<grid, 256, 0, stream>>>(P, ext, prod);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_behz_floor(const DeviceParams *P, int n, const uint64_t *prod, long count, uint64_t *out,
+                                 cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    behz_floor_kernel<<<(unsigned)(count * 3 * (n / 128)), 128, 0, stream>>>(P, prod, out);
+    return cudaGetLastError();
+}
+
+// Reduce lazily stored residues (< 4q, as SEAL keeps the "second" evaluation-key polys,
+// keygenerator.cpp:238-247) to canonical form once at upload.
+__global__ void __launch_bounds__(256)
+canonicalize_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data, long words) {
+    const long w = (long)blockIdx.x * 256 + threadIdx.x;
+    if (w >= words) return;
+    const int n = P->n, K = P->K;
+    const uint64_t q = P->tab[(w / n) % K].mod.q;
+    uint64_t v = data[w];
+    v = v >= 2 * q ? v - 2 * q : v;
+    data[w] = v >= q ? v - q : v;
+}
+
+cudaError_t launch_canonicalize(const DeviceParams *P, uint64_t *data, long words, cudaStream_t stream) {
+    if (words <= 0) return cudaSuccess;
+    canonicalize_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(P, data, words);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// integer-pipe probe: 8 independent 64x64->128 multiply-accumulate chains per thread
+// =====================================================================================
+__global__ void imad_probe_kernel(int iters, uint64_t *sink) {
+    uint64_t a = 0x9E3779B97F4A7C15ULL * (threadIdx.x + 1), b = 0xD1B54A32D192ED03ULL + blockIdx.x;
+    U128 acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = U128{(uint64_t)i, 0};
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) mac128(acc[i], a + i, b);
+        a += acc[0].hi;
+        b ^= acc[7].lo;
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i].lo ^ acc[i].hi;
+    if (s == 0x1234567) sink[0] = s;
+}
+
+cudaError_t launch_imad_probe(int blocks, int threads, int iters, uint64_t *sink, cudaStream_t stream) {
+    imad_probe_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
+}
+
+}  // namespace crcnn

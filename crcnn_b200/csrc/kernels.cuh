@@ -1,0 +1,79 @@
+// Launch wrappers for every device kernel of the encrypted-forward hot path.  All pointers are
+// device pointers; limb-polynomials are dense (stride n, no SEAL pad word).  Ciphertext tensors are
+// uint64[count][size][K][n].  Every wrapper enqueues on `stream` and returns the launch error.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "params.h"
+
+namespace crcnn {
+
+// ---- NTT over `npolys` limb-polynomials; polynomial p uses modulus slot slot_base + p % slot_count.
+cudaError_t launch_ntt(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
+                       bool inverse, cudaStream_t stream);
+
+// ---- plaintext packs: sparse coefficient form -> dense NTT form, one CTA per (plaintext, limb).
+// mode 0: lifted residues (multiplicative use: weights, scale factors)  [evaluator.cpp:1465-1486]
+// mode 1: Delta-scaled residues (additive use: biases, means)           [evaluator.cpp:1169-1191]
+cudaError_t launch_plain_expand(const DeviceParams *P, int logn, int K, const uint32_t *offsets, const uint32_t *idx,
+                                const uint64_t *val, long first, long count, int mode, bool to_ntt, uint64_t *out,
+                                cudaStream_t stream);
+
+// ---- fused weighted sum (conv / fully connected), NTT domain.
+struct MacArgs {
+    const uint64_t *x;       // inputs  [num_in][2][K][n] (NTT form)
+    const uint64_t *w;       // weights [M][R][K][n]      (NTT form, lifted)
+    const uint64_t *bias;    // [M][K][n] NTT of Delta-scaled bias, added to poly 0 (may be null)
+    const int *in_index;     // [Npos][R] input ciphertext index for output position p, term r
+    uint64_t *out;           // output ct index = (p / Pimg) * (Mtotal * Pimg) + (m0 + m) * Pimg + p % Pimg
+    int R, M, Npos, Pimg, Mtotal, m0;
+    int K, n;
+    int chunk_terms;         // terms that may be accumulated in 128 bits before a reduction
+};
+cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t stream);
+
+// ---- window sum (sum-pool / avg-pool): out[o] = (sum_r in[in_index[o][r]]) (* scale[K][n] if given)
+cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout, int R,
+                        const uint64_t *scale_ntt, uint64_t *out, cudaStream_t stream);
+
+// ---- batch-norm, NTT domain: c0' = (c0 - mean_ntt[z]) * invstd_ntt[z], c1' = c1 * invstd_ntt[z]
+// ciphertext i belongs to channel (i / per_channel) % channels.
+cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, long count, int per_channel, int channels,
+                      const uint64_t *mean_ntt, const uint64_t *invstd_ntt, uint64_t *out, cudaStream_t stream);
+
+// ---- generic plaintext ops on `count` ciphertexts of `size` polys (evaluator-level API)
+// op 0: every poly *= pl (pl in NTT lifted form, data in NTT form); op 1/2: poly0 +=/-= pl (scaled form,
+// same domain as data)
+cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data, long count, int size, const uint64_t *pl, int op,
+                            cudaStream_t stream);
+
+// ---- FV square (BEHZ), staged exactly as evaluator.cpp:742-883
+// lift:   in [count][2][K][n] (coefficient form) -> ext [count][2][K+S][n] (q limbs copied, Bsk limbs computed)
+cudaError_t launch_behz_lift(const DeviceParams *P, int n, const uint64_t *in, long count, uint64_t *ext, cudaStream_t stream);
+// tensor: ext (NTT form) -> prod [count][3][K+S][n] (NTT form): c0^2, 2 c0 c1, c1^2
+cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uint64_t *ext, long count, uint64_t *prod, cudaStream_t stream);
+// floor:  prod (coefficient form) -> out [count][3][K][n]: multiply by t, fast_floor, fastbconv_sk
+cudaError_t launch_behz_floor(const DeviceParams *P, int n, const uint64_t *prod, long count, uint64_t *out, cudaStream_t stream);
+
+// ---- relinearize 3 -> 2 with 16-bit digits (evaluator.cpp:934-1069)
+// in3 [count][3][K][n] (coefficient), keys: for prime i, digit k: polys (2k, 2k+1) at
+// evk + key_off[i] + (2k)*K*n, each [K][n] NTT form;  out [count][2][K][n] coefficient form.
+struct RelinArgs {
+    const uint64_t *in3;
+    const uint64_t *evk;
+    long key_off[MAXK];
+    int digits[MAXK];
+    int dbc;
+    uint64_t *out;
+    long count;
+};
+cudaError_t launch_relin(const DeviceParams *P, int logn, int K, const RelinArgs &a, cudaStream_t stream);
+
+// ---- residues stored lazily in [0,4q) (evaluation keys) -> canonical, in place; data = [..][K][n]
+cudaError_t launch_canonicalize(const DeviceParams *P, uint64_t *data, long words, cudaStream_t stream);
+
+// ---- integer-pipe roofline probe: register-only 64x64->128 multiply-accumulate loop.
+// Returns nothing; caller times it.  total MACs = blocks * threads * iters * 8.
+cudaError_t launch_imad_probe(int blocks, int threads, int iters, uint64_t *sink, cudaStream_t stream);
+
+}  // namespace crcnn

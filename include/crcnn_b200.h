@@ -1,0 +1,175 @@
+/* crcnn_b200 -- C ABI of the B200-native engine for CrCNN's encrypted-inference forward pass.
+ *
+ * The reference (barlettacarmen/CrCNN) has no FFI: its hot path sits behind the virtual
+ * Layer::forward(ciphertext3D) (CrCNN/src/layer.h:20) and a process-global seal::Evaluator
+ * (CrCNN/src/globals.h:23).  This header is the boundary a drop-in replacement binds instead of
+ * that Evaluator; each entry point names the reference interface it replaces.  INTEGRATION.md
+ * shows the reference-side binding (the C++17 layer classes in crcnn_b200/cpp/ are that binding).
+ *
+ * Conventions
+ *  - extern "C", opaque handles, plain pointers and sizes; every call returns 0 on success or a
+ *    negative crcnn_status; crcnn_last_error() gives the message.  No exceptions cross the ABI.
+ *  - Host buffers use SEAL 2.3.1's in-memory layout (SEAL/seal/ciphertext.h:448-452, :647-660):
+ *      ciphertext = uint64[size][K][n+1]  (limb stride n+1, trailing pad word 0)
+ *      plaintext  = uint64[coeff_count], values < t
+ *      NTT-form plaintext / evaluation-key polys = uint64[K][n+1]
+ *    Device buffers are re-strided to n on upload and re-padded (pad = 0) on download.
+ *  - A context is bound to one GPU and one CUDA stream; calls on one context must be serialised by
+ *    the caller, different contexts are independent.  Forward calls never change the value of their
+ *    inputs (the reference transforms the caller's copy and the layer's weights in place,
+ *    CrCNN/src/convolutionalLayer.cpp:113,155).
+ *  - All results are canonical residues and bit-identical to SEAL 2.3.1's Evaluator for the same
+ *    inputs.  There is no CPU fallback: without a CUDA device crcnn_ctx_create fails.
+ */
+#ifndef CRCNN_B200_H
+#define CRCNN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct crcnn_ctx crcnn_ctx;
+typedef struct crcnn_tensor crcnn_tensor; /* device tensor of ciphertexts */
+typedef struct crcnn_plain crcnn_plain;   /* device pack of plaintexts (weights, biases, scale factors) */
+typedef struct crcnn_evk crcnn_evk;       /* device copy of evaluation (relinearisation) keys */
+
+typedef enum {
+    CRCNN_OK = 0,
+    CRCNN_ERR_INVALID_ARGUMENT = -1, /* what SEAL reports as std::invalid_argument */
+    CRCNN_ERR_CUDA = -2,
+    CRCNN_ERR_NO_DEVICE = -3,
+    CRCNN_ERR_OUT_OF_MEMORY = -4,
+    CRCNN_ERR_UNSUPPORTED = -5
+} crcnn_status;
+
+/* Message for the most recent failing call on `ctx` (or, with ctx == NULL, for the most recent
+ * failing crcnn_ctx_create on this thread). */
+const char *crcnn_last_error(const crcnn_ctx *ctx);
+
+/* ---- context ---------------------------------------------------------------------------
+ * Replaces: setParameters (CrCNN/src/globals.cpp:25-56) as far as the Evaluator is concerned:
+ * SEALContext + Evaluator + BaseConverter + SmallNTTTables constant derivation
+ * (SEAL/seal/context.cpp:23-165, evaluator.cpp:19-121, util/baseconverter.cpp:20-349).
+ * n: power of two in [1024,16384]; q[K]: distinct NTT primes (= 1 mod 2n), <= 60 bits, K <= 8;
+ * t: plain modulus, t < every q_i.  device: CUDA ordinal. */
+int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, crcnn_ctx **out);
+int crcnn_ctx_destroy(crcnn_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL selects the legacy default stream. */
+int crcnn_ctx_set_stream(crcnn_ctx *ctx, void *cuda_stream);
+int crcnn_ctx_sync(crcnn_ctx *ctx);
+/* Upper bound (bytes) for NTT-form weights kept resident per plaintext pack; larger packs are
+ * expanded chunk by chunk into a scratch buffer during forward.  Default 24 GiB. */
+int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes);
+/* Derived constants, for cross-checking against SEAL: which = 0 root_powers, 1 scaled_root_powers,
+ * 2 inv_root_powers_div_two, 3 scaled_inv_root_powers_div_two (SEAL/seal/util/smallntt.cpp:37-92);
+ * slot in [0,K) = coefficient primes, [K,K+S) = Bsk primes.  out has n words. */
+int crcnn_ctx_ntt_table(const crcnn_ctx *ctx, int slot, int which, uint64_t *out);
+int crcnn_ctx_bsk_count(const crcnn_ctx *ctx);
+
+/* ---- ciphertext tensors ------------------------------------------------------------------
+ * Replaces: the ciphertext3D by-value hand-off between layers (CrCNN/src/globals.h:10). */
+int crcnn_tensor_upload(crcnn_ctx *ctx, const uint64_t *host_words, long count, int ct_size, crcnn_tensor **out);
+/* ntt_form != 0: the host data is already in NTT form (as after Evaluator::transform_to_ntt). */
+int crcnn_tensor_upload_ex(crcnn_ctx *ctx, const uint64_t *host_words, long count, int ct_size, int ntt_form,
+                           crcnn_tensor **out);
+/* Always delivers coefficient form unless want_ntt_form != 0. Blocks until the copy has finished. */
+int crcnn_tensor_download(crcnn_ctx *ctx, crcnn_tensor *t, uint64_t *host_words);
+int crcnn_tensor_download_ex(crcnn_ctx *ctx, crcnn_tensor *t, int want_ntt_form, uint64_t *host_words);
+int crcnn_tensor_free(crcnn_ctx *ctx, crcnn_tensor *t);
+long crcnn_tensor_count(const crcnn_tensor *t);
+int crcnn_tensor_ct_size(const crcnn_tensor *t);
+/* New tensor holding ciphertexts [first, first+count) of t (device copy). */
+int crcnn_tensor_slice(crcnn_ctx *ctx, crcnn_tensor *t, long first, long count, crcnn_tensor **out);
+/* Raw device pointer (uint64[count][size][K][n]) and domain flag (0 coefficient, 1 NTT), for
+ * collectives over NVLink done by the caller (NCCL all-gather of activations). */
+int crcnn_tensor_device_ptr(crcnn_tensor *t, void **dev_ptr, int *ntt_form);
+int crcnn_tensor_wrap_alloc(crcnn_ctx *ctx, long count, int ct_size, int ntt_form, crcnn_tensor **out);
+
+/* ---- plaintext packs ----------------------------------------------------------------------
+ * Replaces: plaintext2D/plaintext4D weights + vector<Plaintext> biases held by the layers
+ * (CrCNN/src/convolutionalLayer.h:30-31, fullyConnectedLayer.h:19-20) and their lazy
+ * Evaluator::transform_to_ntt(Plaintext&) (SEAL/seal/evaluator.cpp:1418-1493). */
+/* `count` plaintexts, each `stride` words apart, of which the first coeff_count are significant. */
+int crcnn_plain_upload(crcnn_ctx *ctx, const uint64_t *host_words, long count, int coeff_count, long stride,
+                       crcnn_plain **out);
+/* Sparse form: plaintext i has coefficients (idx[e], val[e]) for e in [offsets[i], offsets[i+1]). */
+int crcnn_plain_upload_sparse(crcnn_ctx *ctx, const uint32_t *idx, const uint64_t *val, const uint32_t *offsets,
+                              long count, crcnn_plain **out);
+/* Encode floats exactly as CnnBuilder does: FractionalEncoder(t, x^n+1, 64, 32, base 3).encode(v)
+ * (CrCNN/src/cnnBuilder.cpp:25-105, CrCNN/src/globals.cpp:52) -- SURVEY 8(f) row N1. */
+int crcnn_plain_encode(crcnn_ctx *ctx, const float *values, long count, crcnn_plain **out);
+/* Coefficient-form words of plaintext `index` (n+1 words, zero padded) -- for parity checks. */
+int crcnn_plain_get(crcnn_ctx *ctx, const crcnn_plain *p, long index, uint64_t *out_words);
+int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p);
+long crcnn_plain_count(const crcnn_plain *p);
+
+/* ---- evaluation keys -----------------------------------------------------------------------
+ * Replaces: EvaluationKeys *ev_keys16 (CrCNN/src/globals.h:27).  host_words = keys_[0][i] back to
+ * back for i in [0,K), each a ciphertext of sizes[i] polys in SEAL layout [sizes[i]][K][n+1]
+ * (SEAL/seal/keygenerator.cpp:198-215, 652-702); dbc = decomposition bit count. */
+int crcnn_evk_upload(crcnn_ctx *ctx, const uint64_t *host_words, int dbc, const int *sizes, crcnn_evk **out);
+int crcnn_evk_free(crcnn_ctx *ctx, crcnn_evk *k);
+
+/* ---- layers --------------------------------------------------------------------------------
+ * Tensors are [batch][z][x][y] ciphertexts of size 2 (batch independent images; the reference
+ * processes one image per forward call, i.e. batch = 1).  Each call returns a new tensor. */
+
+/* Replaces ConvolutionalLayer::forward (CrCNN/src/convolutionalLayer.cpp:159-197, :56-93).
+ * weights: nf*zd*xf*yf plaintexts in [nf][zd][xf][yf] order; biases: nf plaintexts. */
+int crcnn_conv_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *weights, crcnn_plain *biases, int batch,
+                       int xd, int yd, int zd, int xs, int ys, int xf, int yf, int nf, crcnn_tensor **out);
+/* As above for output channels [k0, k0+kc) only (output-neuron sharding across GPUs). */
+int crcnn_conv_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *weights, crcnn_plain *biases, int batch,
+                             int xd, int yd, int zd, int xs, int ys, int xf, int yf, int nf, int k0, int kc,
+                             crcnn_tensor **out);
+/* Replaces FullyConnectedLayer::forward (CrCNN/src/fullyConnectedLayer.cpp:113-168); the input is
+ * the row-major flattening reshapeInput produces (:38-56).  weights [out_dim][in_dim]. */
+int crcnn_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *weights, crcnn_plain *biases, int batch,
+                     int in_dim, int out_dim, crcnn_tensor **out);
+int crcnn_fc_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *weights, crcnn_plain *biases, int batch,
+                           int in_dim, int out_dim, int o0, int oc, crcnn_tensor **out);
+/* Replaces PoolingLayer::forward (scale == NULL, CrCNN/src/poolingLayer.cpp:22-44) and
+ * AvgPoolingLayer::forward (scale = pack holding encode(1/(xf*yf)), CrCNN/src/avgPoolingLayer.cpp:16-45). */
+int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf,
+                       int yf, crcnn_plain *scale, crcnn_tensor **out);
+/* Replaces BatchNormLayer::forward (CrCNN/src/batchNormLayer.cpp:29-40): sub_plain(mean[z]) then
+ * multiply_plain(invstd[z]). */
+int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd, int yd, crcnn_plain *mean,
+                     crcnn_plain *invstd, crcnn_tensor **out);
+/* Replaces SquareLayer::forward (CrCNN/src/squareLayer.cpp:22-71): Evaluator::square + relinearize. */
+int crcnn_square_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_evk *evk, crcnn_tensor **out);
+
+/* ---- Evaluator-level operations (parity tests and the kernel sweep) --------------------------- */
+/* Evaluator::transform_to_ntt / transform_from_ntt (SEAL/seal/evaluator.cpp:1495-1539); in place. */
+int crcnn_transform_to_ntt(crcnn_ctx *ctx, crcnn_tensor *t);
+int crcnn_transform_from_ntt(crcnn_ctx *ctx, crcnn_tensor *t);
+/* Evaluator::transform_to_ntt(Plaintext&): K*(n+1) words of plaintext `index` in SEAL NTT form. */
+int crcnn_plain_get_ntt(crcnn_ctx *ctx, crcnn_plain *p, long index, uint64_t *out_words);
+/* op 0: Evaluator::multiply_plain (SEAL/seal/evaluator.cpp:1243-1416; also multiply_plain_ntt :1541-1585),
+ * op 1: add_plain (:1145-1192), op 2: sub_plain (:1194-1241); plaintext `index` of the pack is applied
+ * to every ciphertext of t, in place. */
+int crcnn_plain_op(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_plain *p, long index, int op);
+/* Evaluator::add_many over all ciphertexts of t (SEAL/seal/evaluator.cpp:296-308) -> 1 ciphertext. */
+int crcnn_add_many(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_tensor **out);
+/* Evaluator::square, size 2 -> 3 (SEAL/seal/evaluator.cpp:702-884). */
+int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3);
+/* Evaluator::relinearize, size 3 -> 2 (SEAL/seal/evaluator.cpp:886-1069). */
+int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_tensor **out2);
+
+/* ---- measurement ------------------------------------------------------------------------------
+ * Kernel classes are timed with CUDA events on the context's stream while profiling is on. */
+int crcnn_prof_enable(crcnn_ctx *ctx, int on);
+int crcnn_prof_reset(crcnn_ctx *ctx);
+int crcnn_prof_count(crcnn_ctx *ctx); /* number of kernel classes */
+/* name: >= 32 bytes.  launches counts since the last reset (always maintained); ms only while enabled. */
+int crcnn_prof_get(crcnn_ctx *ctx, int cls, char *name, long *launches, double *ms);
+/* Register-only 64x64->128-bit multiply-accumulate probe (integer-pipe roofline): runs
+ * blocks*threads*iters*8 MACs and returns the elapsed device time in ms. */
+int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

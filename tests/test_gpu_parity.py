@@ -1,0 +1,262 @@
+"""GPU parity tests proper: every C-ABI entry point against the CPU oracle, byte for byte.
+
+The checker is oracle/liboracle.so (plain-C restatement, itself pinned to the compiled reference and
+to the golden fixtures by the CPU tests).  Where oracle/_ref/libcrcnn_ref.so is present the real
+reference (SEAL 2.3.1 + CrCNN layers) encrypts the inputs and decrypts the outputs as well.
+Bar: bit-exact (integer residues) -- np.array_equal, no tolerance.
+"""
+import numpy as np
+import pytest
+
+from util import PRIMES, T_FOR_N, random_cts, random_evk, have_ref
+from oracle.port import Oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=[2048, 4096, 8192])
+def env(request):
+    from crcnn_b200.lib import Engine
+    n = request.param
+    primes, t = PRIMES[n], T_FOR_N[n]
+    eng = Engine(n, primes, t)
+    orc = Oracle(n, primes, t)
+    rng = np.random.default_rng(n)
+    yield n, primes, t, eng, orc, rng
+    eng.close()
+
+
+def test_ntt_tables_match_oracle(env):
+    n, primes, t, eng, orc, rng = env
+    K = len(primes)
+    assert eng.S == orc.S
+    for slot in range(K + orc.S):
+        base, idx = (0, slot) if slot < K else (1, slot - K)
+        for which in range(4):
+            assert np.array_equal(eng.ntt_table(slot, which), orc.ntt_table(base, idx, which)), (slot, which)
+
+
+def test_upload_download_roundtrip(env):
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 5)
+    tx = eng.upload(x)
+    assert np.array_equal(eng.download(tx), x)
+
+
+def test_transform_to_from_ntt(env):
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 7)
+    tx = eng.upload(x)
+    eng.to_ntt(tx)
+    want = orc.ct_transform(x)
+    got = eng.download(tx, ntt_form=True)
+    assert np.array_equal(got, want)
+    assert np.array_equal(eng.download(tx), x)  # download converts a copy back
+    eng.from_ntt(tx)
+    assert np.array_equal(eng.download(tx), x)
+
+
+def test_plain_to_ntt_and_encode(env):
+    n, primes, t, eng, orc, rng = env
+    vals = np.array([0.0867, -3.25, 0.0, 1.0, -1.0, 7.0, 0.25, 2.8215, -0.4242, 1 / 9.0, -17.5, 1e-9], dtype=np.float32)
+    p = eng.plain_encode(vals)
+    for i, v in enumerate(vals):
+        want, _ = orc.encode(float(v))
+        got = eng.plain_get(p, i)
+        assert np.array_equal(got, want), v
+        assert np.array_equal(eng.plain_get_ntt(p, i), orc.plain_to_ntt(want)), v
+
+
+@pytest.mark.parametrize("op", ["mul", "add", "sub"])
+def test_plain_ops(env, op):
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 3)
+    w, _ = orc.encode(0.0867)
+    dense = np.zeros(n + 1, dtype=np.uint64)
+    dense[:n] = rng.integers(0, t, size=n, dtype=np.uint64)  # a fully dense plaintext too
+    const = np.array([t - 2], dtype=np.uint64)               # SEAL's constant-plaintext branch
+    for plain in (w, dense, const):
+        p = eng.plain_upload(plain)
+        tx = eng.upload(x)
+        eng.plain_op(tx, p, 0, op)
+        assert np.array_equal(eng.download(tx), orc.plain_op(x, plain, op)), (op, len(plain))
+
+
+def test_multiply_plain_ntt_semantics(env):
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 2)
+    w, _ = orc.encode(-0.731)
+    xn = orc.ct_transform(x)
+    want = orc.multiply_plain_ntt(xn, orc.plain_to_ntt(w))
+    tx = eng.upload(xn, ntt_form=True)
+    eng.plain_op(tx, eng.plain_upload(w), 0, "mul")
+    assert np.array_equal(eng.download(tx, ntt_form=True), want)
+
+
+def test_add_many(env):
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 9)
+    got = eng.download(eng.add_many(eng.upload(x)))
+    assert np.array_equal(got[0], orc.add_many(x))
+
+
+def test_square_and_relinearize(env):
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 3)
+    evk, sizes, dbc = random_evk(rng, n, primes)
+    tx = eng.upload(x)
+    t3 = eng.square(tx)
+    want3 = orc.square(x)
+    got3 = eng.download(t3)
+    assert np.array_equal(got3, want3)
+    k = eng.evk_upload(evk, sizes, dbc)
+    got2 = eng.download(eng.relinearize(t3, k))
+    assert np.array_equal(got2, orc.relinearize(want3, evk, sizes, dbc))
+    got_layer = eng.download(eng.square_layer(eng.upload(x), k))
+    assert np.array_equal(got_layer, got2)
+
+
+def _layer_params(orc, rng, count):
+    vals = rng.uniform(-1, 1, size=count).astype(np.float32)
+    return vals, orc.encode_many(vals)
+
+
+def test_conv_layer(env):
+    n, primes, t, eng, orc, rng = env
+    xd, yd, zd, xs, ys, xf, yf, nf = 5, 4, 2, 2, 1, 3, 2, 3
+    x = random_cts(rng, n, primes, zd * xd * yd)
+    wv, wp = _layer_params(orc, rng, nf * zd * xf * yf)
+    bv, bp = _layer_params(orc, rng, nf)
+    want = orc.conv(x, xd, yd, zd, xs, ys, xf, yf, nf, wp, bp)
+    got = eng.download(eng.conv(eng.upload(x), eng.plain_encode(wv), eng.plain_encode(bv), 1, xd, yd, zd, xs, ys, xf, yf, nf))
+    assert np.array_equal(got.reshape(want.shape), want)
+
+
+def test_conv_layer_batched_and_sharded(env):
+    n, primes, t, eng, orc, rng = env
+    xd, yd, zd, xs, ys, xf, yf, nf, B = 4, 4, 1, 1, 1, 2, 2, 5, 3
+    x = random_cts(rng, n, primes, B * zd * xd * yd)
+    wv, wp = _layer_params(orc, rng, nf * zd * xf * yf)
+    bv, bp = _layer_params(orc, rng, nf)
+    per = zd * xd * yd
+    want = np.stack([orc.conv(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, nf, wp, bp) for b in range(B)])
+    w, b_ = eng.plain_encode(wv), eng.plain_encode(bv)
+    got = eng.download(eng.conv(eng.upload(x), w, b_, B, xd, yd, zd, xs, ys, xf, yf, nf))
+    assert np.array_equal(got.reshape(want.shape), want)
+    # output-channel shard [1, 4) equals the same channels of the full result
+    got_s = eng.download(eng.conv(eng.upload(x), w, b_, B, xd, yd, zd, xs, ys, xf, yf, nf, shard=(1, 3)))
+    assert np.array_equal(got_s.reshape((B, 3) + want.shape[2:]), want[:, 1:4])
+
+
+def test_fc_layer_resident_and_chunked(env):
+    n, primes, t, eng, orc, rng = env
+    in_dim, out_dim = 11, 13
+    x = random_cts(rng, n, primes, in_dim)
+    wv, wp = _layer_params(orc, rng, in_dim * out_dim)
+    bv, bp = _layer_params(orc, rng, out_dim)
+    want = orc.fc(x, in_dim, out_dim, wp, bp)
+    got = eng.download(eng.fc(eng.upload(x), eng.plain_encode(wv), eng.plain_encode(bv), 1, in_dim, out_dim))
+    assert np.array_equal(got.reshape(want.shape), want)
+    # force the chunked path: room for ~3 output rows of NTT-form weights
+    eng.set_weight_cache_bytes(3 * in_dim * len(primes) * n * 8)
+    try:
+        got2 = eng.download(eng.fc(eng.upload(x), eng.plain_encode(wv), eng.plain_encode(bv), 1, in_dim, out_dim))
+    finally:
+        eng.set_weight_cache_bytes(24 << 30)
+    assert np.array_equal(got2.reshape(want.shape), want)
+
+
+def test_fc_layer_batched(env):
+    n, primes, t, eng, orc, rng = env
+    in_dim, out_dim, B = 6, 4, 3
+    x = random_cts(rng, n, primes, B * in_dim)
+    wv, wp = _layer_params(orc, rng, in_dim * out_dim)
+    bv, bp = _layer_params(orc, rng, out_dim)
+    want = np.stack([orc.fc(x[b * in_dim:(b + 1) * in_dim], in_dim, out_dim, wp, bp) for b in range(B)])
+    got = eng.download(eng.fc(eng.upload(x), eng.plain_encode(wv), eng.plain_encode(bv), B, in_dim, out_dim))
+    assert np.array_equal(got.reshape(want.shape), want)
+
+
+@pytest.mark.parametrize("avg", [False, True])
+def test_pool_layers(env, avg):
+    n, primes, t, eng, orc, rng = env
+    for (xd, yd, zd, xs, ys, xf, yf) in [(5, 5, 2, 1, 1, 2, 2), (6, 4, 3, 2, 2, 2, 2)]:
+        x = random_cts(rng, n, primes, zd * xd * yd)
+        if avg:
+            d, cc = orc.encode(1.0 / (xf * yf))
+            want = orc.pool(x, xd, yd, zd, xs, ys, xf, yf, d, cc)
+            got = eng.download(eng.pool(eng.upload(x), 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode([1.0 / (xf * yf)])))
+        else:
+            want = orc.pool(x, xd, yd, zd, xs, ys, xf, yf)
+            got = eng.download(eng.pool(eng.upload(x), 1, xd, yd, zd, xs, ys, xf, yf))
+        assert np.array_equal(got.reshape(want.shape), want)
+
+
+def test_bn_layer(env):
+    n, primes, t, eng, orc, rng = env
+    zd, xd, yd = 3, 2, 2
+    x = random_cts(rng, n, primes, zd * xd * yd)
+    mv, mp = _layer_params(orc, rng, zd)
+    vv = rng.uniform(0.5, 3, size=zd).astype(np.float32)
+    vp = orc.encode_many(vv)
+    want = orc.bn(x, zd, xd, yd, mp, vp)
+    got = eng.download(eng.bn(eng.upload(x), 1, zd, xd, yd, eng.plain_encode(mv), eng.plain_encode(vv)))
+    assert np.array_equal(got.reshape(want.shape), want)
+
+
+def test_layer_chain_stays_exact(env):
+    """conv -> avgpool -> bn -> square -> fc without leaving the device (lazy NTT domain inside)."""
+    n, primes, t, eng, orc, rng = env
+    x = random_cts(rng, n, primes, 16)  # 1x4x4
+    evk, sizes, dbc = random_evk(rng, n, primes)
+    wv, wp = _layer_params(orc, rng, 2 * 4)
+    bv, bp = _layer_params(orc, rng, 2)
+    mv, mp = _layer_params(orc, rng, 2)
+    vv, vp = _layer_params(orc, rng, 2)
+    fv, fp = _layer_params(orc, rng, 3 * 8)
+    fb, fbp = _layer_params(orc, rng, 3)
+    d, cc = orc.encode(0.25)
+    o = orc.conv(x, 4, 4, 1, 1, 1, 2, 2, 2, wp, bp)              # 2x3x3
+    o = orc.pool(o, 3, 3, 2, 1, 1, 2, 2, d, cc)                  # 2x2x2
+    o = orc.bn(o, 2, 2, 2, mp, vp)
+    o = orc.square_layer(o, evk, sizes, dbc)
+    want = orc.fc(o, 8, 3, fp, fbp)
+    g = eng.conv(eng.upload(x), eng.plain_encode(wv), eng.plain_encode(bv), 1, 4, 4, 1, 1, 1, 2, 2, 2)
+    g = eng.pool(g, 1, 3, 3, 2, 1, 1, 2, 2, scale=eng.plain_encode([0.25]))
+    g = eng.bn(g, 1, 2, 2, 2, eng.plain_encode(mv), eng.plain_encode(vv))
+    g = eng.square_layer(g, eng.evk_upload(evk, sizes, dbc))
+    g = eng.fc(g, eng.plain_encode(fv), eng.plain_encode(fb), 1, 8, 3)
+    assert np.array_equal(eng.download(g).reshape(want.shape), want)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_end_to_end_with_real_seal_client():
+    """Real SEAL keys/encryption on the host (client boundary), GPU forward, SEAL decryption."""
+    from oracle.ref import Ref
+    from crcnn_b200.lib import Engine
+    n, t = 4096, 1 << 18
+    r = Ref(n, t, seed=11)
+    eng = Engine(n, r.primes, t)
+    rng = np.random.default_rng(5)
+    img = rng.uniform(-0.4242, 2.8215, size=16).astype(np.float32)
+    x = r.encrypt(img)
+    wv = rng.uniform(-1, 1, size=2 * 4).astype(np.float32)
+    bv = rng.uniform(-1, 1, size=2).astype(np.float32)
+    evk, sizes, dbc = r.evk()
+    want = r.square_layer(r.conv(x, 4, 4, 1, 1, 1, 2, 2, 2, wv, bv), 2, 3, 3)
+    g = eng.conv(eng.upload(x), eng.plain_encode(wv), eng.plain_encode(bv), 1, 4, 4, 1, 1, 1, 2, 2, 2)
+    g = eng.square_layer(g, eng.evk_upload(evk, sizes, dbc))
+    got = eng.download(g)
+    assert np.array_equal(got.reshape(want.shape), want)
+    vals, budgets = r.decrypt(got)
+    ref_vals, ref_budgets = r.decrypt(want)
+    assert np.array_equal(vals, ref_vals) and np.array_equal(budgets, ref_budgets)
+    # and the decrypted numbers are the plain computation
+    plain = np.zeros((2, 3, 3))
+    im = img.reshape(4, 4)
+    for k in range(2):
+        for i in range(3):
+            for j in range(3):
+                plain[k, i, j] = (im[i:i + 2, j:j + 2].ravel() * wv[k * 4:(k + 1) * 4]).sum() + bv[k]
+    assert np.allclose(vals.reshape(2, 3, 3), plain ** 2, atol=1e-3)
+    eng.close()
