@@ -71,6 +71,12 @@ class Ref:
         self.lib.ref_evk(_p(out, _u64p), _p(sizes, _i32p))
         return out, [int(s) for s in sizes], int(self.lib.ref_evk_dbc())
 
+    def set_evk(self, words, sizes, dbc=16):
+        """Replace the reference's evaluation keys by caller-supplied key material."""
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        s = np.ascontiguousarray(sizes, dtype=np.int32)
+        self._chk(self.lib.ref_set_evk(_p(w, _u64p), _p(s, _i32p), dbc))
+
     def encode(self, v):
         out = np.zeros(self.stride, dtype=np.uint64)
         cc = C.c_int(0)

@@ -175,6 +175,29 @@ long ref_evk(uint64_t *out, int *sizes) {
 }
 int ref_evk_dbc() { return ev_keys16->decomposition_bit_count(); }
 
+// Replace ev_keys16 by caller-supplied key material (same layout ref_evk() returns).  Built by
+// writing SEAL's own EvaluationKeys stream format (SEAL/seal/evaluationkeys.cpp:8-39,
+// ciphertext.cpp:103-113) and calling EvaluationKeys::load, so no private member is touched.
+int ref_set_evk(const uint64_t *words, const int *sizes, int dbc) {
+    return guarded([&] {
+        std::stringstream ss(std::ios::in | std::ios::out | std::ios::binary);
+        auto hash = parms->hash_block();
+        ss.write(reinterpret_cast<const char *>(&hash), sizeof(hash));
+        int32_t dbc32 = dbc, dim1 = 1, dim2 = g_K;
+        ss.write(reinterpret_cast<const char *>(&dbc32), 4);
+        ss.write(reinterpret_cast<const char *>(&dim1), 4);
+        ss.write(reinterpret_cast<const char *>(&dim2), 4);
+        size_t off = 0;
+        for (int i = 0; i < g_K; i++) {
+            Ciphertext ct = make_ct(words + off, sizes[i]);
+            ct.save(ss);
+            off += ct_words(sizes[i]);
+        }
+        ss.seekg(0);
+        ev_keys16->load(ss);
+    });
+}
+
 // FractionalEncoder(t, x^n+1, 64, 32, 3).encode(v)  (CrCNN/src/globals.cpp:52)
 int ref_encode(double v, uint64_t *out /* n+1 words */, int *coeff_count) {
     return guarded([&] {
