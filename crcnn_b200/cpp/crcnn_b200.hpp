@@ -1,0 +1,602 @@
+// crcnn_b200.hpp -- C++17 host side of the B200 engine: CrCNN's layer and network classes, same
+// names, constructor parameter lists, public members and virtuals as the reference's
+// CrCNN/src/*.h, implemented over the C ABI (include/crcnn_b200.h) instead of the process-global
+// seal::Evaluator.  A CrCNN program switches by including this header instead of the reference's
+// layer headers and adding `using namespace crcnn_b200;`.
+//
+// Two type modes:
+//   -DCRCNN_WITH_SEAL   Ciphertext / Plaintext / EvaluationKeys are SEAL 2.3.1's own classes
+//                       (true drop-in; needs the SEAL headers and library at build time).
+//   default             layout- and stream-compatible stand-ins (same in-memory word layout,
+//                       same save()/load() byte format: SEAL/seal/ciphertext.cpp:103-130,
+//                       plaintext.cpp:346-364), so the host logic builds and is tested where SEAL's
+//                       sources are absent (the GPU box).
+//
+// Reference interfaces mirrored (file:line under /root/reference/CrCNN/src):
+//   globals.h:10-16 (typedefs), layer.h:10-31, convolutionalLayer.h:33-45, fullyConnectedLayer.h:22-36,
+//   poolingLayer.h:12-21, avgPoolingLayer.h:7-14, batchNormLayer.h:13-30, squareLayer.h:9-20,
+//   network.h:11-39.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <istream>
+#include <memory>
+#include <ostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/crcnn_b200.h"
+
+#ifdef CRCNN_WITH_SEAL
+#include "seal/seal.h"
+#endif
+
+namespace crcnn_b200 {
+
+// ------------------------------------------------------------------------------------------------
+// value types
+// ------------------------------------------------------------------------------------------------
+#ifdef CRCNN_WITH_SEAL
+using seal::Ciphertext;
+using seal::EvaluationKeys;
+using seal::Plaintext;
+#else
+// Stand-in for seal::Plaintext: coeff_count words, values < t (NTT form: K*(n+1) words).
+class Plaintext {
+public:
+    Plaintext() = default;
+    explicit Plaintext(int coeff_count) : w_(coeff_count, 0) {}
+    int coeff_count() const { return (int)w_.size(); }
+    std::uint64_t *data() { return w_.data(); }
+    const std::uint64_t *data() const { return w_.data(); }
+    std::uint64_t &operator[](int i) { return w_[i]; }
+    const std::uint64_t &operator[](int i) const { return w_[i]; }
+    void resize(int coeff_count) { w_.resize(coeff_count, 0); }
+    void save(std::ostream &s) const {
+        std::int32_t c = coeff_count();
+        s.write(reinterpret_cast<const char *>(&c), 4);
+        s.write(reinterpret_cast<const char *>(w_.data()), (std::streamsize)w_.size() * 8);
+    }
+    void load(std::istream &s) {
+        std::int32_t c = 0;
+        s.read(reinterpret_cast<char *>(&c), 4);
+        w_.assign(c, 0);
+        s.read(reinterpret_cast<char *>(w_.data()), (std::streamsize)c * 8);
+    }
+private:
+    std::vector<std::uint64_t> w_;
+};
+
+// Stand-in for seal::Ciphertext: uint64[size][K][n+1] plus the header fields SEAL serialises.
+class Ciphertext {
+public:
+    Ciphertext() = default;
+    Ciphertext(int size, int poly_coeff_count, int coeff_mod_count)
+        : size_(size), pcc_(poly_coeff_count), cmc_(coeff_mod_count), w_((size_t)size * poly_coeff_count * coeff_mod_count, 0) {}
+    int size() const { return size_; }
+    int poly_coeff_count() const { return pcc_; }
+    int coeff_mod_count() const { return cmc_; }
+    std::uint64_t *data() { return w_.data(); }
+    const std::uint64_t *data() const { return w_.data(); }
+    std::uint64_t *data(int poly) { return w_.data() + (size_t)poly * pcc_ * cmc_; }
+    std::uint64_t hash_block[4] = {0, 0, 0, 0};
+    void save(std::ostream &s) const {
+        s.write(reinterpret_cast<const char *>(hash_block), 32);
+        std::int32_t h[3] = {size_, pcc_, cmc_};
+        s.write(reinterpret_cast<const char *>(h), 12);
+        s.write(reinterpret_cast<const char *>(w_.data()), (std::streamsize)w_.size() * 8);
+    }
+    void load(std::istream &s) {
+        s.read(reinterpret_cast<char *>(hash_block), 32);
+        std::int32_t h[3] = {0, 0, 0};
+        s.read(reinterpret_cast<char *>(h), 12);
+        size_ = h[0]; pcc_ = h[1]; cmc_ = h[2];
+        w_.assign((size_t)size_ * pcc_ * cmc_, 0);
+        s.read(reinterpret_cast<char *>(w_.data()), (std::streamsize)w_.size() * 8);
+    }
+private:
+    int size_ = 0, pcc_ = 0, cmc_ = 0;
+    std::vector<std::uint64_t> w_;
+};
+#endif
+
+// CrCNN/src/globals.h:10-16
+typedef std::vector<std::vector<std::vector<Ciphertext>>> ciphertext3D;
+typedef std::vector<std::vector<std::vector<Plaintext>>> plaintext3D;
+typedef std::vector<std::vector<Ciphertext>> ciphertext2D;
+typedef std::vector<std::vector<Plaintext>> plaintext2D;
+typedef std::vector<std::vector<std::vector<std::vector<Plaintext>>>> plaintext4D;
+typedef std::vector<std::vector<std::vector<float>>> floatCube;
+
+// ------------------------------------------------------------------------------------------------
+// Runtime: replaces the process-global `Evaluator *evaluator` / `EvaluationKeys *ev_keys16`
+// (CrCNN/src/globals.h:23,27).  One GPU context per process, like the reference's globals.
+// ------------------------------------------------------------------------------------------------
+class Runtime {
+public:
+    static Runtime &get() { static Runtime r; return r; }
+
+    // setParameters (CrCNN/src/globals.cpp:25-56) as far as evaluation is concerned.
+    void init(int n, const std::vector<std::uint64_t> &q, std::uint64_t t, int device = 0) {
+        reset();
+        int rc = crcnn_ctx_create(n, (int)q.size(), q.data(), t, device, &ctx_);
+        if (rc) fail(rc, crcnn_last_error(nullptr));
+        n_ = n; K_ = (int)q.size(); t_ = t;
+    }
+#ifdef CRCNN_WITH_SEAL
+    // Derive (n, q, t) from the caller's SEALContext; remembers the EncryptionParameters so that
+    // result ciphertexts carry the right parameter hash (SEAL/seal/ciphertext.h:119-123).
+    void init(const seal::SEALContext &context, int device = 0) {
+        std::vector<std::uint64_t> q;
+        for (auto &m : context.coeff_modulus()) q.push_back(m.value());
+        init(context.poly_modulus().coeff_count() - 1, q, context.plain_modulus().value(), device);
+        parms_.reset(new seal::EncryptionParameters(context.parms()));
+    }
+    void setEvaluationKeys(const seal::EvaluationKeys &keys) {
+        // (SEAL 2.3.1's const hash_block() accessors recurse into themselves -- ciphertext.h:612-615,
+        //  evaluationkeys.h:163-166 -- so the non-const overload is used on purpose)
+        if (!parms_ || const_cast<seal::EvaluationKeys &>(keys).hash_block() != parms_->hash_block())
+            throw std::invalid_argument("evaluation_keys is not valid for encryption parameters");  // evaluator.cpp:899-902
+        const auto &row = keys.data()[0];
+        std::vector<int> sizes;
+        std::vector<std::uint64_t> words;
+        for (auto &ct : row) {
+            sizes.push_back(ct.size());
+            words.insert(words.end(), ct.data(), ct.data() + (size_t)ct.size() * K_ * (n_ + 1));
+        }
+        setEvaluationKeys(words.data(), sizes.data(), keys.decomposition_bit_count());
+    }
+    const seal::EncryptionParameters &parms() const { return *parms_; }
+#endif
+    void setEvaluationKeys(const std::uint64_t *words, const int *sizes, int dbc) {
+        need();
+        if (evk_) crcnn_evk_free(ctx_, evk_);
+        evk_ = nullptr;
+        check(crcnn_evk_upload(ctx_, words, dbc, sizes, &evk_));
+    }
+    void reset() {
+        if (ctx_) {
+            if (evk_) crcnn_evk_free(ctx_, evk_);
+            crcnn_ctx_destroy(ctx_);
+        }
+        ctx_ = nullptr; evk_ = nullptr;
+    }
+    ~Runtime() { reset(); }
+
+    crcnn_ctx *ctx() { need(); return ctx_; }
+    crcnn_evk *evk() {
+        if (!evk_) throw std::invalid_argument("not enough evaluation keys");  // evaluator.cpp:903-906
+        return evk_;
+    }
+    int n() const { return n_; }
+    int K() const { return K_; }
+    std::uint64_t t() const { return t_; }
+    size_t ct_words(int size = 2) const { return (size_t)size * K_ * (n_ + 1); }
+
+    // C ABI status -> the exception type the reference's callers see from SEAL
+    void check(int rc) { if (rc) fail(rc, crcnn_last_error(ctx_)); }
+
+private:
+    Runtime() = default;
+    void need() { if (!ctx_) throw std::logic_error("crcnn_b200::Runtime::init() has not been called"); }
+    [[noreturn]] static void fail(int rc, const char *msg) {
+        if (rc == CRCNN_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+        throw std::runtime_error(std::string("crcnn_b200: ") + msg);
+    }
+    crcnn_ctx *ctx_ = nullptr;
+    crcnn_evk *evk_ = nullptr;
+    int n_ = 0, K_ = 0;
+    std::uint64_t t_ = 0;
+#ifdef CRCNN_WITH_SEAL
+    std::unique_ptr<seal::EncryptionParameters> parms_;
+#endif
+};
+
+// RAII handles over the C ABI objects
+struct DeviceTensor {
+    crcnn_tensor *t = nullptr;
+    int zd = 0, xd = 0, yd = 0;
+    DeviceTensor() = default;
+    DeviceTensor(crcnn_tensor *p, int z, int x, int y) : t(p), zd(z), xd(x), yd(y) {}
+    DeviceTensor(DeviceTensor &&o) noexcept : t(o.t), zd(o.zd), xd(o.xd), yd(o.yd) { o.t = nullptr; }
+    DeviceTensor &operator=(DeviceTensor &&o) noexcept {
+        if (this != &o) { release(); t = o.t; zd = o.zd; xd = o.xd; yd = o.yd; o.t = nullptr; }
+        return *this;
+    }
+    DeviceTensor(const DeviceTensor &) = delete;
+    DeviceTensor &operator=(const DeviceTensor &) = delete;
+    ~DeviceTensor() { release(); }
+    void release() { if (t) crcnn_tensor_free(Runtime::get().ctx(), t); t = nullptr; }
+};
+
+struct PlainPack {
+    crcnn_plain *p = nullptr;
+    PlainPack() = default;
+    PlainPack(const PlainPack &) = delete;
+    PlainPack &operator=(const PlainPack &) = delete;
+    ~PlainPack() { clear(); }
+    void clear() { if (p) crcnn_plain_free(Runtime::get().ctx(), p); p = nullptr; }
+    // Coefficient-form plaintexts -> sparse device pack.  NTT-form plaintexts (coeff_count > n+1, what the
+    // reference's layers leave behind after their first forward, convolutionalLayer.cpp:151-156) are rejected
+    // like SEAL rejects them in transform_to_ntt (evaluator.cpp:1426-1429).
+    void assign(const std::vector<const Plaintext *> &pts) {
+        clear();
+        Runtime &rt = Runtime::get();
+        std::vector<std::uint32_t> off(1, 0), idx;
+        std::vector<std::uint64_t> val;
+        for (const Plaintext *pt : pts) {
+            if (pt->coeff_count() > rt.n() + 1) throw std::invalid_argument("plain is not valid for encryption parameters");
+            const std::uint64_t *w = pt->data();
+            for (int c = 0; c < pt->coeff_count(); c++)
+                if (w[c]) { idx.push_back((std::uint32_t)c); val.push_back(w[c]); }
+            off.push_back((std::uint32_t)idx.size());
+        }
+        rt.check(crcnn_plain_upload_sparse(rt.ctx(), idx.data(), val.data(), off.data(), (long)pts.size(), &p));
+    }
+};
+
+// ciphertext3D <-> device
+inline DeviceTensor upload(const ciphertext3D &in) {
+    Runtime &rt = Runtime::get();
+    const int zd = (int)in.size(), xd = (int)in[0].size(), yd = (int)in[0][0].size();
+    const size_t w = rt.ct_words(2);
+    std::vector<std::uint64_t> stage((size_t)zd * xd * yd * w);
+    size_t i = 0;
+    for (auto &plane : in)
+        for (auto &row : plane)
+            for (auto &ct : row) {
+                if (ct.size() != 2 || ct.poly_coeff_count() != rt.n() + 1 || ct.coeff_mod_count() != rt.K())
+                    throw std::invalid_argument("encrypted is not valid for encryption parameters");
+#ifdef CRCNN_WITH_SEAL
+                if (const_cast<Ciphertext &>(ct).hash_block() != rt.parms().hash_block())
+                    throw std::invalid_argument("encrypted is not valid for encryption parameters");  // evaluator.cpp:1503-1506
+#endif
+                std::memcpy(stage.data() + i * w, ct.data(), w * 8);
+                i++;
+            }
+    crcnn_tensor *t = nullptr;
+    rt.check(crcnn_tensor_upload(rt.ctx(), stage.data(), (long)zd * xd * yd, 2, &t));
+    rt.check(crcnn_ctx_sync(rt.ctx()));  // `stage` is pageable and about to go away
+    return DeviceTensor(t, zd, xd, yd);
+}
+
+inline ciphertext3D download(const DeviceTensor &d) {
+    Runtime &rt = Runtime::get();
+    const size_t w = rt.ct_words(2);
+    std::vector<std::uint64_t> stage((size_t)d.zd * d.xd * d.yd * w);
+    rt.check(crcnn_tensor_download(rt.ctx(), d.t, stage.data()));
+    ciphertext3D out(d.zd, ciphertext2D(d.xd, std::vector<Ciphertext>(d.yd)));
+    size_t i = 0;
+    for (auto &plane : out)
+        for (auto &row : plane)
+            for (auto &ct : row) {
+#ifdef CRCNN_WITH_SEAL
+                Ciphertext alias(rt.parms(), 2, stage.data() + i * w);  // sets the parameter hash
+                ct = alias;                                              // deep copy, un-aliased
+#else
+                ct = Ciphertext(2, rt.n() + 1, rt.K());
+                std::memcpy(ct.data(), stage.data() + i * w, w * 8);
+#endif
+                i++;
+            }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer (CrCNN/src/layer.h:10-31)
+// ------------------------------------------------------------------------------------------------
+class Layer {
+public:
+    std::string name;
+    Layer() {}
+    Layer(std::string layer_name) : name(layer_name) {}
+    virtual ~Layer() {}
+    std::string getName() { return name; }
+    virtual void printLayerStructure() = 0;
+    // Reference signature: ciphertexts in and out by value on the host.
+    virtual ciphertext3D forward(ciphertext3D input) { return download(forward_dev(upload(input))); }
+    // Device-resident variant used by Network::forward so activations never leave HBM between layers.
+    virtual DeviceTensor forward_dev(DeviceTensor input) = 0;
+    virtual void savePlaintextParameters(std::ostream *outfile) = 0;
+    virtual void loadPlaintextParameters(std::istream *infile) = 0;
+    // CrCNN/src/layer.cpp:12-26
+    void computeBoundaries(int xd, int yd, int xs, int ys, int xf, int yf, int *xl, int *yl) {
+        *xl = (xf > xs) ? xd - xf + 1 : xd - xs + 1;
+        *yl = (yf > ys) ? yd - yf + 1 : yd - ys + 1;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// ConvolutionalLayer (CrCNN/src/convolutionalLayer.h:9-58)
+// ------------------------------------------------------------------------------------------------
+class ConvolutionalLayer : public Layer {
+public:
+    int xd, yd, zd, xs, ys, xf, yf, nf, th_count;  // th_count is accepted and ignored (the GPU schedules the work)
+    int xo, yo, zo;
+    plaintext4D filters;  // nf,zd,xf,yf -- never modified by forward (the reference NTT-transforms them in place)
+    std::vector<Plaintext> biases;
+    bool filters_already_ntt;  // kept for source compatibility; always false here
+
+    ConvolutionalLayer(std::string name, int xd, int yd, int zd, int xs, int ys, int xf, int yf, int nf, int th_count,
+                       plaintext4D &filters, std::vector<Plaintext> &biases)
+        : Layer(name), xd(xd), yd(yd), zd(zd), xs(xs), ys(ys), xf(xf), yf(yf), nf(nf), th_count(th_count),
+          xo((xd - xf) / xs + 1), yo((yd - yf) / ys + 1), zo(nf), filters(filters), biases(biases), filters_already_ntt(false) {}
+    ConvolutionalLayer(std::string name, int xd, int yd, int zd, int xs, int ys, int xf, int yf, int nf, int th_count,
+                       std::istream *infile)
+        : Layer(name), xd(xd), yd(yd), zd(zd), xs(xs), ys(ys), xf(xf), yf(yf), nf(nf), th_count(th_count),
+          xo((xd - xf) / xs + 1), yo((yd - yf) / ys + 1), zo(nf), filters_already_ntt(false) {
+        loadPlaintextParameters(infile);
+    }
+
+    DeviceTensor forward_dev(DeviceTensor in) override {
+        Runtime &rt = Runtime::get();
+        ensure_packs();
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_conv_forward(rt.ctx(), in.t, w_.p, b_.p, 1, xd, yd, zd, xs, ys, xf, yf, nf, &o));
+        return DeviceTensor(o, zo, xo, yo);
+    }
+    plaintext3D getKernel(int kernel_index) { return filters[kernel_index]; }
+    Plaintext getBias(int bias_index) { return biases[bias_index]; }
+
+    // stream format: per filter zd*xf*yf weight records then the bias (convolutionalLayer.cpp:213-229)
+    void savePlaintextParameters(std::ostream *outfile) override {
+        for (int n = 0; n < nf; n++) {
+            for (int z = 0; z < zd; z++)
+                for (int i = 0; i < xf; i++)
+                    for (int j = 0; j < yf; j++) { filters[n][z][i][j].save(*outfile); outfile->flush(); }
+            biases[n].save(*outfile);
+            outfile->flush();
+        }
+    }
+    void loadPlaintextParameters(std::istream *infile) override {
+        plaintext4D w(nf, plaintext3D(zd, plaintext2D(xf, std::vector<Plaintext>(yf))));
+        std::vector<Plaintext> b(nf);
+        for (int n = 0; n < nf; n++) {
+            for (int z = 0; z < zd; z++)
+                for (int i = 0; i < xf; i++)
+                    for (int j = 0; j < yf; j++) w[n][z][i][j].load(*infile);
+            b[n].load(*infile);
+        }
+        filters = w; biases = b;
+        w_.clear(); b_.clear();
+    }
+    void printLayerStructure() override {
+        std::fprintf(stderr, "Convolutional %s : input (%d,%d,%d); kernel(%d,%d,%d,%d); stride(%d,%d); output(%d,%d,%d)\n",
+                     name.c_str(), zd, xd, yd, nf, zd, xf, yf, xs, ys, zo, xo, yo);
+    }
+
+private:
+    void ensure_packs() {
+        if (w_.p) return;
+        std::vector<const Plaintext *> ws, bs;
+        for (auto &f : filters) for (auto &pl : f) for (auto &row : pl) for (auto &p : row) ws.push_back(&p);
+        for (auto &p : biases) bs.push_back(&p);
+        if ((int)ws.size() != nf * zd * xf * yf || (int)bs.size() != nf) throw std::invalid_argument("kernel shape does not match the layer");
+        w_.assign(ws); b_.assign(bs);
+    }
+    PlainPack w_, b_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// FullyConnectedLayer (CrCNN/src/fullyConnectedLayer.h:13-50)
+// ------------------------------------------------------------------------------------------------
+class FullyConnectedLayer : public Layer {
+public:
+    int in_dim, out_dim, th_count;
+    plaintext2D weights;
+    std::vector<Plaintext> biases;
+    bool weights_already_ntt;
+
+    FullyConnectedLayer(std::string name, int in_dim, int out_dim, int th_count, plaintext2D &weights, std::vector<Plaintext> &biases)
+        : Layer(name), in_dim(in_dim), out_dim(out_dim), th_count(th_count), weights(weights), biases(biases), weights_already_ntt(false) {}
+    FullyConnectedLayer(std::string name, int in_dim, int out_dim, int th_count, std::istream *infile)
+        : Layer(name), in_dim(in_dim), out_dim(out_dim), th_count(th_count), weights_already_ntt(false) {
+        loadPlaintextParameters(infile);
+    }
+
+    // reshapeInput (fullyConnectedLayer.cpp:38-56): [z][x][y] -> [1][z*x*y][1], row-major.
+    ciphertext3D reshapeInput(ciphertext3D input) {
+        int x_size = (int)input[0].size(), y_size = (int)input[0][0].size(), z_size = (int)input.size();
+        if (z_size != 1 && y_size != 1) {
+            ciphertext3D r(1, ciphertext2D(in_dim, std::vector<Ciphertext>(1)));
+            for (int i = 0; i < in_dim; ++i) {
+                int z = i / (x_size * y_size), x = i / y_size - (x_size * z), y = i % y_size;
+                r[0][i][0] = input[z][x][y];
+            }
+            return r;
+        }
+        return input;
+    }
+    DeviceTensor forward_dev(DeviceTensor in) override {
+        Runtime &rt = Runtime::get();
+        ensure_packs();
+        // the device layout [z][x][y] is already the row-major flattening reshapeInput produces
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_fc_forward(rt.ctx(), in.t, w_.p, b_.p, 1, in_dim, out_dim, &o));
+        return DeviceTensor(o, 1, out_dim, 1);
+    }
+    Plaintext getWeight(int x_index, int y_index) { return weights[x_index][y_index]; }
+    Plaintext getBias(int x_index) { return biases[x_index]; }
+
+    // per output row in_dim weights then the bias (fullyConnectedLayer.cpp:198-208)
+    void savePlaintextParameters(std::ostream *outfile) override {
+        for (int i = 0; i < out_dim; i++) {
+            for (int j = 0; j < in_dim; j++) { weights[i][j].save(*outfile); outfile->flush(); }
+            biases[i].save(*outfile);
+            outfile->flush();
+        }
+    }
+    void loadPlaintextParameters(std::istream *infile) override {
+        std::vector<Plaintext> b(out_dim);
+        plaintext2D w(out_dim, std::vector<Plaintext>(in_dim));
+        for (int i = 0; i < out_dim; i++) {
+            for (int j = 0; j < in_dim; j++) w[i][j].load(*infile);
+            b[i].load(*infile);
+        }
+        weights = w; biases = b;
+        w_.clear(); b_.clear();
+    }
+    void printLayerStructure() override { std::fprintf(stderr, "FullyConnected %s : (%d -> %d)\n", name.c_str(), in_dim, out_dim); }
+
+private:
+    void ensure_packs() {
+        if (w_.p) return;
+        std::vector<const Plaintext *> ws, bs;
+        for (auto &row : weights) for (auto &p : row) ws.push_back(&p);
+        for (auto &p : biases) bs.push_back(&p);
+        if ((int)ws.size() != in_dim * out_dim || (int)bs.size() != out_dim) throw std::invalid_argument("weight shape does not match the layer");
+        w_.assign(ws); b_.assign(bs);
+    }
+    PlainPack w_, b_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// PoolingLayer / AvgPoolingLayer (CrCNN/src/poolingLayer.h:9-34, avgPoolingLayer.h:5-16)
+// ------------------------------------------------------------------------------------------------
+class PoolingLayer : public Layer {
+public:
+    int xd, yd, xs, ys, xf, yf, xo, yo, zo;
+    PoolingLayer(std::string name, int xd, int yd, int zd, int xs, int ys, int xf, int yf)
+        : Layer(name), xd(xd), yd(yd), xs(xs), ys(ys), xf(xf), yf(yf), xo((xd - xf) / xs + 1), yo((yd - yf) / ys + 1), zo(zd) {}
+    DeviceTensor forward_dev(DeviceTensor in) override {
+        Runtime &rt = Runtime::get();
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_pool_forward(rt.ctx(), in.t, 1, xd, yd, zo, xs, ys, xf, yf, scale(), &o));
+        return DeviceTensor(o, zo, xo, yo);
+    }
+    void printLayerStructure() override {
+        std::fprintf(stderr, "Pooling %s : input (%d,%d,%d); kernel(%d,%d); stride(%d,%d); output(%d,%d,%d)\n", name.c_str(), zo, xd, yd, xf, yf, xs, ys, zo, xo, yo);
+    }
+    void savePlaintextParameters(std::ostream *) override {}
+    void loadPlaintextParameters(std::istream *) override {}
+protected:
+    virtual crcnn_plain *scale() { return nullptr; }
+};
+
+class AvgPoolingLayer : public PoolingLayer {
+public:
+    Plaintext div_factor;  // encode(1/(xf*yf)), avgPoolingLayer.cpp:10-13
+    AvgPoolingLayer(std::string name, int xd, int yd, int zd, int xs, int ys, int xf, int yf)
+        : PoolingLayer(name, xd, yd, zd, xs, ys, xf, yf) {
+        Runtime &rt = Runtime::get();
+        float v = (float)(1. / (xf * yf));
+        rt.check(crcnn_plain_encode(rt.ctx(), &v, 1, &pack_.p));
+        div_factor = Plaintext(rt.n() + 1);
+        rt.check(crcnn_plain_get(rt.ctx(), pack_.p, 0, div_factor.data()));
+    }
+protected:
+    crcnn_plain *scale() override { return pack_.p; }
+private:
+    PlainPack pack_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// BatchNormLayer (CrCNN/src/batchNormLayer.h:10-40) -- `var` holds 1/sqrt(var+1e-5) as in the reference
+// ------------------------------------------------------------------------------------------------
+class BatchNormLayer : public Layer {
+public:
+    int num_channels;
+    std::vector<Plaintext> mean;
+    std::vector<Plaintext> var;
+    BatchNormLayer(std::string name, int num_channels, std::vector<Plaintext> &mean, std::vector<Plaintext> &var)
+        : Layer(name), num_channels(num_channels), mean(mean), var(var) {}
+    BatchNormLayer(std::string name, int num_channels, std::istream *infile) : Layer(name), num_channels(num_channels) {
+        loadPlaintextParameters(infile);
+    }
+    DeviceTensor forward_dev(DeviceTensor in) override {
+        Runtime &rt = Runtime::get();
+        if (!m_.p) {
+            std::vector<const Plaintext *> ms, vs;
+            for (auto &p : mean) ms.push_back(&p);
+            for (auto &p : var) vs.push_back(&p);
+            m_.assign(ms); v_.assign(vs);
+        }
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_bn_forward(rt.ctx(), in.t, 1, in.zd, in.xd, in.yd, m_.p, v_.p, &o));
+        return DeviceTensor(o, in.zd, in.xd, in.yd);
+    }
+    Plaintext getMean(int index) { return mean[index]; }
+    Plaintext getVar(int index) { return var[index]; }
+    // alternating mean / var records (batchNormLayer.cpp:42-48)
+    void savePlaintextParameters(std::ostream *outfile) override {
+        for (int i = 0; i < num_channels; i++) { mean[i].save(*outfile); var[i].save(*outfile); outfile->flush(); }
+    }
+    void loadPlaintextParameters(std::istream *infile) override {
+        std::vector<Plaintext> m(num_channels), v(num_channels);
+        for (int i = 0; i < num_channels; i++) { m[i].load(*infile); v[i].load(*infile); }
+        mean = m; var = v;
+        m_.clear(); v_.clear();
+    }
+    void printLayerStructure() override { std::fprintf(stderr, "BatchNormLayer2D %s :num_channels %d\n", name.c_str(), num_channels); }
+private:
+    PlainPack m_, v_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// SquareLayer (CrCNN/src/squareLayer.h:6-28)
+// ------------------------------------------------------------------------------------------------
+class SquareLayer : public Layer {
+public:
+    int th_count;
+    SquareLayer(std::string name, int th_count) : Layer(name), th_count(th_count) {}
+    SquareLayer() : th_count(1) {}
+    DeviceTensor forward_dev(DeviceTensor in) override {
+        Runtime &rt = Runtime::get();
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_square_forward(rt.ctx(), in.t, rt.evk(), &o));
+        return DeviceTensor(o, in.zd, in.xd, in.yd);
+    }
+    void printLayerStructure() override { std::fprintf(stderr, "SquareLayer %s\n", name.c_str()); }
+    void savePlaintextParameters(std::ostream *) override {}
+    void loadPlaintextParameters(std::istream *) override {}
+};
+
+// ------------------------------------------------------------------------------------------------
+// Network (CrCNN/src/network.h:11-39, network.cpp:22-47)
+// ------------------------------------------------------------------------------------------------
+class OutOfBudgetException : public std::exception {
+public:
+    const int last_layer_computed;
+    OutOfBudgetException(int last_layer_computed) : last_layer_computed(last_layer_computed),
+        msg_("OutOfBudgetException at layer " + std::to_string(last_layer_computed)) {}
+    const char *what() const throw() override { return msg_.c_str(); }
+private:
+    std::string msg_;
+};
+
+class Network {
+public:
+    std::vector<std::shared_ptr<Layer>> layers;
+    // The reference re-encrypts (decrypt + encrypt with the SECRET key) unconditionally before layer 6
+    // (network.cpp:23,30-38).  That step belongs to the key holder: install it here if wanted; by default
+    // no re-encryption happens and the whole network runs device-resident.
+    int layer_before_reenc = 6;
+    std::function<ciphertext3D(ciphertext3D)> reencrypt;
+
+    Network() {}
+    ~Network() {}
+    int getNumLayers() { return (int)layers.size(); }
+    virtual std::shared_ptr<Layer> getLayer(int i) { return layers[i]; }
+    std::vector<std::shared_ptr<Layer>> &getLayers() { return layers; }
+    void printNetworkStructure() {
+        for (size_t i = 0; i < layers.size(); i++) { std::fprintf(stderr, "(%zu) : ", i); layers[i]->printLayerStructure(); }
+    }
+    // Segment API: layers [first, last) without leaving the device.
+    DeviceTensor forward_dev(DeviceTensor x, int first, int last) {
+        for (int i = first; i < last; i++) x = layers[i]->forward_dev(std::move(x));
+        return x;
+    }
+    ciphertext3D forward(ciphertext3D input) {
+        const int L = (int)layers.size();
+        if (reencrypt && layer_before_reenc > 0 && layer_before_reenc < L) {
+            ciphertext3D mid = download(forward_dev(upload(input), 0, layer_before_reenc));
+            return download(forward_dev(upload(reencrypt(mid)), layer_before_reenc, L));
+        }
+        return download(forward_dev(upload(input), 0, L));
+    }
+};
+
+}  // namespace crcnn_b200
