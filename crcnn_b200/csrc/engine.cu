@@ -757,13 +757,31 @@ int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_t
     rc = new_tensor(ctx, in3->count, 2, 0, &o);
     if (rc) return rc;
     RelinArgs a{};
-    a.in3 = in3->d; a.evk = evk->d; a.dbc = evk->dbc; a.out = o->d; a.count = in3->count;
+    a.evk = evk->d; a.dbc = evk->dbc;
     for (int i = 0; i < MAXK; i++) { a.key_off[i] = evk->key_off[i]; a.digits[i] = evk->digits[i]; }
-    {
-        ProfScope ps(ctx, KC_RELIN);
-        cudaError_t e = launch_relin(ctx->dP, ctx->logn, ctx->K, a, ctx->stream);
-        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    // scratch per ciphertext: scaled c2 (K polys) + digit NTTs (D*K polys) + accumulators (2K polys);
+    // chunked so it stays near 2 GB
+    const size_t pw = poly_words(ctx);
+    const size_t per_ct = (size_t)(1 + total_digits + 2) * pw * 8;
+    const long step = std::max<long>(1, std::min<long>(in3->count, (long)((2ull << 30) / per_ct)));
+    uint64_t *scratch = nullptr;
+    rc = dev_alloc(ctx, (size_t)step * per_ct, (void **)&scratch);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+    a.dsc = scratch;
+    a.dig = scratch + (size_t)step * pw;
+    a.acc = a.dig + (size_t)step * total_digits * pw;
+    for (long c0 = 0; c0 < in3->count && !rc; c0 += step) {
+        a.count = std::min<long>(step, in3->count - c0);
+        a.in3 = in3->d + c0 * 3 * pw;
+        a.out = o->d + c0 * 2 * pw;
+        cudaError_t e;
+        { ProfScope ps(ctx, KC_RELIN); e = launch_relin(ctx->dP, ctx->logn, ctx->K, a, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV); e = launch_ntt(ctx->dP, ctx->logn, a.acc, a.count * 2 * ctx->K, 0, ctx->K, true, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_PLAIN_OP); e = launch_relin_finish(ctx->dP, ctx->n, ctx->K, a, ctx->stream); }
+        if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
     }
+    dev_free(ctx, scratch);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
     *out2 = o;
     return CRCNN_OK;
 }

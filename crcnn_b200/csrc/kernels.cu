@@ -8,7 +8,7 @@ namespace crcnn {
 // NTT / inverse NTT of dense limb-polynomials
 // =====================================================================================
 template <int LOGN>
-__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS)
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
 ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count) {
     extern __shared__ uint64_t sm[];
     const long p = blockIdx.x;
@@ -19,7 +19,7 @@ ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, 
 }
 
 template <int LOGN>
-__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS)
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
 ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count) {
     extern __shared__ uint64_t sm[];
     const long p = blockIdx.x;
@@ -41,6 +41,9 @@ static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npol
     if (!configured) {
         cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // without this the driver sizes the carve-out for ONE resident CTA (seen in ncu: occupancy limit 1)
+        cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(ki, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     if (npolys <= 0) return cudaSuccess;
@@ -65,7 +68,7 @@ cudaError_t launch_ntt(const DeviceParams *P, int logn, uint64_t *data, long npo
 // plaintext expansion: sparse (index, value<t) -> dense residues, optionally NTT form
 // =====================================================================================
 template <int LOGN>
-__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS)
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
 plain_expand_kernel(const DeviceParams *__restrict__ P, int K, const uint32_t *__restrict__ offsets,
                     const uint32_t *__restrict__ idx, const uint64_t *__restrict__ val, long first, int mode,
                     int to_ntt, uint64_t *__restrict__ out) {
@@ -108,7 +111,11 @@ static cudaError_t launch_plain_expand_t(const DeviceParams *P, int K, const uin
     size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto k = plain_expand_kernel<LOGN>;
     static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
+    if (!configured) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
     if (count <= 0) return cudaSuccess;
     k<<<(unsigned)(count * K), Pl::THREADS, smem, stream>>>(P, K, offsets, idx, val, first, mode, to_ntt ? 1 : 0, out);
     return cudaGetLastError();
@@ -159,15 +166,21 @@ mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
     }
     __syncthreads();
 
-    U128 acc[TM][TN][2];
+    Acc7 acc[TM][TN][2];
 #pragma unroll
     for (int m = 0; m < TM; m++)
 #pragma unroll
-        for (int t = 0; t < TN; t++) { acc[m][t][0] = U128{0, 0}; acc[m][t][1] = U128{0, 0}; }
+        for (int t = 0; t < TN; t++) { acc[m][t][0] = acc7_zero(); acc[m][t][1] = acc7_zero(); }
 
-    const uint64_t *wrow[TM];
+    // byte-addressed streams: weight row m advances by one plaintext per term; inputs are gathered
+    // with one 32x32+64 multiply-add per load (ciphertext index x ciphertext stride + base)
+    const unsigned w_step = (unsigned)(poly_words * 8), ct_step = (unsigned)(2 * poly_words * 8);
+    const char *wptr[TM];
 #pragma unroll
-    for (int m = 0; m < TM; m++) wrow[m] = a.w + (long)min(m_base + m, a.M - 1) * R * poly_words + limb_off;
+    for (int m = 0; m < TM; m++)
+        wptr[m] = reinterpret_cast<const char *>(a.w + (long)min(m_base + m, a.M - 1) * R * poly_words + limb_off);
+    const char *x0 = reinterpret_cast<const char *>(a.x + limb_off);
+    const char *x1 = x0 + w_step;
 
     for (int r0 = 0; r0 < R; r0 += a.chunk_terms) {
         const int r1 = min(R, r0 + a.chunk_terms);
@@ -175,19 +188,19 @@ mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
         for (int r = r0; r < r1; r++) {
             uint64_t W[TM], X[TN][2];
 #pragma unroll
-            for (int m = 0; m < TM; m++) W[m] = __ldg(wrow[m] + (long)r * poly_words);
+            for (int m = 0; m < TM; m++) { W[m] = __ldg(reinterpret_cast<const uint64_t *>(wptr[m])); wptr[m] += w_step; }
 #pragma unroll
             for (int t = 0; t < TN; t++) {
-                const uint64_t *xp = a.x + (long)s_idx[t * R + r] * 2 * poly_words + limb_off;
-                X[t][0] = __ldg(xp);
-                X[t][1] = __ldg(xp + poly_words);
+                const unsigned long long off = (unsigned long long)(unsigned)s_idx[t * R + r] * ct_step;
+                X[t][0] = __ldg(reinterpret_cast<const uint64_t *>(x0 + off));
+                X[t][1] = __ldg(reinterpret_cast<const uint64_t *>(x1 + off));
             }
 #pragma unroll
             for (int m = 0; m < TM; m++)
 #pragma unroll
                 for (int t = 0; t < TN; t++) {
-                    mac128(acc[m][t][0], X[t][0], W[m]);
-                    mac128(acc[m][t][1], X[t][1], W[m]);
+                    mac7(acc[m][t][0], X[t][0], W[m]);
+                    mac7(acc[m][t][1], X[t][1], W[m]);
                 }
         }
         if (r1 < R) {
@@ -195,8 +208,8 @@ mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
             for (int m = 0; m < TM; m++)
 #pragma unroll
                 for (int t = 0; t < TN; t++) {
-                    acc[m][t][0] = U128{barrett128(acc[m][t][0], mod), 0};
-                    acc[m][t][1] = U128{barrett128(acc[m][t][1], mod), 0};
+                    acc[m][t][0] = acc7_from(barrett128(acc7_value(acc[m][t][0]), mod));
+                    acc[m][t][1] = acc7_from(barrett128(acc7_value(acc[m][t][1]), mod));
                 }
         }
     }
@@ -208,7 +221,7 @@ mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
         for (int t = 0; t < TN; t++) {
             const int p = p_base + t;
             if (p >= a.Npos) continue;
-            uint64_t v0 = barrett128(acc[m][t][0], mod), v1 = barrett128(acc[m][t][1], mod);
+            uint64_t v0 = barrett128(acc7_value(acc[m][t][0]), mod), v1 = barrett128(acc7_value(acc[m][t][1]), mod);
             if (a.bias) v0 = addmod(v0, __ldg(a.bias + (long)(m_base + m) * poly_words + limb_off), mod.q);
             long oct = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + (long)(a.m0 + m_base + m) * a.Pimg + p % a.Pimg;
             uint64_t *op = a.out + oct * 2 * poly_words + limb_off;
@@ -399,88 +412,135 @@ behz_floor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict
 }
 
 // =====================================================================================
-// relinearize: digit decomposition x NTT-form keys, accumulated in registers
-// One CTA per (ciphertext, output limb j, output poly).  For every (prime i, digit k) the digit
-// polynomial is built in shared memory, transformed mod q_j there, and multiplied into 128-bit
-// register accumulators against the key polynomial; then one Barrett, one inverse NTT in shared
-// memory and the addition to c0 / c1.
+// relinearize 3 -> 2 (evaluator.cpp:934-1069), staged so every transform runs in the tuned NTT
+// kernel and nothing is recomputed:
+//   1. scale:   d_i = c2_i * (q/q_i)^-1 mod q_i                          (:984-985)
+//   2. digits:  for every (prime i, digit k, prime j): forward NTT mod q_j of the 16-bit digit
+//               polynomial (d_i >> 16k) & 0xffff, built on the fly while loading   (:997-1011)
+//   3. mac:     acc_p[j] = sum_(i,k) D_(i,k,j) (.) key_(i,k,p)[j], 128-bit lazy, one Barrett   (:1015-1046)
+//   4. inverse NTT of acc (generic kernel), 5. out_p = c_p + acc_p                 (:1047-1068)
 // =====================================================================================
-template <int LOGN, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-relin_kernel(const DeviceParams *__restrict__ P, RelinArgs a) {
-    extern __shared__ uint64_t sm[];
-    constexpr int N = 1 << LOGN;
-    constexpr int EPT = N / THREADS;
-    const int K = P->K;
+__global__ void __launch_bounds__(256)
+relin_scale_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in3, uint64_t *__restrict__ dsc) {
+    const int n = P->n, K = P->K;
+    const long pw = (long)K * n;
     const long ct = blockIdx.x;
-    const int j = blockIdx.y, poly = blockIdx.z;
-    const NttTable tb = P->tab[j];
-    const long pw = (long)K * N;
-    const uint64_t *c2 = a.in3 + (ct * 3 + 2) * pw;
-    const uint64_t mask = (1ULL << a.dbc) - 1;
-
-    U128 acc[EPT];
-#pragma unroll
-    for (int u = 0; u < EPT; u++) acc[u] = U128{0, 0};
-
-    for (int i = 0; i < K; i++) {
-        const Mod mi = P->tab[i].mod;
-        const uint64_t inv = P->inv_qhat[i];
-        for (int k = 0; k < a.digits[i]; k++) {
-            const int shift = a.dbc * k;
-#pragma unroll
-            for (int u = 0; u < EPT; u++) {
-                int e = threadIdx.x + u * THREADS;
-                uint64_t d = mulmod(__ldg(c2 + (long)i * N + e), inv, mi);  // evaluator.cpp:984-985
-                sm[ntt_pad(e)] = (d >> shift) & mask;                       // evaluator.cpp:997-1001
-            }
-            __syncthreads();
-            ntt_forward_in_smem<LOGN>(sm, tb);  // lazy [0,4q), ends with a barrier
-            const uint64_t *key = a.evk + a.key_off[i] + (long)(2 * k + poly) * pw + (long)j * N;
-#pragma unroll
-            for (int u = 0; u < EPT; u++) {
-                int e = threadIdx.x + u * THREADS;
-                mac128(acc[u], sm[ntt_pad(e)], __ldg(key + e));
-            }
-            __syncthreads();
-        }
-    }
-#pragma unroll
-    for (int u = 0; u < EPT; u++) sm[ntt_pad(threadIdx.x + u * THREADS)] = barrett128(acc[u], tb.mod);
-    __syncthreads();
-    ntt_inverse_in_smem<LOGN>(sm, tb);  // [0,2q), ends with a barrier
-    const uint64_t *cin = a.in3 + (ct * 3 + poly) * pw + (long)j * N;
-    uint64_t *cout = a.out + (ct * 2 + poly) * pw + (long)j * N;
-#pragma unroll
-    for (int u = 0; u < EPT; u++) {
-        int e = threadIdx.x + u * THREADS;
-        uint64_t v = sm[ntt_pad(e)];
-        v = v >= tb.mod.q ? v - tb.mod.q : v;
-        cout[e] = addmod(__ldg(cin + e), v, tb.mod.q);
-    }
+    const long lw = (long)blockIdx.y * 256 + threadIdx.x;  // i*n + e
+    const int i = (int)(lw / n);
+    dsc[ct * pw + lw] = mulmod(__ldg(in3 + (ct * 3 + 2) * pw + lw), P->inv_qhat[i], P->tab[i].mod);
 }
 
-template <int LOGN, int THREADS>
-static cudaError_t launch_relin_t(const DeviceParams *P, const RelinArgs &a, int K, cudaStream_t stream) {
-    size_t smem = NttPlan<LOGN>::SMEM_WORDS * sizeof(uint64_t);
-    auto k = relin_kernel<LOGN, THREADS>;
+struct DigitMap {
+    int D;                    // total digits = sum_i digits_i
+    unsigned char prime[32];  // digit d belongs to prime i
+    unsigned char shift[32];  // and is (d_i >> shift) & mask
+};
+
+template <int LOGN>
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
+ntt_fwd_digits_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ dsc, DigitMap map, uint64_t mask,
+                      uint64_t *__restrict__ dig) {
+    extern __shared__ uint64_t sm[];
+    constexpr int N = 1 << LOGN;
+    const int K = P->K;
+    const long b = blockIdx.x;  // (ct, digit, j)
+    const int j = (int)(b % K);
+    const int d = (int)((b / K) % map.D);
+    const long ct = b / ((long)K * map.D);
+    const NttTable tb = P->tab[j];
+    const uint64_t *src = dsc + (ct * K + map.prime[d]) * N;
+    const int shift = map.shift[d];
+    for (int e = threadIdx.x; e < N; e += blockDim.x) sm[ntt_pad(e)] = (__ldg(src + e) >> shift) & mask;
+    __syncthreads();
+    ntt_forward_in_smem<LOGN>(sm, tb);
+    smem_store_poly_canonical<LOGN>(sm, dig + b * N, tb.mod.q);
+}
+
+__global__ void __launch_bounds__(256)
+relin_mac_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ dig, const uint64_t *__restrict__ evk,
+                 RelinArgs a, DigitMap map, uint64_t *__restrict__ acc_out) {
+    const int n = P->n, K = P->K;
+    const long pw = (long)K * n;
+    const long ct = blockIdx.x;
+    const long lw = (long)blockIdx.y * 256 + threadIdx.x;  // j*n + e
+    const int j = (int)(lw / n);
+    Acc7 acc0 = acc7_zero(), acc1 = acc7_zero();
+    const uint64_t *dp = dig + ct * map.D * pw + lw;
+    for (int d = 0; d < map.D; d++) {
+        const int i = map.prime[d], k = map.shift[d] / a.dbc;
+        const uint64_t *key = evk + a.key_off[i] + (long)(2 * k) * pw + lw;
+        const uint64_t dv = __ldg(dp + (long)d * pw);
+        mac7(acc0, dv, __ldg(key));
+        mac7(acc1, dv, __ldg(key + pw));
+    }
+    const Mod mod = P->tab[j].mod;
+    acc_out[(ct * 2) * pw + lw] = barrett128(acc7_value(acc0), mod);
+    acc_out[(ct * 2 + 1) * pw + lw] = barrett128(acc7_value(acc1), mod);
+}
+
+__global__ void __launch_bounds__(256)
+relin_add_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in3, const uint64_t *__restrict__ acc,
+                 uint64_t *__restrict__ out) {
+    const int n = P->n, K = P->K;
+    const long pw = (long)K * n;
+    const long ct = blockIdx.x;
+    const long w = (long)blockIdx.y * 256 + threadIdx.x;  // p*pw + j*n + e, p in {0,1}
+    const uint64_t q = P->tab[(w % pw) / n].mod.q;
+    out[ct * 2 * pw + w] = addmod(__ldg(in3 + ct * 3 * pw + w), __ldg(acc + ct * 2 * pw + w), q);
+}
+
+template <int LOGN>
+static cudaError_t launch_digits_t(const DeviceParams *P, int K, const uint64_t *dsc, const DigitMap &map, uint64_t mask,
+                                   long count, uint64_t *dig, cudaStream_t stream) {
+    using Pl = NttPlan<LOGN>;
+    size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
+    auto k = ntt_fwd_digits_kernel<LOGN>;
     static bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); configured = true; }
-    if (a.count <= 0) return cudaSuccess;
-    dim3 grid((unsigned)a.count, K, 2);
-    k<<<grid, THREADS, smem, stream>>>(P, a);
+    if (!configured) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    k<<<(unsigned)(count * map.D * K), Pl::THREADS, smem, stream>>>(P, dsc, map, mask, dig);
     return cudaGetLastError();
 }
 
+// Stages 1-3 of the relinearisation for a.count ciphertexts; the caller runs the inverse NTT on
+// a.acc (count*2*K polynomials) and then launch_relin_finish.
 cudaError_t launch_relin(const DeviceParams *P, int logn, int K, const RelinArgs &a, cudaStream_t stream) {
+    if (a.count <= 0) return cudaSuccess;
+    const int n = 1 << logn;
+    DigitMap map{};
+    for (int i = 0; i < K; i++)
+        for (int k = 0; k < a.digits[i]; k++) {
+            if (map.D >= 32) return cudaErrorInvalidValue;
+            map.prime[map.D] = (unsigned char)i;
+            map.shift[map.D] = (unsigned char)(k * a.dbc);
+            map.D++;
+        }
+    const uint64_t mask = (1ULL << a.dbc) - 1;
+    dim3 g1((unsigned)a.count, (unsigned)((long)K * n / 256));
+    relin_scale_kernel<<<g1, 256, 0, stream>>>(P, a.in3, a.dsc);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
     switch (logn) {
-        case 10: return launch_relin_t<10, 128>(P, a, K, stream);
-        case 11: return launch_relin_t<11, 256>(P, a, K, stream);
-        case 12: return launch_relin_t<12, 512>(P, a, K, stream);
-        case 13: return launch_relin_t<13, 1024>(P, a, K, stream);
-        case 14: return launch_relin_t<14, 1024>(P, a, K, stream);
+        case 10: e = launch_digits_t<10>(P, K, a.dsc, map, mask, a.count, a.dig, stream); break;
+        case 11: e = launch_digits_t<11>(P, K, a.dsc, map, mask, a.count, a.dig, stream); break;
+        case 12: e = launch_digits_t<12>(P, K, a.dsc, map, mask, a.count, a.dig, stream); break;
+        case 13: e = launch_digits_t<13>(P, K, a.dsc, map, mask, a.count, a.dig, stream); break;
+        case 14: e = launch_digits_t<14>(P, K, a.dsc, map, mask, a.count, a.dig, stream); break;
         default: return cudaErrorInvalidValue;
     }
+    if (e != cudaSuccess) return e;
+    relin_mac_kernel<<<g1, 256, 0, stream>>>(P, a.dig, a.evk, a, map, a.acc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const RelinArgs &a, cudaStream_t stream) {
+    if (a.count <= 0) return cudaSuccess;
+    dim3 g((unsigned)a.count, (unsigned)(2L * K * n / 256));
+    relin_add_kernel<<<g, 256, 0, stream>>>(P, a.in3, a.acc, a.out);
+    return cudaGetLastError();
 }
 
 // =====================================================================================
@@ -557,18 +617,18 @@ cudaError_t launch_canonicalize(const DeviceParams *P, uint64_t *data, long word
 // =====================================================================================
 __global__ void imad_probe_kernel(int iters, uint64_t *sink) {
     uint64_t a = 0x9E3779B97F4A7C15ULL * (threadIdx.x + 1), b = 0xD1B54A32D192ED03ULL + blockIdx.x;
-    U128 acc[8];
+    Acc7 acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = U128{(uint64_t)i, 0};
+    for (int i = 0; i < 8; i++) acc[i] = acc7_from((uint64_t)i);
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) mac128(acc[i], a + i, b);
-        a += acc[0].hi;
-        b ^= acc[7].lo;
+        for (int i = 0; i < 8; i++) mac7(acc[i], a + i, b);
+        a += acc[0].a3;
+        b ^= acc[7].a0;
     }
     uint64_t s = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) s += acc[i].lo ^ acc[i].hi;
+    for (int i = 0; i < 8; i++) { U128 v = acc7_value(acc[i]); s += v.lo ^ v.hi; }
     if (s == 0x1234567) sink[0] = s;
 }
 

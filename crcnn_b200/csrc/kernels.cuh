@@ -66,8 +66,12 @@ struct RelinArgs {
     int dbc;
     uint64_t *out;
     long count;
+    // scratch (per call): dsc [count][K][n], dig [count][sum digits][K][n], acc [count][2][K][n]
+    uint64_t *dsc, *dig, *acc;
 };
+// stages 1-3 (scale, digit NTTs, key MAC); then the caller inverse-NTTs `acc` and calls launch_relin_finish
 cudaError_t launch_relin(const DeviceParams *P, int logn, int K, const RelinArgs &a, cudaStream_t stream);
+cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const RelinArgs &a, cudaStream_t stream);
 
 // ---- residues stored lazily in [0,4q) (evaluation keys) -> canonical, in place; data = [..][K][n]
 cudaError_t launch_canonicalize(const DeviceParams *P, uint64_t *data, long words, cudaStream_t stream);

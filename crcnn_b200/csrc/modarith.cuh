@@ -47,6 +47,57 @@ CRCNN_HD void mac128(U128 &acc, uint64_t a, uint64_t b) {
     acc.hi += hi + (acc.lo < lo);
 }
 
+// Lazy multiply-accumulate with a split accumulator: `even` (128 bit) collects a0*b0 + a1*b1*2^64,
+// `odd` (96 bit, weight 2^32) collects the cross products a0*b1 + a1*b0.  On the device every
+// mad.lo.cc/madc.hi pair fuses into one IMAD.WIDE.U32 (carry-out) / IMAD.WIDE.U32.X (carry-in), so a
+// 64x64+acc step is 4 IMAD.WIDE + 1 IADD3.X -- no explicit carry compares, no register shuffles.
+// Capacity: `even` holds 2^(128 - 2*bits(q)) products like a plain 128-bit accumulator, `odd` far more.
+struct Acc7 {
+    uint32_t a0, a1, a2, a3;  // even accumulator, little endian
+    uint32_t b0, b1, b2;      // odd accumulator (weight 2^32)
+};
+
+CRCNN_HD Acc7 acc7_zero() { return Acc7{0, 0, 0, 0, 0, 0, 0}; }
+
+CRCNN_HD void mac7(Acc7 &c, uint64_t x, uint64_t w) {
+#if defined(__CUDA_ARCH__)
+    uint32_t x0 = (uint32_t)x, x1 = (uint32_t)(x >> 32), w0 = (uint32_t)w, w1 = (uint32_t)(w >> 32);
+    asm("mad.lo.cc.u32 %0, %7, %9, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %9, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.u32 %3, %8, %10, %3;\n\t"
+        "mad.lo.cc.u32 %4, %7, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %7, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;\n\t"
+        "mad.lo.cc.u32 %4, %8, %9, %4;\n\t"
+        "madc.hi.cc.u32 %5, %8, %9, %5;\n\t"
+        "addc.u32 %6, %6, 0;\n\t"
+        : "+r"(c.a0), "+r"(c.a1), "+r"(c.a2), "+r"(c.a3), "+r"(c.b0), "+r"(c.b1), "+r"(c.b2)
+        : "r"(x0), "r"(x1), "r"(w0), "r"(w1));
+#else
+    typedef unsigned __int128 u128;
+    uint64_t x0 = (uint32_t)x, x1 = x >> 32, w0 = (uint32_t)w, w1 = w >> 32;
+    u128 even = ((u128)(((uint64_t)c.a3 << 32) | c.a2) << 64) | (((uint64_t)c.a1 << 32) | c.a0);
+    even += (u128)(x0 * w0) + ((u128)(x1 * w1) << 64);
+    u128 odd = ((u128)c.b2 << 64) | (((uint64_t)c.b1 << 32) | c.b0);
+    odd += (u128)(x0 * w1) + (u128)(x1 * w0);
+    c.a0 = (uint32_t)even; c.a1 = (uint32_t)(even >> 32); c.a2 = (uint32_t)(even >> 64); c.a3 = (uint32_t)(even >> 96);
+    c.b0 = (uint32_t)odd; c.b1 = (uint32_t)(odd >> 32); c.b2 = (uint32_t)(odd >> 64);
+#endif
+}
+
+// even + odd * 2^32 as a plain 128-bit value
+CRCNN_HD U128 acc7_value(const Acc7 &c) {
+    uint64_t lo = ((uint64_t)c.a1 << 32) | c.a0, hi = ((uint64_t)c.a3 << 32) | c.a2;
+    uint64_t add_lo = (uint64_t)c.b0 << 32, add_hi = ((uint64_t)c.b2 << 32) | c.b1;
+    U128 r;
+    r.lo = lo + add_lo;
+    r.hi = hi + add_hi + (r.lo < lo);
+    return r;
+}
+
+CRCNN_HD Acc7 acc7_from(uint64_t v) { return Acc7{(uint32_t)v, (uint32_t)(v >> 32), 0, 0, 0, 0, 0}; }
+
 CRCNN_HD void add128_64(U128 &acc, uint64_t v) {
     acc.lo += v;
     acc.hi += (acc.lo < v);

@@ -24,7 +24,9 @@ __device__ __forceinline__ int ntt_pad(int i) { return i + (i >> 4); }
 template <int LOGN>
 struct NttPlan {
     static constexpr int N = 1 << LOGN;
-    static constexpr int THREADS = N / 16;
+    static constexpr int THREADS = N / 32;  // 2 groups of 16 (4 of 8) residues per thread and pass
+    // CTAs per SM the shared-memory footprint allows (227 KB usable), capped so 85 registers per thread suffice
+    static constexpr int MIN_CTAS = (227 * 1024) / ((N + N / 16) * 8) > 768 / THREADS ? 768 / THREADS : ((227 * 1024) / ((N + N / 16) * 8) < 1 ? 1 : (227 * 1024) / ((N + N / 16) * 8));
     static constexpr int PASSES = (LOGN + 3) / 4;
     static constexpr int WIDE = LOGN - 3 * PASSES;  // how many passes take 4 stages (the rest take 3)
     static constexpr int SMEM_WORDS = N + N / 16;

@@ -46,8 +46,9 @@ def case_layers(n, t, seed, fname):
         evk=evk, evk_sizes=np.array(sizes, dtype=np.int32), dbc=dbc,
         conv=conv, pool=pool, avgpool=avgpool, bn=bn, sq3=sq3, relin=relin, sq_layer=sq_layer, fc=fc,
         fc_decrypted=dec, fc_budget=budget,
-        enc_vals=np.array([0.0867, -3.25, 0.0, 1.0, 2.8215, -0.4242], dtype=np.float64),
-        enc_plain=np.stack([r.encode(v)[0] for v in [0.0867, -3.25, 0.0, 1.0, 2.8215, -0.4242]]),
+        # floats, as CnnBuilder passes them to FractionalEncoder::encode(double) (cnnBuilder.cpp:41)
+        enc_vals=np.array([0.0867, -3.25, 0.0, 1.0, 2.8215, -0.4242], dtype=np.float32),
+        enc_plain=np.stack([r.encode(float(v))[0] for v in np.array([0.0867, -3.25, 0.0, 1.0, 2.8215, -0.4242], dtype=np.float32)]),
         w0_ntt=r.plain_to_ntt(r.encode(float(conv_w[0]))[0]))
     print(fname, "fc decrypts to", dec, "budget", budget)
 

@@ -69,3 +69,15 @@ def test_cpp_layer_classes_match_oracle(tmp_path):
             assert struct.unpack("<iii", r[32:44]) == (2, n + 1, K)
             got = np.frombuffer(r[44:], dtype=np.uint64).reshape(2, K, n + 1)
             assert np.array_equal(got, want[i]), (run, i)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_seal_test")),
+                    reason="oracle/_ref/dropin_seal_test not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("n,t", [(4096, 1 << 20), (8192, 1 << 30)])
+def test_seal_mode_dropin_against_reference_classes(n, t):
+    """One process, real SEAL types: the reference's layer classes vs crcnn_b200's on the same encrypted
+    image and encoded weights; every layer memcmp-equal, decrypted scores / label / noise budget equal."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "dropin_seal_test")
+    res = subprocess.run([exe, str(n), str(t)], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "DROPIN OK" in res.stdout, res.stdout[-2000:] + res.stderr[-500:]
+    assert res.stdout.count("bit-identical") == 8
