@@ -37,6 +37,7 @@ struct crcnn_tensor {
 
 struct crcnn_plain {
     long count;
+    bool sparse_shape = false;       // every plaintext supported in [0,64) U [n-32,n) (FractionalEncoder output)
     std::vector<uint32_t> off, idx;  // host copy of the sparse form
     std::vector<uint64_t> val;
     uint32_t *d_off = nullptr, *d_idx = nullptr;
@@ -157,7 +158,7 @@ enum PlainForm { PF_NTT_MUL, PF_NTT_ADD, PF_COEF_ADD };
 int expand_range(crcnn_ctx *ctx, crcnn_plain *p, long first, long count, PlainForm f, uint64_t *dst) {
     ProfScope ps(ctx, KC_PLAIN_EXPAND);
     CU(launch_plain_expand(ctx->dP, ctx->logn, ctx->K, p->d_off, p->d_idx, p->d_val, first, count,
-                           f == PF_NTT_MUL ? 0 : 1, f != PF_COEF_ADD, dst, ctx->stream));
+                           (f == PF_NTT_MUL ? 0 : 1) | (p->sparse_shape ? 2 : 0), f != PF_COEF_ADD, dst, ctx->stream));
     return CRCNN_OK;
 }
 
@@ -175,6 +176,9 @@ int make_plain(crcnn_ctx *ctx, std::vector<uint32_t> &&off, std::vector<uint32_t
     auto *p = new crcnn_plain();
     p->count = (long)off.size() - 1;
     p->off = std::move(off); p->idx = std::move(idx); p->val = std::move(val);
+    p->sparse_shape = true;
+    for (uint32_t ix : p->idx)
+        if (ix >= 64 && ix < (uint32_t)(ctx->n - 32)) { p->sparse_shape = false; break; }
     int rc = dev_alloc(ctx, p->off.size() * 4, (void **)&p->d_off);
     if (!rc) rc = dev_alloc(ctx, std::max<size_t>(p->idx.size(), 1) * 4, (void **)&p->d_idx);
     if (!rc) rc = dev_alloc(ctx, std::max<size_t>(p->val.size(), 1) * 8, (void **)&p->d_val);
@@ -299,8 +303,10 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
     for (int s = 0; s < slots && e == cudaSuccess; s++) {
         e = up(hp.w[s], &hp.d.tab[s].w);
         if (e == cudaSuccess) e = up(hp.wp[s], &hp.d.tab[s].wp);
-        if (e == cudaSuccess) e = up(hp.iw[s], &hp.d.tab[s].iw);
-        if (e == cudaSuccess) e = up(hp.iwp[s], &hp.d.tab[s].iwp);
+        if (e == cudaSuccess) e = up(hp.iwf[s], &hp.d.tab[s].iw);
+        if (e == cudaSuccess) e = up(hp.iwfp[s], &hp.d.tab[s].iwp);
+        hp.d.tab[s].tf = nullptr;
+        if (e == cudaSuccess && s < K) e = up(hp.tf[s], &hp.d.tab[s].tf);
     }
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->dP, sizeof(DeviceParams));
     if (e == cudaSuccess) e = cudaMemcpy(c->dP, &hp.d, sizeof(DeviceParams), cudaMemcpyHostToDevice);

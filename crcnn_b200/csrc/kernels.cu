@@ -15,7 +15,7 @@ ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, 
     const NttTable tb = P->tab[slot_base + (int)(p % slot_count)];
     uint64_t *poly = data + p * (1L << LOGN);
     ntt_forward_to_smem<LOGN>(sm, poly, tb);
-    smem_store_poly_canonical<LOGN>(sm, poly, tb.mod.q);
+    smem_store_poly_canonical<LOGN>(sm, poly, tb.mod);
 }
 
 template <int LOGN>
@@ -79,25 +79,46 @@ plain_expand_kernel(const DeviceParams *__restrict__ P, int K, const uint32_t *_
     const int j = (int)(b % K);
     const NttTable tb = P->tab[j];
     const uint64_t half = P->half;
+    const int sparse_shape = (mode >> 1) & 1;  // bit 1: every plaintext of the pack has the FractionalEncoder shape
+    mode &= 1;                                 // bit 0: 0 lifted (multiplicative), 1 Delta-scaled (additive)
     for (int i = threadIdx.x; i < NttPlan<LOGN>::SMEM_WORDS; i += blockDim.x) sm[i] = 0;
     __syncthreads();
     const uint32_t lo = offsets[first + pi], hi = offsets[first + pi + 1];
-    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-        uint64_t c = val[e], v;
-        if (mode == 0) {
-            v = c >= half ? c + P->lift_inc[j] : c;  // evaluator.cpp:1475-1484
-        } else {                                     // evaluator.cpp:1171-1190
-            U128 z = mul128(P->delta[j], c);
-            if (c >= half) add128_64(z, P->rho[j]);
-            v = barrett128(z, tb.mod);
-        }
-        sm[ntt_pad((int)idx[e])] = v;
-    }
-    __syncthreads();
+    auto residue = [&](uint64_t c) -> uint64_t {
+        if (mode == 0) return c >= half ? c + P->lift_inc[j] : c;  // evaluator.cpp:1475-1484
+        U128 z = mul128(P->delta[j], c);                            // evaluator.cpp:1171-1190
+        if (c >= half) add128_64(z, P->rho[j]);
+        return barrett128(z, tb.mod);
+    };
     uint64_t *dst = out + b * N;
+    if (to_ntt && sparse_shape) {
+        // FractionalEncoder-shaped plaintext (support in [0,64) U [n-32,n)): the first SKIP stages of
+        // the Cooley-Tukey transform only copy the low part into every block and scale the top part by a
+        // per-block constant (params.cpp, tf tables), so the blocks are written directly and the
+        // schedule resumes at the first dense pass.
+        constexpr int SKIP = sparse_skip_stages(LOGN);
+        constexpr int NB = 1 << SKIP, M = N >> SKIP;
+        const uint32_t cnt = (hi - lo) * NB;
+        for (uint32_t w = threadIdx.x; w < cnt; w += blockDim.x) {
+            const uint32_t e = lo + w / NB, blk = w % NB;
+            const int ix = (int)idx[e];
+            uint64_t v = residue(val[e]);
+            if (ix < 64) {
+                sm[ntt_pad((int)blk * M + ix)] = v;
+            } else {
+                sm[ntt_pad((int)blk * M + M - (N - ix))] = mulmod(v, __ldg(tb.tf + blk), tb.mod);
+            }
+        }
+        __syncthreads();
+        ntt_forward_in_smem<LOGN, NttPlan<LOGN>::skip_passes()>(sm, tb);
+        smem_store_poly_canonical<LOGN>(sm, dst, tb.mod);
+        return;
+    }
+    for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) sm[ntt_pad((int)idx[e])] = residue(val[e]);
+    __syncthreads();
     if (to_ntt) {
         ntt_forward_in_smem<LOGN>(sm, tb);
-        smem_store_poly_canonical<LOGN>(sm, dst, tb.mod.q);
+        smem_store_poly_canonical<LOGN>(sm, dst, tb.mod);
     } else {
         for (int i = threadIdx.x; i < N; i += blockDim.x) dst[i] = sm[ntt_pad(i)];
     }
@@ -153,7 +174,11 @@ mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
     const int j = blockIdx.y / slices_per_limb;
     const int c = (blockIdx.y % slices_per_limb) * MAC_THREADS + threadIdx.x;
     const int tiles_m = (a.M + TM - 1) / TM;
-    const int tm = blockIdx.x % tiles_m, tn = blockIdx.x / tiles_m;
+    // position tiles fastest: CTAs that stream the same weight rows (fc: 164 GB of them) run back to back
+    // and hit L2 instead of re-reading HBM once per position tile
+    const int tiles_n = (a.Npos + TN - 1) / TN;
+    const int tn = blockIdx.x % tiles_n, tm = blockIdx.x / tiles_n;
+    (void)tiles_m;
     const int m_base = tm * TM, p_base = tn * TN;
     const Mod mod = P->tab[j].mod;
     const long limb_off = (long)j * n + c;
@@ -453,7 +478,7 @@ ntt_fwd_digits_kernel(const DeviceParams *__restrict__ P, const uint64_t *__rest
     for (int e = threadIdx.x; e < N; e += blockDim.x) sm[ntt_pad(e)] = (__ldg(src + e) >> shift) & mask;
     __syncthreads();
     ntt_forward_in_smem<LOGN>(sm, tb);
-    smem_store_poly_canonical<LOGN>(sm, dig + b * N, tb.mod.q);
+    smem_store_poly_canonical<LOGN>(sm, dig + b * N, tb.mod);
 }
 
 __global__ void __launch_bounds__(256)

@@ -122,6 +122,13 @@ CRCNN_HD uint64_t barrett128(U128 z, const Mod &m) {
     return r >= m.q ? r - m.q : r;
 }
 
+// x mod q for any 64-bit x: the high word of floor(2^128/q) is floor(2^64/q), so the quotient
+// estimate is at most one short and one conditional subtraction finishes.
+CRCNN_HD uint64_t reduce64(uint64_t x, const Mod &m) {
+    uint64_t r = x - mulhi64(x, m.r1) * m.q;
+    return r >= m.q ? r - m.q : r;
+}
+
 CRCNN_HD uint64_t mulmod(uint64_t a, uint64_t b, const Mod &m) { return barrett128(mul128(a, b), m); }
 
 CRCNN_HD uint64_t addmod(uint64_t a, uint64_t b, uint64_t q) {

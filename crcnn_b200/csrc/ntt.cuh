@@ -3,16 +3,21 @@
 // One CTA transforms one limb-polynomial (n residues of one prime).  The transform is the same
 // map as the reference's ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey
 // (SEAL/seal/util/smallntt.cpp:195-375, smallntt.h:210-258): Cooley-Tukey forward with
-// bit-reversed output, Gentleman-Sande inverse with n^-1 folded into pre-halved inverse roots,
-// using the reference's own table order (root_powers[bitrev(i)] = psi^i), so NTT-form data made by
-// SEAL (evaluation keys, NTT plaintexts) is interchangeable.  Outputs are canonical [0, q).
+// bit-reversed output, Gentleman-Sande inverse, in the reference's own table order
+// (root_powers[bitrev(i)] = psi^i), so NTT-form data made by SEAL (evaluation keys, NTT plaintexts)
+// is interchangeable.  Outputs are canonical [0, q); only the lazy intermediate ranges differ:
+//   * forward: for q < 2^58 the Harvey correction of X is dropped altogether -- values grow by 2q per
+//     stage (< 30q < 2^63 after 14 stages) and are reduced once at the final store; the Shoup product
+//     accepts any 64-bit operand.  61-bit moduli (the Bsk primes of `square`) keep the correction.
+//   * inverse: the n^-1 factor is applied once at the end (one Shoup product per residue) instead of a
+//     halving in every butterfly, so the tables hold the plain inverse powers.
+// Both remove ALU-pipe work, which ncu showed to be the binding pipe (profiles/r01b_*).
 //
-// Schedule: log2(n) stages are grouped into passes of 4 or 3 stages done in registers
-// (16 or 8 residues per thread); between passes the polynomial lives in shared memory with one
-// pad word every 16 residues, which makes both the strided passes and the final contiguous pass
-// bank-conflict free.  The first forward pass reads HBM directly (coalesced, stride n/16), the
-// last inverse pass writes HBM directly; the contiguous end is staged through shared memory so
-// every global access is a full-warp contiguous 256 B segment.
+// Schedule: log2(n) stages are grouped into passes of 3 or 4 stages done in registers
+// (8 or 16 residues per thread and group); between passes the polynomial lives in shared memory
+// with one pad word every 16 residues, which makes the strided passes (gaps >= 32 or 16) and the
+// final contiguous pass bank-conflict free.  The first forward pass reads HBM directly (coalesced),
+// the last inverse pass writes HBM directly; the contiguous ends are staged through shared memory.
 #pragma once
 #include "modarith.cuh"
 #include "params.h"
@@ -25,35 +30,45 @@ template <int LOGN>
 struct NttPlan {
     static constexpr int N = 1 << LOGN;
     static constexpr int THREADS = N / 32;  // 2 groups of 16 (4 of 8) residues per thread and pass
+    static constexpr int SMEM_WORDS = N + N / 16;
     // CTAs per SM the shared-memory footprint allows (227 KB usable), capped so 85 registers per thread suffice
-    static constexpr int MIN_CTAS = (227 * 1024) / ((N + N / 16) * 8) > 768 / THREADS ? 768 / THREADS : ((227 * 1024) / ((N + N / 16) * 8) < 1 ? 1 : (227 * 1024) / ((N + N / 16) * 8));
+    static constexpr int FIT = (227 * 1024) / (SMEM_WORDS * 8);
+    static constexpr int MIN_CTAS = FIT > 768 / THREADS ? 768 / THREADS : (FIT < 1 ? 1 : FIT);
     static constexpr int PASSES = (LOGN + 3) / 4;
     static constexpr int WIDE = LOGN - 3 * PASSES;  // how many passes take 4 stages (the rest take 3)
-    static constexpr int SMEM_WORDS = N + N / 16;
     // wide passes go last so the gaps seen by shared memory are >=32, 16 and 1 only (conflict free)
     __host__ __device__ static constexpr int bits(int pass) { return pass >= PASSES - WIDE ? 4 : 3; }
+    // passes covered by sparse_skip_stages(LOGN)
+    __host__ __device__ static constexpr int skip_passes() {
+        int st = 0, p = 0;
+        while (st < sparse_skip_stages(LOGN)) { st += bits(p); p++; }
+        return p;
+    }
 };
 
+// moduli below 2^58 never need the per-stage correction (2q growth per stage stays below 2^63)
+__device__ __forceinline__ bool ntt_needs_correction(uint64_t q) { return (q >> 58) != 0; }
+
+template <bool CORR>
 __device__ __forceinline__ void ct_butterfly(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twoq) {
-    // Harvey butterfly: x, y in [0,4q) -> [0,4q)
-    uint64_t X = x >= twoq ? x - twoq : x;
+    // Harvey butterfly; with CORR x,y in [0,4q) -> [0,4q), without it the bound grows by 2q per stage
+    uint64_t X = (CORR && x >= twoq) ? x - twoq : x;
     uint64_t Q = mulshoup_lazy(y, W, Wp, q);
     x = X + Q;
     y = X + twoq - Q;
 }
 
 __device__ __forceinline__ void gs_butterfly(uint64_t &u, uint64_t &v, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twoq) {
-    // u, v in [0,2q) -> [0,2q); W = (psi^-k)/2 so every stage also halves
+    // u, v in [0,2q) -> [0,2q); W = psi^-k (no halving here, n^-1 is applied at the end)
     uint64_t T = u + twoq - v;
     uint64_t S = u + v;
-    S = S >= twoq ? S - twoq : S;
-    u = (S + ((S & 1) ? q : 0)) >> 1;
+    u = S >= twoq ? S - twoq : S;
     v = mulshoup_lazy(T, W, Wp, q);
 }
 
 // B forward stages on 2^B residues spaced g apart; m0 = number of blocks at the first stage,
 // blk = this group's block index at that stage.
-template <int B>
+template <int B, bool CORR>
 __device__ __forceinline__ void fwd_group(uint64_t (&x)[1 << B], const uint64_t *__restrict__ w,
                                           const uint64_t *__restrict__ wp, uint64_t q, uint64_t twoq, int m0, int blk) {
 #pragma unroll
@@ -64,7 +79,7 @@ __device__ __forceinline__ void fwd_group(uint64_t (&x)[1 << B], const uint64_t 
             const int lb = pr >> (B - 1 - s), a = pr & ((1 << (B - 1 - s)) - 1);
             const int ia = (lb << (B - s)) + a, ib = ia + (1 << (B - 1 - s));
             const int tw = ((m0 + blk) << s) + lb;
-            ct_butterfly(x[ia], x[ib], __ldg(w + tw), __ldg(wp + tw), q, twoq);
+            ct_butterfly<CORR>(x[ia], x[ib], __ldg(w + tw), __ldg(wp + tw), q, twoq);
         }
     }
 }
@@ -87,7 +102,7 @@ __device__ __forceinline__ void inv_group(uint64_t (&x)[1 << B], const uint64_t 
 }
 
 // One forward pass over the whole polynomial.  SRC_GLOBAL: read `gsrc` (unpadded) instead of smem.
-template <int LOGN, int B, bool SRC_GLOBAL>
+template <int LOGN, int B, bool SRC_GLOBAL, bool CORR>
 __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restrict__ gsrc, const NttTable &tb, int m0, int g) {
     constexpr int N = 1 << LOGN;
     const uint64_t q = tb.mod.q, twoq = 2 * q;
@@ -97,12 +112,13 @@ __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restric
         uint64_t x[1 << B];
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) x[k] = SRC_GLOBAL ? gsrc[base + k * g] : sm[ntt_pad(base + k * g)];
-        fwd_group<B>(x, tb.w, tb.wp, q, twoq, m0, blk);
+        fwd_group<B, CORR>(x, tb.w, tb.wp, q, twoq, m0, blk);
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) sm[ntt_pad(base + k * g)] = x[k];
     }
 }
 
+// DST_GLOBAL marks the last pass: the n^-1 scaling and the canonical store happen there.
 template <int LOGN, int B, bool DST_GLOBAL>
 __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gdst, const NttTable &tb, int g) {
     constexpr int N = 1 << LOGN;
@@ -118,7 +134,7 @@ __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gd
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) {
             if (DST_GLOBAL) {
-                uint64_t v = x[k];
+                uint64_t v = mulshoup_lazy(x[k], tb.ninv, tb.ninvp, q);
                 gdst[base + k * g] = v >= q ? v - q : v;
             } else {
                 sm[ntt_pad(base + k * g)] = x[k];
@@ -127,36 +143,38 @@ __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gd
     }
 }
 
-// Forward transform of one polynomial: src (global, n words, values < 4q) -> sm (padded, lazy [0,4q)).
-template <int LOGN>
-__device__ __forceinline__ void ntt_forward_to_smem(uint64_t *sm, const uint64_t *__restrict__ src, const NttTable &tb) {
+template <int LOGN, int FIRST_PASS, bool CORR>
+__device__ __forceinline__ void ntt_forward_passes(uint64_t *sm, const uint64_t *__restrict__ src, const NttTable &tb) {
     using P = NttPlan<LOGN>;
     int m0 = 1, g = P::N;
-    g >>= P::bits(0);
-    if (P::bits(0) == 4) fwd_pass<LOGN, 4, true>(sm, src, tb, m0, g); else fwd_pass<LOGN, 3, true>(sm, src, tb, m0, g);
-    m0 <<= P::bits(0);
-    __syncthreads();
 #pragma unroll
-    for (int p = 1; p < P::PASSES; p++) {
+    for (int p = 0; p < FIRST_PASS; p++) { g >>= P::bits(p); m0 <<= P::bits(p); }
+#pragma unroll
+    for (int p = FIRST_PASS; p < P::PASSES; p++) {
         g >>= P::bits(p);
-        if (P::bits(p) == 4) fwd_pass<LOGN, 4, false>(sm, nullptr, tb, m0, g); else fwd_pass<LOGN, 3, false>(sm, nullptr, tb, m0, g);
+        if (p == 0 && src != nullptr) {
+            if (P::bits(p) == 4) fwd_pass<LOGN, 4, true, CORR>(sm, src, tb, m0, g); else fwd_pass<LOGN, 3, true, CORR>(sm, src, tb, m0, g);
+        } else {
+            if (P::bits(p) == 4) fwd_pass<LOGN, 4, false, CORR>(sm, nullptr, tb, m0, g); else fwd_pass<LOGN, 3, false, CORR>(sm, nullptr, tb, m0, g);
+        }
         m0 <<= P::bits(p);
         __syncthreads();
     }
 }
 
-// Forward transform when the polynomial is already in padded shared memory (values < 4q).
+// Forward transform of one polynomial: src (global, n words, canonical or < 4q) -> sm (padded, lazy).
 template <int LOGN>
+__device__ __forceinline__ void ntt_forward_to_smem(uint64_t *sm, const uint64_t *__restrict__ src, const NttTable &tb) {
+    if (ntt_needs_correction(tb.mod.q)) ntt_forward_passes<LOGN, 0, true>(sm, src, tb);
+    else ntt_forward_passes<LOGN, 0, false>(sm, src, tb);
+}
+
+// Forward transform when the polynomial is already in padded shared memory (values < 4q).
+// FIRST_PASS > 0 resumes the schedule after the passes a sparse-input expansion has replaced.
+template <int LOGN, int FIRST_PASS = 0>
 __device__ __forceinline__ void ntt_forward_in_smem(uint64_t *sm, const NttTable &tb) {
-    using P = NttPlan<LOGN>;
-    int m0 = 1, g = P::N;
-#pragma unroll
-    for (int p = 0; p < P::PASSES; p++) {
-        g >>= P::bits(p);
-        if (P::bits(p) == 4) fwd_pass<LOGN, 4, false>(sm, nullptr, tb, m0, g); else fwd_pass<LOGN, 3, false>(sm, nullptr, tb, m0, g);
-        m0 <<= P::bits(p);
-        __syncthreads();
-    }
+    if (ntt_needs_correction(tb.mod.q)) ntt_forward_passes<LOGN, FIRST_PASS, true>(sm, nullptr, tb);
+    else ntt_forward_passes<LOGN, FIRST_PASS, false>(sm, nullptr, tb);
 }
 
 // Inverse transform of the polynomial in padded shared memory (values < 2q) -> dst (global, canonical).
@@ -174,33 +192,15 @@ __device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__
     if (P::bits(0) == 4) inv_pass<LOGN, 4, true>(sm, dst, tb, g); else inv_pass<LOGN, 3, true>(sm, dst, tb, g);
 }
 
-// Inverse transform leaving the result (lazy, [0,2q)) in shared memory.
-template <int LOGN>
-__device__ __forceinline__ void ntt_inverse_in_smem(uint64_t *sm, const NttTable &tb) {
-    using P = NttPlan<LOGN>;
-    int g = 1;
-#pragma unroll
-    for (int p = P::PASSES - 1; p >= 0; p--) {
-        if (P::bits(p) == 4) inv_pass<LOGN, 4, false>(sm, nullptr, tb, g); else inv_pass<LOGN, 3, false>(sm, nullptr, tb, g);
-        g <<= P::bits(p);
-        __syncthreads();
-    }
-}
-
 // Coalesced copies between global (unpadded) and shared (padded).
 template <int LOGN>
 __device__ __forceinline__ void smem_load_poly(uint64_t *sm, const uint64_t *__restrict__ src) {
     for (int i = threadIdx.x; i < (1 << LOGN); i += blockDim.x) sm[ntt_pad(i)] = src[i];
 }
+// Lazy forward output (any value below 2^63) -> canonical residues in global memory.
 template <int LOGN>
-__device__ __forceinline__ void smem_store_poly_canonical(const uint64_t *sm, uint64_t *__restrict__ dst, uint64_t q) {
-    // input lazy in [0,4q)
-    const uint64_t twoq = 2 * q;
-    for (int i = threadIdx.x; i < (1 << LOGN); i += blockDim.x) {
-        uint64_t v = sm[ntt_pad(i)];
-        v = v >= twoq ? v - twoq : v;
-        dst[i] = v >= q ? v - q : v;
-    }
+__device__ __forceinline__ void smem_store_poly_canonical(const uint64_t *sm, uint64_t *__restrict__ dst, const Mod &mod) {
+    for (int i = threadIdx.x; i < (1 << LOGN); i += blockDim.x) dst[i] = reduce64(sm[ntt_pad(i)], mod);
 }
 
 }  // namespace crcnn

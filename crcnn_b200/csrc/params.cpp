@@ -98,20 +98,25 @@ static void build_tables(HostParams &hp, int slot, int logn, const Mod &m) {
         throw std::invalid_argument("modulus " + std::to_string(m.q) + " has no primitive 2n-th root of unity");
     uint64_t psi_inv = inv_mod(psi, m.q);
     auto &w = hp.w[slot], &wp = hp.wp[slot], &iw = hp.iw[slot], &iwp = hp.iwp[slot];
-    w.assign(n, 0); wp.assign(n, 0); iw.assign(n, 0); iwp.assign(n, 0);
+    auto &iwf = hp.iwf[slot], &iwfp = hp.iwfp[slot];
+    w.assign(n, 0); wp.assign(n, 0); iw.assign(n, 0); iwp.assign(n, 0); iwf.assign(n, 0); iwfp.assign(n, 0);
     uint64_t pw = 1, ipw = 1;
     for (int i = 0; i < n; i++) {
         uint32_t r = bit_reverse((uint32_t)i, logn);
         w[r] = pw;
         // inverse power halved mod q (q odd): x/2 = (x + (x odd ? q : 0)) >> 1
         iw[r] = (ipw & 1) ? (uint64_t)(((u128)ipw + m.q) >> 1) : (ipw >> 1);
+        iwf[r] = ipw;
         pw = mulmod(pw, psi, m);
         ipw = mulmod(ipw, psi_inv, m);
     }
     for (int i = 0; i < n; i++) {
         wp[i] = (uint64_t)((((u128)w[i]) << 64) / m.q);
         iwp[i] = (uint64_t)((((u128)iw[i]) << 64) / m.q);
+        iwfp[i] = (uint64_t)((((u128)iwf[i]) << 64) / m.q);
     }
+    hp.d.tab[slot].ninv = inv_mod((uint64_t)n % m.q, m.q);
+    hp.d.tab[slot].ninvp = (uint64_t)((((u128)hp.d.tab[slot].ninv) << 64) / m.q);
     hp.roots[slot] = psi;
 }
 
@@ -137,7 +142,7 @@ HostParams derive_params(int n, int K, const uint64_t *q, uint64_t t) {
     d.L = K + ((32 + bits_of(t) + total_bits >= 61 * K + 61) ? 1 : 0);
     d.S = d.L + 1;
     int slots = K + d.S;
-    hp.w.resize(slots); hp.wp.resize(slots); hp.iw.resize(slots); hp.iwp.resize(slots); hp.roots.resize(slots);
+    hp.w.resize(slots); hp.wp.resize(slots); hp.iw.resize(slots); hp.iwp.resize(slots); hp.iwf.resize(slots); hp.iwfp.resize(slots); hp.roots.resize(slots);
 
     std::vector<uint64_t> bsk(d.S);
     for (int i = 0; i < d.L; i++) bsk[i] = kAuxPrimes[i];
@@ -145,6 +150,24 @@ HostParams derive_params(int n, int K, const uint64_t *q, uint64_t t) {
     for (int i = 0; i < K; i++) { d.tab[i].mod = make_mod(q[i]); build_tables(hp, i, logn, d.tab[i].mod); }
     for (int k = 0; k < d.S; k++) { d.tab[K + k].mod = make_mod(bsk[k]); build_tables(hp, K + k, logn, d.tab[K + k].mod); }
     for (int s = 0; s < slots; s++) d.t_mod[s] = t % d.tab[s].mod.q;
+    // Sparse-input forward NTT: after `skip` Cooley-Tukey stages a coefficient sitting in the top 32
+    // positions of the polynomial has only been multiplied, stage by stage, by +W (lower child block) or
+    // -W (upper child block); block b therefore holds it times  prod_s (+-) w[2^s + (b >> (skip - s))].
+    hp.tf.resize(K);
+    const int skip = sparse_skip_stages(logn);
+    for (int j = 0; j < K; j++) {
+        const Mod &m = d.tab[j].mod;
+        hp.tf[j].assign((size_t)1 << skip, 0);
+        for (int b = 0; b < (1 << skip); b++) {
+            uint64_t c = 1;
+            for (int s = 0; s < skip; s++) {
+                uint64_t w = hp.w[j][((size_t)1 << s) + (b >> (skip - s))];
+                if ((b >> (skip - 1 - s)) & 1) w = negmod(w, m.q);
+                c = mulmod(c, w, m);
+            }
+            hp.tf[j][b] = c;
+        }
+    }
 
     Mod mt = make_mod(kMtilde), msk = make_mod(kMsk), tm = make_mod(t);
     // Delta = floor(Q/t), rho = Q - t*Delta = Q mod t.  t*Delta = Q - rho, so modulo q_j

@@ -28,9 +28,18 @@ struct NttTable {
     Mod mod;
     const uint64_t *w;    // root_powers            (psi^bitrev(i))
     const uint64_t *wp;   // scaled_root_powers     floor(w * 2^64 / q)
-    const uint64_t *iw;   // inv_root_powers_div_two
+    const uint64_t *iw;   // inverse root powers psi^-bitrev(i) (NOT pre-halved: the kernels scale by n^-1 once at the end)
     const uint64_t *iwp;  // its scaled companion
+    uint64_t ninv, ninvp; // n^-1 mod q and floor(n^-1 * 2^64 / q)
+    const uint64_t *tf;   // top-block factors for the sparse-input forward transform (see ntt.cuh), 2^skip entries
 };
+
+// Forward-NTT stages that can be skipped for FractionalEncoder-shaped plaintexts (support in
+// [0,64) U [n-32,n)): whole passes of the NttPlan schedule while the block length stays >= 128.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr int sparse_skip_stages(int logn) { return logn == 13 ? 6 : logn == 12 ? 4 : logn == 14 ? 6 : 3; }
 
 // Everything the kernels read; lives in device global memory, one per context.
 struct DeviceParams {
@@ -61,8 +70,10 @@ struct DeviceParams {
 // Host copy: the scalar part of DeviceParams plus the tables as vectors.
 struct HostParams {
     DeviceParams d{};                               // table pointers left null
-    std::vector<std::vector<uint64_t>> w, wp, iw, iwp;  // per modulus, n entries
+    std::vector<std::vector<uint64_t>> w, wp, iw, iwp;  // per modulus, n entries (iw/iwp = SEAL's pre-halved inverse tables, for cross-checks)
+    std::vector<std::vector<uint64_t>> iwf, iwfp;       // un-halved inverse powers: what the device uses
     std::vector<uint64_t> roots;                    // minimal primitive 2n-th root per modulus
+    std::vector<std::vector<uint64_t>> tf;          // per coefficient prime: top-block factors
 };
 
 // Throws std::invalid_argument on parameters the reference's SEALContext would reject
