@@ -259,6 +259,7 @@ def main_b200(args, rank, world, local_rank):
     B, K, n = args.batch, len(PRIMES), N_POLY
     eng = Engine(n, PRIMES, T_PLAIN, device=local_rank)
     stream = torch.cuda.Stream()
+    copy_stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(1000 + rank)
     evk_words, sizes, dbc = synth_evk(rng, PRIMES, n)
@@ -321,8 +322,13 @@ def main_b200(args, rank, world, local_rank):
         barrier()
         ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev2[0].record(stream)
+        # double-buffered: the H2D copy of step s+1 runs on a copy stream while step s computes
+        x_next = eng.upload_ptr_on(host_in.data_ptr(), B * per_image, copy_stream.cuda_stream)
         for s in range(args.steps):
-            x = eng.upload_ptr(host_in.data_ptr(), B * per_image)
+            eng.wait_stream(copy_stream.cuda_stream)
+            x = x_next
+            if s + 1 < args.steps:
+                x_next = eng.upload_ptr_on(host_in.data_ptr(), B * per_image, copy_stream.cuda_stream)
             y = net.forward(x, batch=B)
             eng.download_ptr(y, host_out.data_ptr())
             x.free(); y.free()

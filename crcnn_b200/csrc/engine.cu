@@ -379,6 +379,33 @@ int crcnn_tensor_upload_ex(crcnn_ctx *ctx, const uint64_t *host, long count, int
     *out = t;
     return CRCNN_OK;
 }
+int crcnn_tensor_upload_on(crcnn_ctx *ctx, const uint64_t *host, long count, int size, int ntt_form, void *copy_stream,
+                           crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(host && out && count >= 0 && size >= 2 && size <= 3, "bad tensor upload arguments");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    auto *t = new crcnn_tensor{count, size, ntt_form ? 1 : 0, nullptr};
+    const size_t n = ctx->n, rows = (size_t)count * size * ctx->K;
+    if (rows) {
+        cudaError_t e = cudaMallocAsync((void **)&t->d, rows * n * 8, cs);
+        if (e == cudaSuccess) e = cudaMemcpy2DAsync(t->d, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, cs);
+        if (e != cudaSuccess) { delete t; return fail(ctx, e == cudaErrorMemoryAllocation ? CRCNN_ERR_OUT_OF_MEMORY : CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = t;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_wait_stream(crcnn_ctx *ctx, void *other_stream) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, (cudaStream_t)other_stream));
+    CU(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    CU(cudaEventDestroy(ev));
+    return CRCNN_OK;
+}
+
 int crcnn_tensor_upload(crcnn_ctx *ctx, const uint64_t *host, long count, int size, crcnn_tensor **out) {
     return crcnn_tensor_upload_ex(ctx, host, count, size, 0, out);
 }

@@ -1,6 +1,7 @@
 // Device kernels of the encrypted-forward hot path (sm_100a).  See kernels.cuh for the contracts.
 #include "kernels.cuh"
 #include "ntt.cuh"
+#include <cstdlib>
 
 namespace crcnn {
 
@@ -166,7 +167,7 @@ cudaError_t launch_plain_expand(const DeviceParams *P, int logn, int K, const ui
 constexpr int MAC_THREADS = 128;
 
 template <int TM, int TN>
-__global__ void __launch_bounds__(MAC_THREADS)
+__global__ void __launch_bounds__(MAC_THREADS, (TM * TN <= 4) ? 4 : 2)
 mac_kernel(const DeviceParams *__restrict__ P, MacArgs a) {
     extern __shared__ int s_idx[];  // [TN][R]
     const int n = a.n, K = a.K, R = a.R;
@@ -268,8 +269,21 @@ static cudaError_t launch_mac_t(const DeviceParams *P, const MacArgs &a, cudaStr
 
 cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t stream) {
     if (a.M <= 0 || a.Npos <= 0) return cudaSuccess;
-    if (a.Npos == 1) return launch_mac_t<8, 1>(P, a, stream);
-    return launch_mac_t<4, 2>(P, a, stream);
+    // tile override for tuning sweeps: CRCNN_MAC_TILE=<TM><TN>, e.g. 22
+    static const int forced = [] { const char *e = getenv("CRCNN_MAC_TILE"); return e ? atoi(e) : 0; }();
+    switch (forced) {
+        case 42: return launch_mac_t<4, 2>(P, a, stream);
+        case 22: return launch_mac_t<2, 2>(P, a, stream);
+        case 24: return launch_mac_t<2, 4>(P, a, stream);
+        case 41: return launch_mac_t<4, 1>(P, a, stream);
+        case 21: return launch_mac_t<2, 1>(P, a, stream);
+        case 81: return launch_mac_t<8, 1>(P, a, stream);
+        case 12: return launch_mac_t<1, 2>(P, a, stream);
+        case 14: return launch_mac_t<1, 4>(P, a, stream);
+        default: break;
+    }
+    if (a.Npos == 1) return launch_mac_t<4, 1>(P, a, stream);
+    return launch_mac_t<2, 2>(P, a, stream);
 }
 
 // =====================================================================================
@@ -278,17 +292,28 @@ cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t str
 __global__ void __launch_bounds__(256)
 pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, const int *__restrict__ in_index,
             int R, const uint64_t *__restrict__ scale, uint64_t *__restrict__ out) {
+    // two adjacent residues per thread: 128-bit loads and stores
     const int n = P->n, K = P->K;
     const long ctw = 2L * K * n;
     const long o = blockIdx.x;
-    const long word = (long)blockIdx.y * 256 + threadIdx.x;  // within the ciphertext
+    const long word = ((long)blockIdx.y * 256 + threadIdx.x) * 2;  // within the ciphertext
     const int j = (int)((word / n) % K);
     const Mod mod = P->tab[j].mod;
-    U128 s{0, 0};
-    for (int r = 0; r < R; r++) add128_64(s, __ldg(in + (long)__ldg(in_index + o * R + r) * ctw + word));
-    uint64_t v = barrett128(s, mod);
-    if (scale) v = mulmod(v, __ldg(scale + (long)j * n + word % n), mod);
-    out[o * ctw + word] = v;
+    U128 s0{0, 0}, s1{0, 0};
+    for (int r = 0; r < R; r++) {
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word));
+        add128_64(s0, v.x);
+        add128_64(s1, v.y);
+    }
+    ulonglong2 res;
+    res.x = barrett128(s0, mod);
+    res.y = barrett128(s1, mod);
+    if (scale) {
+        const ulonglong2 sc = __ldg(reinterpret_cast<const ulonglong2 *>(scale + (long)j * n + word % n));
+        res.x = mulmod(res.x, sc.x, mod);
+        res.y = mulmod(res.y, sc.y, mod);
+    }
+    *reinterpret_cast<ulonglong2 *>(out + o * ctw + word) = res;
 }
 
 // =====================================================================================
@@ -300,15 +325,22 @@ bn_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, i
     const int n = P->n, K = P->K;
     const long pw = (long)K * n, ctw = 2 * pw;
     const long ct = blockIdx.x;
-    const long word = (long)blockIdx.y * 256 + threadIdx.x;
+    const long word = ((long)blockIdx.y * 256 + threadIdx.x) * 2;  // two adjacent residues per thread
     const int poly = (int)(word / pw);
     const long lw = word - poly * pw;  // j*n + c
     const int j = (int)(lw / n);
     const int z = (int)((ct / per_channel) % channels);
     const Mod mod = P->tab[j].mod;
-    uint64_t x = __ldg(in + ct * ctw + word);
-    if (poly == 0) x = submod(x, __ldg(mean + z * pw + lw), mod.q);
-    out[ct * ctw + word] = mulmod(x, __ldg(invstd + z * pw + lw), mod);
+    ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(in + ct * ctw + word));
+    if (poly == 0) {
+        const ulonglong2 m = __ldg(reinterpret_cast<const ulonglong2 *>(mean + z * pw + lw));
+        x.x = submod(x.x, m.x, mod.q);
+        x.y = submod(x.y, m.y, mod.q);
+    }
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(invstd + z * pw + lw));
+    x.x = mulmod(x.x, v.x, mod);
+    x.y = mulmod(x.y, v.y, mod);
+    *reinterpret_cast<ulonglong2 *>(out + ct * ctw + word) = x;
 }
 
 __global__ void __launch_bounds__(256)
@@ -331,7 +363,10 @@ plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data,
 // BEHZ square pieces
 // =====================================================================================
 // q -> Bsk U {m_tilde} fast conversion followed by the Montgomery-style q-overflow removal
-// (baseconverter.cpp:663-742 then :581-622), one thread per coefficient.
+// (baseconverter.cpp:663-742 then :581-622), one thread per coefficient.  With
+// y_i = x_i * m_tilde*(q/q_i)^-1 mod q_i and r = -(sum_i y_i (q/q_i)) * q^-1 mod 2^32 (not centred), the
+// output residue mod p_k is ((sum_i y_i (q/q_i) + q r) * m_tilde^-1) mod p_k; the constant factors are
+// folded (lift_a, lift_b) so each residue is one lazy 128-bit sum and one Barrett reduction.
 __global__ void __launch_bounds__(128)
 behz_lift_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, uint64_t *__restrict__ ext) {
     const int n = P->n, K = P->K, S = P->S;
@@ -353,16 +388,12 @@ behz_lift_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict_
     }
     const uint32_t r = zmt * (uint32_t)P->neg_inv_q_mod_mt;  // (-(z * q^-1)) mod 2^32, in [0, 2^32)
     for (int k = 0; k < S; k++) {
-        const Mod mod = P->tab[K + k].mod;
-        U128 acc{0, 0};
+        Acc7 acc = acc7_zero();
 #pragma unroll
         for (int i = 0; i < MAXK; i++)
-            if (i < K) mac128(acc, y[i], P->qhat_mod_bsk[k][i]);
-        uint64_t z = barrett128(acc, mod);
-        U128 t2 = mul128(P->q_mod_bsk[k], (uint64_t)r);
-        add128_64(t2, z);
-        uint64_t v = barrett128(t2, mod);
-        dst[(long)(K + k) * n] = mulmod(v, P->inv_mt_mod_bsk[k], mod);
+            if (i < K) mac7(acc, y[i], P->lift_a[k][i]);
+        mac7(acc, (uint64_t)r, P->lift_b[k]);
+        dst[(long)(K + k) * n] = barrett128(acc7_value(acc), P->tab[K + k].mod);
     }
 }
 
@@ -384,7 +415,14 @@ square_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restr
 }
 
 // multiply by t, fast_floor (q U Bsk -> Bsk), fastbconv_sk (Bsk -> q)
-// (evaluator.cpp:852-883, baseconverter.cpp:624-661, :448-579), one thread per coefficient.
+// (evaluator.cpp:852-883, baseconverter.cpp:624-661, :448-579), one thread per coefficient.  Constant
+// factors are folded (fl_c, fl_T, fl_N, fl_P in params.h) so that every residue the reference computes
+// in several reduced steps is one lazy sum + one Barrett here:
+//   u_i   = x_i * t (q/q_i)^-1                       mod q_i
+//   f_k   = (x_k t - sum_i u_i (q/q_i)) q^-1          mod p_k      (fast_floor)
+//   g_k   = f_k (M/m_k)^-1                            mod m_k, k < L
+//   alpha = (sum_k g_k (M/m_k) - f_sk) M^-1           mod m_sk, centred
+//   out_j = sum_k g_k (M/m_k) - alpha M               mod q_j      (fastbconv_sk)
 __global__ void __launch_bounds__(128)
 behz_floor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ prod, uint64_t *__restrict__ out) {
     const int n = P->n, K = P->K, S = P->S, L = P->L;
@@ -396,47 +434,38 @@ behz_floor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict
     uint64_t u[MAXK], g[MAXS];
 #pragma unroll
     for (int i = 0; i < MAXK; i++)
-        if (i < K) {
-            const Mod mod = P->tab[i].mod;
-            uint64_t xt = mulmod(__ldg(src + (long)i * n), P->t_mod[i], mod);
-            u[i] = mulmod(xt, P->inv_qhat[i], mod);
-        }
+        if (i < K) u[i] = mulmod(__ldg(src + (long)i * n), P->fl_c[i], P->tab[i].mod);
     uint64_t f_sk = 0;
 #pragma unroll
     for (int k = 0; k < MAXS; k++)
         if (k < S) {
-            const Mod mod = P->tab[K + k].mod;
-            U128 acc{0, 0};
+            Acc7 acc = acc7_zero();
+            mac7(acc, __ldg(src + (long)(K + k) * n), P->fl_T[k]);
 #pragma unroll
             for (int i = 0; i < MAXK; i++)
-                if (i < K) mac128(acc, u[i], P->qhat_mod_bsk[k][i]);
-            uint64_t v = barrett128(acc, mod);
-            uint64_t xt = mulmod(__ldg(src + (long)(K + k) * n), P->t_mod[K + k], mod);
-            uint64_t f = mulmod(xt + mod.q - v, P->inv_q_mod_bsk[k], mod);
-            if (k < L) g[k] = mulmod(f, P->inv_Mhat[k], mod); else f_sk = f;
+                if (i < K) mac7(acc, u[i], P->fl_N[k][i]);
+            uint64_t v = barrett128(acc7_value(acc), P->tab[K + k].mod);
+            if (k < L) g[k] = v; else f_sk = v;
         }
     const Mod msk = P->tab[K + L].mod;
-    U128 acc{0, 0};
+    Acc7 acc = acc7_zero();
 #pragma unroll
     for (int i = 0; i < MAXS; i++)
-        if (i < L) mac128(acc, g[i], P->Mhat_mod_msk[i]);
-    uint64_t s = barrett128(acc, msk);
-    uint64_t alpha = mulmod(s + (msk.q - f_sk), P->inv_M_mod_msk, msk);
-    const bool centered_neg = alpha > (msk.q >> 1);
+        if (i < L) mac7(acc, g[i], P->fl_P[i]);
+    mac7(acc, msk.q - f_sk, P->inv_M_mod_msk);
+    const uint64_t alpha = barrett128(acc7_value(acc), msk);
+    const bool centered_neg = alpha > (msk.q >> 1);  // baseconverter.cpp:547-577
+    const uint64_t alpha_mag = centered_neg ? msk.q - alpha : alpha;
     for (int j = 0; j < K; j++) {
-        const Mod mod = P->tab[j].mod;
-        U128 e{0, 0};
+        Acc7 e = acc7_zero();
 #pragma unroll
         for (int i = 0; i < MAXS; i++)
-            if (i < L) mac128(e, g[i], P->Mhat_mod_q[j][i]);
-        uint64_t ev = barrett128(e, mod);
-        U128 corr = centered_neg ? mul128(P->M_mod_q[j], msk.q - alpha) : mul128(P->neg_M_mod_q[j], alpha);
-        add128_64(corr, ev);
-        dst[(long)j * n] = barrett128(corr, mod);
+            if (i < L) mac7(e, g[i], P->Mhat_mod_q[j][i]);
+        mac7(e, alpha_mag, centered_neg ? P->M_mod_q[j] : P->neg_M_mod_q[j]);
+        dst[(long)j * n] = barrett128(acc7_value(e), P->tab[j].mod);
     }
 }
 
-// =====================================================================================
 // relinearize 3 -> 2 (evaluator.cpp:934-1069), staged so every transform runs in the tuned NTT
 // kernel and nothing is recomputed:
 //   1. scale:   d_i = c2_i * (q/q_i)^-1 mod q_i                          (:984-985)
@@ -574,7 +603,7 @@ cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const Relin
 cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout,
                            int R, const uint64_t *scale_ntt, uint64_t *out, cudaStream_t stream) {
     if (Nout <= 0) return cudaSuccess;
-    dim3 grid(Nout, (unsigned)(2L * K * n / 256));
+    dim3 grid(Nout, (unsigned)(2L * K * n / 512));
     pool_kernel<<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, out);
     return cudaGetLastError();
 }
@@ -583,7 +612,7 @@ cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, l
                          int channels, const uint64_t *mean_ntt, const uint64_t *invstd_ntt, uint64_t *out,
                          cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    dim3 grid((unsigned)count, (unsigned)(2L * K * n / 256));
+    dim3 grid((unsigned)count, (unsigned)(2L * K * n / 512));
     bn_kernel<<<grid, 256, 0, stream>>>(P, in, per_channel, channels, mean_ntt, invstd_ntt, out);
     return cudaGetLastError();
 }

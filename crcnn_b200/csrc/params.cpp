@@ -199,6 +199,19 @@ HostParams derive_params(int n, int K, const uint64_t *q, uint64_t t) {
         d.Mhat_mod_msk[i] = product_mod(bsk.data(), d.L, i, msk);
     }
     d.inv_M_mod_msk = inv_mod(product_mod(bsk.data(), d.L, -1, msk), kMsk);
+    // folded constants (see params.h)
+    for (int j = 0; j < K; j++) d.fl_c[j] = mulmod(t % d.tab[j].mod.q, d.inv_qhat[j], d.tab[j].mod);
+    for (int k = 0; k < d.S; k++) {
+        const Mod &m = d.tab[K + k].mod;
+        const uint64_t fold = k < d.L ? mulmod(d.inv_q_mod_bsk[k], d.inv_Mhat[k], m) : d.inv_q_mod_bsk[k];
+        d.lift_b[k] = mulmod(d.q_mod_bsk[k], d.inv_mt_mod_bsk[k], m);
+        d.fl_T[k] = mulmod(t % m.q, fold, m);
+        for (int i = 0; i < K; i++) {
+            d.lift_a[k][i] = mulmod(d.qhat_mod_bsk[k][i], d.inv_mt_mod_bsk[k], m);
+            d.fl_N[k][i] = negmod(mulmod(d.qhat_mod_bsk[k][i], fold, m), m.q);
+        }
+    }
+    for (int i = 0; i < d.L; i++) d.fl_P[i] = mulmod(d.Mhat_mod_msk[i], d.inv_M_mod_msk, msk);
     return hp;
 }
 

@@ -65,6 +65,14 @@ struct DeviceParams {
     uint64_t M_mod_q[MAXK];             // M mod q_j
     uint64_t neg_M_mod_q[MAXK];         // q_j - (M mod q_j)
     uint64_t t_mod[MAXK + MAXS];        // t mod each modulus (the scalar multiply inside square)
+    // Folded constants: products of the above that let each base-conversion output be ONE lazy
+    // 128-bit sum followed by ONE Barrett reduction (same residues, fewer reductions).
+    uint64_t lift_a[MAXS][MAXK];        // (q/q_i mod p_k) * m_tilde^-1 mod p_k
+    uint64_t lift_b[MAXS];              // (q mod p_k) * m_tilde^-1 mod p_k
+    uint64_t fl_c[MAXK];                // t * (q/q_i)^-1 mod q_i
+    uint64_t fl_T[MAXS];                // t * q^-1 [* (M/m_k)^-1 for k < L] mod p_k
+    uint64_t fl_N[MAXS][MAXK];          // -(q/q_i mod p_k) * q^-1 [* (M/m_k)^-1 for k < L] mod p_k
+    uint64_t fl_P[MAXS];                // (M/m_i mod m_sk) * M^-1 mod m_sk
 };
 
 // Host copy: the scalar part of DeviceParams plus the tables as vectors.

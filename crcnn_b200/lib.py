@@ -31,6 +31,8 @@ SYMBOLS = [
     ("crcnn_ctx_bsk_count", _I, [_vp]),
     ("crcnn_tensor_upload", _I, [_vp, _vp, _L, _I, _vpp]),
     ("crcnn_tensor_upload_ex", _I, [_vp, _vp, _L, _I, _I, _vpp]),
+    ("crcnn_tensor_upload_on", _I, [_vp, _vp, _L, _I, _I, _vp, _vpp]),
+    ("crcnn_ctx_wait_stream", _I, [_vp, _vp]),
     ("crcnn_tensor_download", _I, [_vp, _vp, _vp]),
     ("crcnn_tensor_download_ex", _I, [_vp, _vp, _I, _vp]),
     ("crcnn_tensor_free", _I, [_vp, _vp]),
@@ -178,6 +180,13 @@ class Engine:
     def upload_ptr(self, host_ptr, count, size=2, ntt_form=False):
         """Upload from a raw host address (e.g. a pinned torch tensor)."""
         return self._new(self.lib.crcnn_tensor_upload_ex, "tensor", host_ptr, count, size, int(ntt_form))
+
+    def upload_ptr_on(self, host_ptr, count, copy_stream_ptr, size=2, ntt_form=False):
+        """H2D on a separate copy stream (double buffering); call wait_stream() before using the tensor."""
+        return self._new(self.lib.crcnn_tensor_upload_on, "tensor", host_ptr, count, size, int(ntt_form), C.c_void_p(copy_stream_ptr))
+
+    def wait_stream(self, stream_ptr):
+        self._chk(self.lib.crcnn_ctx_wait_stream(self.h, C.c_void_p(stream_ptr)))
 
     def download(self, t, ntt_form=False, out=None):
         count, size = self.lib.crcnn_tensor_count(t.ptr), self.lib.crcnn_tensor_ct_size(t.ptr)

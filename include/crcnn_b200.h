@@ -74,6 +74,13 @@ int crcnn_tensor_upload(crcnn_ctx *ctx, const uint64_t *host_words, long count, 
 /* ntt_form != 0: the host data is already in NTT form (as after Evaluator::transform_to_ntt). */
 int crcnn_tensor_upload_ex(crcnn_ctx *ctx, const uint64_t *host_words, long count, int ct_size, int ntt_form,
                            crcnn_tensor **out);
+/* Double buffering: enqueue the host->device copy on a caller-owned copy stream so it overlaps the
+ * forward pass running on the context's stream; call crcnn_ctx_wait_stream(ctx, copy_stream) before the
+ * first use of the tensor.  host_words should be pinned and must stay valid until the copy has run. */
+int crcnn_tensor_upload_on(crcnn_ctx *ctx, const uint64_t *host_words, long count, int ct_size, int ntt_form,
+                           void *copy_stream, crcnn_tensor **out);
+/* Make the context's stream wait for everything enqueued so far on other_stream (event, no host sync). */
+int crcnn_ctx_wait_stream(crcnn_ctx *ctx, void *other_stream);
 /* Always delivers coefficient form unless want_ntt_form != 0. Blocks until the copy has finished. */
 int crcnn_tensor_download(crcnn_ctx *ctx, crcnn_tensor *t, uint64_t *host_words);
 int crcnn_tensor_download_ex(crcnn_ctx *ctx, crcnn_tensor *t, int want_ntt_form, uint64_t *host_words);
