@@ -3,6 +3,7 @@
 // kernels in kernels.cu.  Host code only orchestrates; every arithmetic step runs on the GPU.
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -11,6 +12,7 @@
 #include "../../include/crcnn_b200.h"
 #include "kernels.cuh"
 #include "params.h"
+#include "tc_mac.cuh"
 
 using namespace crcnn;
 
@@ -18,11 +20,11 @@ namespace {
 
 enum KernelClass {
     KC_NTT_FWD = 0, KC_NTT_INV, KC_MAC, KC_PLAIN_EXPAND, KC_POOL, KC_BN, KC_PLAIN_OP,
-    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_COUNT
+    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_COUNT
 };
 const char *kClassNames[KC_COUNT] = {"ntt_forward", "ntt_inverse", "weighted_sum_mac", "plain_expand_ntt", "pool_sum",
                                      "batch_norm", "plain_op", "behz_lift", "square_tensor", "behz_floor_sk",
-                                     "relinearize", "imad_probe"};
+                                     "relinearize", "imad_probe", "tc_plane_split", "weighted_sum_tc_i8"};
 
 thread_local std::string g_create_error;
 
@@ -45,6 +47,10 @@ struct crcnn_plain {
     uint64_t *ntt_mul = nullptr;   // [count][K][n] NTT(lift)            (multiplicative use)
     uint64_t *ntt_add = nullptr;   // [count][K][n] NTT(Delta-scaled)    (additive use, NTT-form data)
     uint64_t *coef_add = nullptr;  // [count][K][n] Delta-scaled         (additive use, coefficient-form data)
+    // tensor-core form (tc_mac.cuh): ternary tap matrix [count/R * 32 (+128 pad rows)][Kpad] for fan-in R
+    int tc_state = 0;              // 0 not examined, 1 eligible, -1 not (support outside x^(n-32..n-1) or digits other than +-1)
+    int8_t *tc_A = nullptr;
+    int tc_R = 0, tc_Kpad = 0;
 };
 
 struct crcnn_evk {
@@ -63,6 +69,10 @@ struct crcnn_ctx {
     int n = 0, logn = 0, K = 0, S = 0;
     int chunk_terms = 1 << 30;
     size_t weight_cache_bytes = 24ull << 30;
+    int sm_count = 148;
+    int tc_mode = 1;                 // 1: weighted sums with fan-in >= tc_min_fanin run on tcgen05 kind::i8 when the weights allow it
+    int tc_min_fanin = 64;
+    size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
     // profiling
@@ -213,8 +223,78 @@ void boundaries(int xd, int yd, int xs, int ys, int xf, int yf, int *xl, int *yl
 }
 
 // Weighted-sum driver shared by conv and fc: M output channels [m_first, m_first+M) of Mall.
+// Ternary tap matrix of a weight pack for fan-in R (tc_mac.cuh): built once, on the host, from the sparse form.
+int ensure_tc_form(crcnn_ctx *ctx, crcnn_plain *w, int R) {
+    if (w->tc_state < 0) return CRCNN_OK;
+    if (w->tc_state == 1 && w->tc_R == R) return CRCNN_OK;
+    const uint32_t n = (uint32_t)ctx->n;
+    const uint64_t t = ctx->hp.d.t;
+    for (size_t e = 0; e < w->idx.size(); e++)
+        if (w->idx[e] < n - TC_TAPS || (w->val[e] != 1 && w->val[e] != t - 1)) { w->tc_state = -1; return CRCNN_OK; }
+    if (w->count % R) { w->tc_state = -1; return CRCNN_OK; }
+    const long Mall = w->count / R;
+    const int Kpad = ((R + 31) / 32 + 3) / 4 * TC_BK;
+    const size_t rows = (size_t)Mall * TC_TAPS + TC_BM;  // one tile of zero rows so shard tiles may over-read
+    std::vector<int8_t> A(rows * Kpad, 0);
+    for (long wi = 0; wi < w->count; wi++) {
+        const long m = wi / R, r = wi % R;
+        for (uint32_t e = w->off[wi]; e < w->off[wi + 1]; e++) {
+            const int tap = (int)(n - w->idx[e]);  // 1..32
+            // lifted digit s = +1 (value 1) or -1 (value t-1); x^(n-tap) = -x^(-tap) flips it
+            A[((size_t)m * TC_TAPS + tap - 1) * Kpad + r] = w->val[e] == 1 ? (int8_t)-1 : (int8_t)1;
+        }
+    }
+    if (w->tc_A) { dev_free(ctx, w->tc_A); w->tc_A = nullptr; }
+    int rc = dev_alloc(ctx, A.size(), (void **)&w->tc_A);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(w->tc_A, A.data(), A.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    w->tc_state = 1; w->tc_R = R; w->tc_Kpad = Kpad;
+    return CRCNN_OK;
+}
+
+// Weighted sum on the tensor cores: coefficient-domain inputs and outputs, no transform anywhere.
+int run_weighted_sum_tc(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
+                        int Npos, int Pimg, int m_first, int M, crcnn_tensor *out) {
+    int rc = ensure_domain(ctx, in, 0);
+    if (!rc) rc = ensure_form(ctx, b, PF_COEF_ADD);
+    if (rc) return rc;
+    const size_t pw = poly_words(ctx);
+    TcMacArgs a{};
+    a.A = w->tc_A + (size_t)m_first * TC_TAPS * w->tc_Kpad;
+    a.x = in->d; a.bias = b->coef_add + (size_t)m_first * pw; a.out = out->d;
+    a.M = M; a.Mpad = (M * TC_TAPS + TC_BM - 1) / TC_BM * TC_BM; a.R = R; a.Kpad = w->tc_Kpad;
+    a.planes = tc_planes_for(ctx->hp.d);
+    a.Pimg = Pimg; a.Mtotal = M; a.m0 = 0; a.n = ctx->n; a.K = ctx->K;
+    a.npos = 1;
+    const size_t per_pos = tc_b_bytes(a);
+    long chunk = (long)std::max<size_t>(1, ctx->tc_scratch_bytes / per_pos);
+    chunk = std::min<long>(std::min<long>(chunk, Npos), 65535 / (2 * ctx->K));
+    uint8_t *scratch = nullptr;
+    rc = dev_alloc(ctx, (size_t)chunk * per_pos, (void **)&scratch);
+    if (rc) return rc;
+    a.B = scratch;
+    for (long p0 = 0; p0 < Npos && !rc; p0 += chunk) {
+        a.npos = (int)std::min<long>(chunk, Npos - p0);
+        a.p0 = (int)p0;
+        a.in_index = d_index + p0 * R;
+        cudaError_t e;
+        { ProfScope ps(ctx, KC_TC_SPLIT); e = launch_tc_split(ctx->dP, a, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_TC_MAC); e = launch_tc_mac(ctx->dP, a, ctx->sm_count, ctx->stream); }
+        if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, std::string("tensor-core weighted sum: ") + cudaGetErrorString(e));
+    }
+    dev_free(ctx, scratch);
+    if (!rc) out->ntt = 0;
+    return rc;
+}
+
 int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
                      int Npos, int Pimg, int Mall, int m_first, int M, crcnn_tensor *out) {
+    if (ctx->tc_mode && R >= ctx->tc_min_fanin && w->sparse_shape && tc_mac_available() == cudaSuccess) {
+        int rc = ensure_tc_form(ctx, w, R);
+        if (rc) return rc;
+        if (w->tc_state == 1) return run_weighted_sum_tc(ctx, in, w, b, d_index, R, Npos, Pimg, m_first, M, out);
+    }
     int rc = ensure_domain(ctx, in, 1);
     if (rc) return rc;
     rc = ensure_form(ctx, b, PF_NTT_ADD);
@@ -283,6 +363,8 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
     for (int i = 0; i < K; i++) { int b = 0; for (uint64_t v = q[i]; v; v >>= 1) b++; maxbits = std::max(maxbits, b); }
     int spare = 128 - 2 * maxbits;
     c->chunk_terms = spare >= 30 ? (1 << 30) : (1 << spare);
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *e = getenv("CRCNN_TC")) c->tc_mode = atoi(e);
     // stream-ordered allocator: keep freed blocks cached
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -352,6 +434,15 @@ int crcnn_ctx_sync(crcnn_ctx *ctx) {
 int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     ctx->weight_cache_bytes = bytes;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size_t scratch_bytes) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(mode == 0 || mode == 1, "tensor-core mode must be 0 or 1");
+    ctx->tc_mode = mode;
+    if (min_fanin > 0) ctx->tc_min_fanin = min_fanin;
+    if (scratch_bytes > 0) ctx->tc_scratch_bytes = scratch_bytes;
     return CRCNN_OK;
 }
 
@@ -547,7 +638,7 @@ int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     if (!p) return CRCNN_OK;
     dev_free(ctx, p->d_off); dev_free(ctx, p->d_idx); dev_free(ctx, p->d_val);
-    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add);
+    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A);
     delete p;
     return CRCNN_OK;
 }

@@ -1,0 +1,397 @@
+// tcgen05 kind::i8 weighted-sum path (see tc_mac.cuh for the algorithm and the exactness argument).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include "modarith.cuh"
+#include "tc_mac.cuh"
+
+namespace crcnn {
+
+namespace {
+
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_STAGE = TC_BM * TC_BK;  // 16 KB
+constexpr int TC_THREADS = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int TC_ACC_STRIDE = 256;         // TMEM columns between the two accumulator buffers
+constexpr int TC_SCRATCH_WARP = 64 * 32 * 4;
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// A protocol error must end the launch with an error, never hang the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 28)) {
+            printf("tc_mac_kernel: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], u8/s8 operands, s32 accumulators
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, 128-byte rows, 128B swizzle: 8-row atoms of 1024 B (SBO), LBO unused (1),
+// descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ------------------------------------------------------------------------------------ the GEMM kernel
+template <int PLANES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const DeviceParams *__restrict__ P, TcMacArgs a) {
+    constexpr int N = PLANES * TC_CB;               // UMMA N: 224 or 256
+    constexpr int B_STAGE = N * TC_BK;              // 28 / 32 KB
+    constexpr uint32_t IDESC = (2u << 4)            // accumulator format S32
+                               | (1u << 7)          // A = signed 8 bit
+                               | (0u << 10)         // B = unsigned 8 bit
+                               | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);  // K-major A and B
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sA = base, sB = base + TC_STAGES * TC_A_STAGE;
+    const uint32_t off_scratch = TC_STAGES * (TC_A_STAGE + B_STAGE);
+    const uint32_t off_bar = off_scratch + 4 * TC_SCRATCH_WARP;
+    const uint32_t bar_full = base + off_bar, bar_empty = bar_full + 8 * TC_STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * TC_STAGES, bar_tempty = bar_tfull + 16;
+    const uint32_t tmem_slot = bar_tempty + 16;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + off_bar + 16 * TC_STAGES + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.n, K = a.K;
+    const int m_tiles = a.Mpad / TC_BM;
+    const long items = (long)a.npos * 2 * K * m_tiles;
+    const int NU = n / TC_CB + 1;                   // coefficient blocks incl. the negated wrap-around block
+    const int ksteps = (a.R + 31) / 32;
+    const int KB = (ksteps + 3) / 4;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4); }
+        fence_barrier_init();
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x) {
+                const int g = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+                for (int u = 0; u < NU; u++)
+                    for (int kb = 0; kb < KB; kb++) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, TC_A_STAGE + B_STAGE);
+                        tma_load_2d(sA + stage * TC_A_STAGE, &tmA, bar_full + 8 * stage, kb * TC_BK, mt * TC_BM);
+                        tma_load_4d(sB + stage * B_STAGE, &tmB, bar_full + 8 * stage, kb * TC_BK, u * TC_CB, 0, g);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x)
+                for (int u = 0; u < NU; u++) {
+                    mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
+                    for (int kb = 0; kb < KB; kb++) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint64_t da = umma_desc_sw128(sA + stage * TC_A_STAGE), db = umma_desc_sw128(sB + stage * B_STAGE);
+                        const int nks = min(4, ksteps - kb * 4);
+                        for (int ks = 0; ks < nks; ks++)
+                            umma_i8(d_tmem, da + 2 * ks, db + 2 * ks, IDESC, (kb | ks) != 0);  // +32 B per K-step
+                        umma_commit(bar_empty + 8 * stage);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull + 8 * acc);
+                    if ((acc ^= 1) == 0) acc_phase ^= 1;
+                }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================================== epilogue
+        const int lg = warp & 3;  // TMEM lane group this warp may read = output (mt*4 + lg), lane = tap-1
+        int *S = reinterpret_cast<int *>(base_ptr + off_scratch + (warp - 2) * TC_SCRATCH_WARP);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (long item = blockIdx.x; item < items; item += gridDim.x) {
+            const int g = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+            const int j = g % K, poly = (g / K) & 1, p = g / (2 * K);
+            const int m = mt * 4 + lg;
+            const bool valid = m < a.M;
+            const Mod mod = P->tab[j].mod;
+            // offset q * 2^s >= 2^84 that makes the signed plane sum non-negative before the reduction
+            const int s = 85 - (64 - __clzll(mod.q));
+            const uint64_t off_lo = mod.q << s, off_hi = mod.q >> (64 - s);
+            const int pg = a.p0 + p;  // position index within the whole layer
+            const long oct = (long)(pg / a.Pimg) * ((long)a.Mtotal * a.Pimg) + (long)(a.m0 + m) * a.Pimg + pg % a.Pimg;
+            uint64_t *optr = a.out + ((oct * 2 + poly) * K + j) * (long)n;
+            const uint64_t *bptr = (a.bias && poly == 0 && valid) ? a.bias + ((long)m * K + j) * n : nullptr;
+            int carry[PLANES];
+#pragma unroll
+            for (int l = 0; l < PLANES; l++) carry[l] = 0;
+            for (int u = 0; u < NU; u++) {
+                mbar_wait(bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+                int lo[PLANES], hi[PLANES];
+#pragma unroll
+                for (int l = 0; l < PLANES; l++) {
+                    int v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_ACC_STRIDE + l * TC_CB, v);
+                    // D[(m,tap), cc] belongs to output coefficient cc - tap of this block (tap = lane+1):
+                    // skew into S[cc - tap + 32][lane]; rows < 32 finish the previous block, rows >= 32 start this one
+#pragma unroll
+                    for (int cc = 0; cc < 32; cc++) S[(cc - lane + 31) * 32 + lane] = v[cc];
+                    __syncwarp();
+                    int slo = 0, shi = 0;
+#pragma unroll
+                    for (int st = 0; st < 32; st++) {
+                        const int i = (st + lane) & 31;
+                        const bool is_lo = i >= 31 - lane;
+                        const int val = S[(lane + (is_lo ? 0 : 32)) * 32 + i];
+                        slo += is_lo ? val : 0;
+                        shi += is_lo ? 0 : val;
+                    }
+                    __syncwarp();
+                    lo[l] = slo;
+                    hi[l] = shi;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if ((acc ^= 1) == 0) acc_phase ^= 1;
+                if (u >= 1 && valid) {
+                    long long v0 = 0, v1 = 0;
+#pragma unroll
+                    for (int l = 0; l < PLANES; l++) {
+                        const long long pl = (long long)(carry[l] + lo[l]);
+                        if (l < 4) v0 += pl << (8 * l); else v1 += pl << (8 * (l - 4));
+                    }
+                    // total = v0 + v1 * 2^32 as a 128-bit two's complement number, plus the offset
+                    U128 z;
+                    const uint64_t t_lo = (uint64_t)v1 << 32;
+                    z.lo = (uint64_t)v0 + t_lo;
+                    z.hi = (uint64_t)(v0 >> 63) + (uint64_t)(v1 >> 32) + (z.lo < t_lo);
+                    const uint64_t l2 = z.lo + off_lo;
+                    z.hi += off_hi + (l2 < off_lo);
+                    z.lo = l2;
+                    uint64_t r = barrett128(z, mod);
+                    const int c = (u - 1) * TC_CB + lane;
+                    if (bptr) r = addmod(r, __ldg(bptr + c), mod.q);
+                    optr[c] = r;
+                }
+#pragma unroll
+                for (int l = 0; l < PLANES; l++) carry[l] = hi[l];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------ operand staging
+// Gathers the layer's input ciphertexts per output position, splits every residue into byte planes and
+// writes them transposed (fan-in index contiguous) with the 32 negated wrap-around coefficients appended:
+//   B[g][l][c][r] = byte l of X~_(in_index[p][r])[poly][j][c],   g = (p*2 + poly)*K + j,  c in [0, n+32)
+__global__ void __launch_bounds__(256)
+tc_split_kernel(const DeviceParams *__restrict__ P, TcMacArgs a) {
+    __shared__ uint64_t tile[32][133];    // [c][(r & 3) * 33 + (r >> 2)]; row stride 133 = 5 mod 16: conflict free both ways
+    const int n = a.n, K = a.K;
+    const int ct = blockIdx.x;            // coefficient block, n/32 = the wrap-around block
+    const int g = blockIdx.y;
+    const int r0 = blockIdx.z * 128;
+    const int j = g % K, poly = (g / K) & 1, p = g / (2 * K);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t q = P->tab[j].mod.q;
+    const bool wrap = ct == n / 32;
+    for (int rr = warp; rr < 128; rr += 8) {
+        const int r = r0 + rr;
+        uint64_t v = 0;
+        if (r < a.R) {
+            const long ctx = __ldg(a.in_index + (long)p * a.R + r);
+            const uint64_t *src = a.x + ((ctx * 2 + poly) * K + j) * (long)n;
+            if (!wrap) v = __ldg(src + ct * 32 + lane);
+            else { v = __ldg(src + lane); v = v ? q - v : 0; }
+        }
+        tile[lane][(rr & 3) * 33 + (rr >> 2)] = v;
+    }
+    __syncthreads();
+    const long plane_stride = (long)(n + 32) * a.Kpad;
+    uint8_t *dst = a.B + (long)g * a.planes * plane_stride + (long)(ct * 32) * a.Kpad + r0;
+    for (int w = threadIdx.x; w < a.planes * 1024; w += 256) {
+        const int l = w >> 10, c = (w >> 5) & 31, rw = w & 31;
+        const int sh = 8 * l;
+        const uint32_t word = (uint32_t)((tile[c][rw] >> sh) & 0xff) | (uint32_t)((tile[c][33 + rw] >> sh) & 0xff) << 8 |
+                              (uint32_t)((tile[c][66 + rw] >> sh) & 0xff) << 16 | (uint32_t)((tile[c][99 + rw] >> sh) & 0xff) << 24;
+        *reinterpret_cast<uint32_t *>(dst + l * plane_stride + (long)c * a.Kpad + 4 * rw) = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+template <int PLANES>
+size_t tc_smem_bytes() {
+    return 1024 + (size_t)TC_STAGES * (TC_A_STAGE + PLANES * TC_CB * TC_BK) + 4 * TC_SCRATCH_WARP + 16 * TC_STAGES + 32 + 16;
+}
+
+template <int PLANES>
+cudaError_t launch_tc_mac_t(const DeviceParams *P, const TcMacArgs &a, int sm_count, cudaStream_t stream) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)a.Kpad, (cuuint64_t)a.Mpad};
+        cuuint64_t strides[1] = {(cuuint64_t)a.Kpad};
+        cuuint32_t box[2] = {TC_BK, TC_BM}, es[2] = {1, 1};
+        if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)a.A, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t rows = (cuuint64_t)a.n + 32, groups = (cuuint64_t)a.npos * 2 * a.K;
+        cuuint64_t dims[4] = {(cuuint64_t)a.Kpad, rows, (cuuint64_t)PLANES, groups};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Kpad, rows * a.Kpad, rows * a.Kpad * PLANES};
+        cuuint32_t box[4] = {TC_BK, TC_CB, PLANES, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.B, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    auto k = tc_mac_kernel<PLANES>;
+    const size_t smem = tc_smem_bytes<PLANES>();
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const long items = (long)a.npos * 2 * a.K * (a.Mpad / TC_BM);
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    k<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, P, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t tc_b_bytes(const TcMacArgs &a) { return (size_t)a.npos * 2 * a.K * a.planes * (size_t)(a.n + 32) * a.Kpad; }
+
+cudaError_t tc_mac_available() { return encode_tiled() ? cudaSuccess : cudaErrorNotSupported; }
+
+cudaError_t launch_tc_split(const DeviceParams *P, const TcMacArgs &a, cudaStream_t stream) {
+    if (a.npos <= 0) return cudaSuccess;
+    dim3 grid((unsigned)(a.n / 32 + 1), (unsigned)(a.npos * 2 * a.K), (unsigned)(a.Kpad / 128));
+    tc_split_kernel<<<grid, 256, 0, stream>>>(P, a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tc_mac(const DeviceParams *P, const TcMacArgs &a, int sm_count, cudaStream_t stream) {
+    if (a.npos <= 0 || a.M <= 0) return cudaSuccess;
+    if (a.Kpad % TC_BK || a.Mpad % TC_BM || a.n % TC_CB || (long)a.npos * 2 * a.K > 65535) return cudaErrorInvalidValue;
+    if (a.planes == 7) return launch_tc_mac_t<7>(P, a, sm_count, stream);
+    if (a.planes == 8) return launch_tc_mac_t<8>(P, a, sm_count, stream);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace crcnn

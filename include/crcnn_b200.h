@@ -62,6 +62,13 @@ int crcnn_ctx_sync(crcnn_ctx *ctx);
 /* Upper bound (bytes) for NTT-form weights kept resident per plaintext pack; larger packs are
  * expanded chunk by chunk into a scratch buffer during forward.  Default 24 GiB. */
 int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes);
+/* Weighted sums (conv / fc) whose weights are FractionalEncoder base-3 plaintexts with |w| < 1/2 (every
+ * weight of the reference's models) and whose fan-in is >= min_fanin run as a u8 x s8 -> s32 GEMM on the
+ * tcgen05 tensor cores in the coefficient domain (crcnn_b200/csrc/tc_mac.cuh); results are the same canonical
+ * residues.  mode 0 forces the CUDA-core NTT-domain kernel (also the fallback for any other weights).
+ * min_fanin <= 0 / scratch_bytes == 0 keep the current values (defaults 64, 12 GiB).  Env CRCNN_TC=0|1 sets the
+ * initial mode. */
+int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size_t scratch_bytes);
 /* Derived constants, for cross-checking against SEAL: which = 0 root_powers, 1 scaled_root_powers,
  * 2 inv_root_powers_div_two, 3 scaled_inv_root_powers_div_two (SEAL/seal/util/smallntt.cpp:37-92);
  * slot in [0,K) = coefficient primes, [K,K+S) = Bsk primes.  out has n words. */
