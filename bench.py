@@ -317,6 +317,7 @@ def main_b200(args, rank, world, local_rank):
         clocks = sampler.stop()
         ms_total = ev[0].elapsed_time(ev[1])
         prof = eng.prof()
+        work = eng.prof_work()
         eng.prof_enable(False)
         # ---- timed: end to end through the C ABI with host buffers
         barrier()
@@ -350,41 +351,67 @@ def main_b200(args, rank, world, local_rank):
     for i, name in enumerate(layer_names):
         per_layer[name] = float(np.mean([evs[i].elapsed_time(evs[i + 1]) for evs in layer_events]))
 
-    # ---- roofline of the dominant kernel class
-    dom = max(prof.items(), key=lambda kv: kv[1][1])
+    # ---- per-class rooflines from the engine's own work counters (crcnn_prof_get_work: algorithmic bytes and
+    # operations counted at launch time) and the CUDA-event time of every launch of the class
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    bf16_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     layers = net.layers
-    terms = sum(nets.layer_terms(l) for l in layers)
-    mac_launch_ms = prof["weighted_sum_mac"][1] / max(1, prof["weighted_sum_mac"][0])
-    # algorithmic bytes of the weighted-sum kernel per step: inputs + outputs once, distinct weights once
-    alg_bytes = 0
-    for l in layers:
-        if l[0] in ("conv", "fc"):
-            nin, nout = nets.layer_io_counts(l)
-            nw = (l[9] * l[4] * l[7] * l[8]) if l[0] == "conv" else l[2] * l[3]  # distinct weight plaintexts
-            alg_bytes += (nin + nout) * B * 2 * K * n * W + nw * K * n * W
-    mac_ms_step = prof["weighted_sum_mac"][1] / args.steps
-    achieved = alg_bytes / (mac_ms_step / 1000.0) / 1e9
-    # integer-pipe view: 64x64->128 MACs per second against the register-only probe
+    # integer pipe: 64x64->128-bit multiply-accumulates per second of a register-only loop, measured in this run
     probe_ms = eng.probe_imad(148 * 8, 256, 4096)
     probe_rate = 148 * 8 * 256 * 4096 * 8 / (probe_ms / 1000.0)
-    mac_rate = terms * B * 2 * K * n / (mac_ms_step / 1000.0)
-    roofline = {
-        "kernel": "weighted_sum_mac", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-        "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-        "avg_launch_ms": mac_launch_ms, "launches_per_step": prof["weighted_sum_mac"][0] / args.steps,
-        "share_of_step": mac_ms_step / (ms_total / args.steps),
-        "int_pipe": {"achieved_gmac_s": mac_rate / 1e9, "probe_gmac_s": probe_rate / 1e9, "frac": mac_rate / probe_rate,
-                     "note": "64x64->128-bit multiply-accumulates; peak = register-only probe measured in this run"},
-        "dominant_class_by_time": dom[0],
-    }
-    kernel_ms = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in prof.items() if v[0]}
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    MAC_CLASSES = ("weighted_sum_mac", "behz_lift", "behz_floor_sk")
+    BFLY_CLASSES = ("ntt_forward", "ntt_inverse", "plain_expand_ntt", "relinearize")
+    BFLY_MACS = 2.5  # one Harvey butterfly = 10 IMAD-pipe instructions (mulhi64 + two mullo64) = 2.5 split-accumulator MACs of 4
+    kernel_ms, classes = {}, {}
+    for name, (launches_c, ms_c) in prof.items():
+        if not launches_c:
+            continue
+        byts, ops = work.get(name, (0.0, 0.0))
+        sec = ms_c / 1000.0
+        ent = {"launches_per_step": launches_c / args.steps, "ms_per_step": ms_c / args.steps,
+               "share_of_step": ms_c / ms_total, "alg_gb_per_step": byts / args.steps / 1e9,
+               "hbm_gbs": byts / sec / 1e9 if sec else None, "hbm_frac": byts / sec / 1e9 / hbm_peak if sec else None}
+        if name == "weighted_sum_tc_i8":
+            ent["int8_tops"] = 2 * ops / sec / 1e12
+            ent["tensor_frac"] = ent["int8_tops"] / (2 * bf16_peak)
+        elif name in MAC_CLASSES:
+            ent["gmac_s"] = ops / sec / 1e9
+            ent["int_pipe_frac"] = ops / sec / probe_rate
+        elif name in BFLY_CLASSES:
+            ent["gbutterfly_s"] = ops / sec / 1e9
+            ent["int_pipe_frac"] = BFLY_MACS * ops / sec / probe_rate
+        classes[name] = ent
+        kernel_ms[name] = {"launches_per_step": ent["launches_per_step"], "ms_per_step": ent["ms_per_step"]}
+    dom = max(classes.items(), key=lambda kv: kv[1]["ms_per_step"])
+    dname, d = dom
+    avg_launch_ms = d["ms_per_step"] / d["launches_per_step"]
+    if dname == "weighted_sum_tc_i8":
+        roofline = {"kernel": dname, "bound": "tensor", "achieved": d["int8_tops"], "peak": 2 * bf16_peak, "unit": "TFLOP/s",
+                    "frac": d["tensor_frac"],
+                    "peak_source": "2 x measured sustained bf16 (MEASURED_PEAKS.json): kind::i8 runs at twice the bf16 rate; "
+                                   "achieved counts 2 ops per int8 multiply-accumulate of the unpadded GEMM"}
+    else:
+        roofline = {"kernel": dname, "bound": "hbm", "achieved": d["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": d["hbm_frac"], "peak_source": peak_src}
+        if "int_pipe_frac" in d:
+            roofline["int_pipe"] = {"frac": d["int_pipe_frac"], "probe_gmac_s": probe_rate / 1e9,
+                                    "note": "the binding resource of this kernel: 64-bit integer multiply pipe; peak = register-only "
+                                            "64x64->128 multiply-accumulate loop measured in this run"
+                                            + ("; one butterfly counted as %.1f MACs" % BFLY_MACS if dname in BFLY_CLASSES else "")}
+    roofline.update({"traffic": traffic.get(dname), "avg_launch_ms": avg_launch_ms, "launches_per_step": d["launches_per_step"],
+                     "share_of_step": d["share_of_step"], "alg_bytes_per_launch": d["alg_gb_per_step"] * 1e9 / d["launches_per_step"],
+                     "int_pipe_probe_gmac_s": probe_rate / 1e9, "classes": classes})
     launches = int(sum(v[0] for v in prof.values()))
 
     line = {
@@ -394,7 +421,7 @@ def main_b200(args, rank, world, local_rank):
         "config": {"workload": "PlainModel.h5 encoded net (conv-avgpool-bn-conv-square-avgpool-bn-fc-fc), n=8192, K=4, t=2^30, 32x32 zero-bordered input",
                    "images_per_step_per_gpu": B, "parallelism": "image replicas x%d (no collective)" % world,
                    "l2": "inputs (%.1f GB per step) and weights exceed the 126 MB L2; no flush needed" % (h2d / 1e9),
-                   "weights": "conv1/conv2/fc4 NTT-form resident; fc3 (164 GB in NTT form) re-expanded from sparse form every step"},
+                   "weights": "conv1/conv2/fc4: NTT-form plaintexts resident (CUDA-core weighted sum); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,

@@ -45,6 +45,7 @@ struct crcnn_plain {
     uint32_t *d_off = nullptr, *d_idx = nullptr;
     uint64_t *d_val = nullptr;
     uint64_t *ntt_mul = nullptr;   // [count][K][n] NTT(lift)            (multiplicative use)
+    uint64_t *ntt_mul_sh = nullptr;  // Shoup companions of ntt_mul (small packs only: pooling scale, batch-norm factors)
     uint64_t *ntt_add = nullptr;   // [count][K][n] NTT(Delta-scaled)    (additive use, NTT-form data)
     uint64_t *coef_add = nullptr;  // [count][K][n] Delta-scaled         (additive use, coefficient-form data)
     // tensor-core form (tc_mac.cuh): ternary tap matrix [count/R * 32 (+128 pad rows)][Kpad] for fan-in R
@@ -70,8 +71,9 @@ struct crcnn_ctx {
     int chunk_terms = 1 << 30;
     size_t weight_cache_bytes = 24ull << 30;
     int sm_count = 148;
-    int tc_mode = 1;                 // 1: weighted sums with fan-in >= tc_min_fanin run on tcgen05 kind::i8 when the weights allow it
-    int tc_min_fanin = 64;
+    int tc_mode = 1;                 // 1: weighted sums with fan-in >= tc_min_fanin and >= tc_min_outputs outputs run on tcgen05 kind::i8 when the weights allow it; 2: regardless of the output count
+    int tc_min_fanin = 256;
+    int tc_min_outputs = 32;
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
@@ -79,6 +81,8 @@ struct crcnn_ctx {
     bool prof_on = false;
     long launches[KC_COUNT] = {0};
     double ms[KC_COUNT] = {0};
+    double work_bytes[KC_COUNT] = {0};  // algorithmic (compulsory) HBM bytes enqueued per class since the last reset
+    double work_ops[KC_COUNT] = {0};    // algorithmic operations (unit depends on the class, see crcnn_prof_get_work)
     struct Pending { int cls; cudaEvent_t a, b; };
     std::vector<Pending> pending;
     std::vector<cudaEvent_t> event_pool;
@@ -105,8 +109,10 @@ int fail(crcnn_ctx *ctx, int code, const std::string &msg) {
 
 struct ProfScope {
     crcnn_ctx *c; int cls; cudaEvent_t a = nullptr, b = nullptr;
-    ProfScope(crcnn_ctx *ctx, int k) : c(ctx), cls(k) {
+    ProfScope(crcnn_ctx *ctx, int k, double bytes = 0, double ops = 0) : c(ctx), cls(k) {
         c->launches[cls]++;
+        c->work_bytes[cls] += bytes;
+        c->work_ops[cls] += ops;
         if (!c->prof_on) return;
         auto get = [&]() { cudaEvent_t e; if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
@@ -132,6 +138,9 @@ void prof_collect(crcnn_ctx *c) {
 }
 
 inline size_t poly_words(const crcnn_ctx *c) { return (size_t)c->K * c->n; }
+// algorithmic work of `polys` limb-polynomials: bytes of one pass over them, butterflies of one transform each
+inline double lp_bytes(const crcnn_ctx *c, double polys) { return polys * c->n * 8.0; }
+inline double lp_bfly(const crcnn_ctx *c, double polys) { return polys * (c->n / 2) * c->logn; }
 
 int dev_alloc(crcnn_ctx *ctx, size_t bytes, void **out) {
     *out = nullptr;
@@ -150,7 +159,7 @@ int new_tensor(crcnn_ctx *ctx, long count, int size, int ntt, crcnn_tensor **out
 }
 
 int ntt_inplace(crcnn_ctx *ctx, uint64_t *d, long npolys, int slot_base, int slot_count, bool inverse) {
-    ProfScope ps(ctx, inverse ? KC_NTT_INV : KC_NTT_FWD);
+    ProfScope ps(ctx, inverse ? KC_NTT_INV : KC_NTT_FWD, 2 * lp_bytes(ctx, npolys), lp_bfly(ctx, npolys));
     CU(launch_ntt(ctx->dP, ctx->logn, d, npolys, slot_base, slot_count, inverse, ctx->stream));
     return CRCNN_OK;
 }
@@ -166,7 +175,7 @@ int ensure_domain(crcnn_ctx *ctx, crcnn_tensor *t, int want_ntt) {
 enum PlainForm { PF_NTT_MUL, PF_NTT_ADD, PF_COEF_ADD };
 
 int expand_range(crcnn_ctx *ctx, crcnn_plain *p, long first, long count, PlainForm f, uint64_t *dst) {
-    ProfScope ps(ctx, KC_PLAIN_EXPAND);
+    ProfScope ps(ctx, KC_PLAIN_EXPAND, lp_bytes(ctx, (double)count * ctx->K), f != PF_COEF_ADD ? lp_bfly(ctx, (double)count * ctx->K) : 0);
     CU(launch_plain_expand(ctx->dP, ctx->logn, ctx->K, p->d_off, p->d_idx, p->d_val, first, count,
                            (f == PF_NTT_MUL ? 0 : 1) | (p->sparse_shape ? 2 : 0), f != PF_COEF_ADD, dst, ctx->stream));
     return CRCNN_OK;
@@ -203,6 +212,18 @@ int make_plain(crcnn_ctx *ctx, std::vector<uint32_t> &&off, std::vector<uint32_t
     return CRCNN_OK;
 }
 
+// Shoup companions of the multiplicative NTT form (element-wise layers multiply by a per-channel constant:
+// one mulhi + two mullo instead of a 128-bit Barrett reduction per residue).
+int ensure_shoup(crcnn_ctx *ctx, crcnn_plain *p) {
+    int rc = ensure_form(ctx, p, PF_NTT_MUL);
+    if (rc || p->ntt_mul_sh) return rc;
+    const size_t words = (size_t)p->count * poly_words(ctx);
+    rc = dev_alloc(ctx, words * 8, (void **)&p->ntt_mul_sh);
+    if (rc) return rc;
+    CU(launch_shoup_companion(ctx->dP, p->ntt_mul, (long)words, p->ntt_mul_sh, ctx->stream));
+    return CRCNN_OK;
+}
+
 // Device copy of an index table, cached by content key.
 int get_index_table(crcnn_ctx *ctx, const std::vector<int> &key, const std::vector<int> &table, const int **out) {
     auto it = ctx->index_cache.find(key);
@@ -214,6 +235,13 @@ int get_index_table(crcnn_ctx *ctx, const std::vector<int> &key, const std::vect
     ctx->index_cache[key] = d;
     *out = d;
     return CRCNN_OK;
+}
+
+// R residues of any coefficient prime add up below 2^64
+bool sum_fits_64(const crcnn_ctx *ctx, long R) {
+    uint64_t maxq = 0;
+    for (int j = 0; j < ctx->K; j++) maxq = std::max(maxq, ctx->hp.d.tab[j].mod.q);
+    return R > 0 && (uint64_t)R <= UINT64_MAX / maxq;
 }
 
 // Layer::computeBoundaries (CrCNN/src/layer.cpp:12-26)
@@ -279,8 +307,15 @@ int run_weighted_sum_tc(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_
         a.p0 = (int)p0;
         a.in_index = d_index + p0 * R;
         cudaError_t e;
-        { ProfScope ps(ctx, KC_TC_SPLIT); e = launch_tc_split(ctx->dP, a, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_TC_MAC); e = launch_tc_mac(ctx->dP, a, ctx->sm_count, ctx->stream); }
+        // split: gathers npos*R ciphertexts and writes their byte planes; GEMM: reads the planes, writes the outputs;
+        // ops = int8 multiply-accumulates of the unpadded problem (32 taps x planes per term and coefficient)
+        const double bbytes = (double)a.npos * per_pos;
+        { ProfScope ps(ctx, KC_TC_SPLIT, lp_bytes(ctx, (double)a.npos * R * 2 * ctx->K) + bbytes, 0); e = launch_tc_split(ctx->dP, a, ctx->stream); }
+        if (e == cudaSuccess) {
+            ProfScope ps(ctx, KC_TC_MAC, bbytes + lp_bytes(ctx, (double)a.npos * M * 2 * ctx->K),
+                         (double)a.npos * 2 * ctx->K * ctx->n * a.planes * (double)M * TC_TAPS * R);
+            e = launch_tc_mac(ctx->dP, a, ctx->sm_count, ctx->stream);
+        }
         if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, std::string("tensor-core weighted sum: ") + cudaGetErrorString(e));
     }
     dev_free(ctx, scratch);
@@ -290,7 +325,7 @@ int run_weighted_sum_tc(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_
 
 int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
                      int Npos, int Pimg, int Mall, int m_first, int M, crcnn_tensor *out) {
-    if (ctx->tc_mode && R >= ctx->tc_min_fanin && w->sparse_shape && tc_mac_available() == cudaSuccess) {
+    if (ctx->tc_mode && R >= ctx->tc_min_fanin && (ctx->tc_mode == 2 || M >= ctx->tc_min_outputs) && w->sparse_shape && tc_mac_available() == cudaSuccess) {
         int rc = ensure_tc_form(ctx, w, R);
         if (rc) return rc;
         if (w->tc_state == 1) return run_weighted_sum_tc(ctx, in, w, b, d_index, R, Npos, Pimg, m_first, M, out);
@@ -311,7 +346,8 @@ int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_pla
         a.w = w->ntt_mul + (size_t)m_first * R * pw;
         a.bias = b->ntt_add + (size_t)m_first * pw;
         a.M = M; a.m0 = 0;
-        ProfScope ps(ctx, KC_MAC);
+        ProfScope ps(ctx, KC_MAC, lp_bytes(ctx, ((double)in->count + (double)M * Npos) * 2 * ctx->K + (double)M * R * ctx->K),
+                     (double)M * Npos * R * 2 * ctx->K * ctx->n);
         CU(launch_mac(ctx->dP, a, ctx->stream));
         return CRCNN_OK;
     }
@@ -327,12 +363,30 @@ int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_pla
         if (rc) break;
         a.w = scratch; a.bias = b->ntt_add + (size_t)(m_first + m0) * pw;
         a.M = (int)cur; a.m0 = (int)m0;
-        ProfScope ps(ctx, KC_MAC);
+        ProfScope ps(ctx, KC_MAC, lp_bytes(ctx, ((double)in->count + (double)cur * Npos) * 2 * ctx->K + (double)cur * R * ctx->K),
+                     (double)cur * Npos * R * 2 * ctx->K * ctx->n);
         cudaError_t e = launch_mac(ctx->dP, a, ctx->stream);
         if (e != cudaSuccess) { rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); break; }
     }
     dev_free(ctx, scratch);
     return rc;
+}
+
+// Host (SEAL layout, limb stride n+1) -> device (stride n): one contiguous H2D copy into a staging buffer, then a
+// re-stride kernel, all on `s`.  Small uploads keep the single strided copy.
+int upload_rows(crcnn_ctx *ctx, const uint64_t *host, size_t rows, uint64_t *dst, cudaStream_t s) {
+    const size_t n = ctx->n;
+    if (rows * n * 8 < (8u << 20)) {
+        CU(cudaMemcpy2DAsync(dst, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, s));
+        return CRCNN_OK;
+    }
+    uint64_t *stage = nullptr;
+    CU(cudaMallocAsync((void **)&stage, rows * (n + 1) * 8, s));
+    cudaError_t e = cudaMemcpyAsync(stage, host, rows * (n + 1) * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = launch_strip_pad(stage, dst, (long)rows, (int)n, s);
+    cudaFreeAsync(stage, s);
+    if (e != cudaSuccess) return fail(ctx, CRCNN_ERR_CUDA, std::string("upload: ") + cudaGetErrorString(e));
+    return CRCNN_OK;
 }
 
 }  // namespace
@@ -383,10 +437,14 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
     };
     cudaError_t e = cudaSuccess;
     for (int s = 0; s < slots && e == cudaSuccess; s++) {
-        e = up(hp.w[s], &hp.d.tab[s].w);
-        if (e == cudaSuccess) e = up(hp.wp[s], &hp.d.tab[s].wp);
-        if (e == cudaSuccess) e = up(hp.iwf[s], &hp.d.tab[s].iw);
-        if (e == cudaSuccess) e = up(hp.iwfp[s], &hp.d.tab[s].iwp);
+        // one 128-bit load per butterfly fetches the twiddle and its Shoup companion
+        std::vector<uint64_t> fw(2 * (size_t)n), bw(2 * (size_t)n);
+        for (int i = 0; i < n; i++) {
+            fw[2 * i] = hp.w[s][i]; fw[2 * i + 1] = hp.wp[s][i];
+            bw[2 * i] = hp.iwf[s][i]; bw[2 * i + 1] = hp.iwfp[s][i];
+        }
+        e = up(fw, &hp.d.tab[s].w);
+        if (e == cudaSuccess) e = up(bw, &hp.d.tab[s].iw);
         hp.d.tab[s].tf = nullptr;
         if (e == cudaSuccess && s < K) e = up(hp.tf[s], &hp.d.tab[s].tf);
     }
@@ -439,7 +497,7 @@ int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes) {
 
 int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size_t scratch_bytes) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
-    REQUIRE(mode == 0 || mode == 1, "tensor-core mode must be 0 or 1");
+    REQUIRE(mode >= 0 && mode <= 2, "tensor-core mode must be 0, 1 or 2");
     ctx->tc_mode = mode;
     if (min_fanin > 0) ctx->tc_min_fanin = min_fanin;
     if (scratch_bytes > 0) ctx->tc_scratch_bytes = scratch_bytes;
@@ -466,7 +524,11 @@ int crcnn_tensor_upload_ex(crcnn_ctx *ctx, const uint64_t *host, long count, int
     int rc = new_tensor(ctx, count, size, ntt_form ? 1 : 0, &t);
     if (rc) return rc;
     const size_t n = ctx->n, rows = (size_t)count * size * ctx->K;
-    if (rows) CU(cudaMemcpy2DAsync(t->d, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, ctx->stream));
+    if (rows) {
+        int rc2 = upload_rows(ctx, host, rows, t->d, ctx->stream);
+        if (rc2) { crcnn_tensor_free(ctx, t); return rc2; }
+    }
+    (void)n;
     *out = t;
     return CRCNN_OK;
 }
@@ -480,8 +542,9 @@ int crcnn_tensor_upload_on(crcnn_ctx *ctx, const uint64_t *host, long count, int
     const size_t n = ctx->n, rows = (size_t)count * size * ctx->K;
     if (rows) {
         cudaError_t e = cudaMallocAsync((void **)&t->d, rows * n * 8, cs);
-        if (e == cudaSuccess) e = cudaMemcpy2DAsync(t->d, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, cs);
         if (e != cudaSuccess) { delete t; return fail(ctx, e == cudaErrorMemoryAllocation ? CRCNN_ERR_OUT_OF_MEMORY : CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+        int rc2 = upload_rows(ctx, host, rows, t->d, cs);
+        if (rc2) { cudaFreeAsync(t->d, cs); delete t; return rc2; }
     }
     *out = t;
     return CRCNN_OK;
@@ -638,7 +701,7 @@ int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     if (!p) return CRCNN_OK;
     dev_free(ctx, p->d_off); dev_free(ctx, p->d_idx); dev_free(ctx, p->d_val);
-    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A);
+    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_mul_sh); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A);
     delete p;
     return CRCNN_OK;
 }
@@ -790,15 +853,16 @@ int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int 
     int rc = CRCNN_OK;
     if (scale) {
         rc = ensure_domain(ctx, in, 1);
-        if (!rc) rc = ensure_form(ctx, scale, PF_NTT_MUL);
+        if (!rc) rc = ensure_shoup(ctx, scale);
         if (rc) return rc;
     }
     crcnn_tensor *o = nullptr;
     rc = new_tensor(ctx, Nout, 2, in->ntt, &o);
     if (rc) return rc;
     {
-        ProfScope ps(ctx, KC_POOL);
-        cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nout, R, scale ? scale->ntt_mul : nullptr, o->d, ctx->stream);
+        ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)in->count + Nout) * 2 * ctx->K), (double)Nout * R * 2 * ctx->K * ctx->n);
+        cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nout, R, scale ? scale->ntt_mul : nullptr,
+                                    scale ? scale->ntt_mul_sh : nullptr, sum_fits_64(ctx, R), o->d, ctx->stream);
         if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
     }
     *out = o;
@@ -815,14 +879,14 @@ int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd
     CU(cudaSetDevice(ctx->device));
     int rc = ensure_domain(ctx, in, 1);
     if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
-    if (!rc) rc = ensure_form(ctx, invstd, PF_NTT_MUL);
+    if (!rc) rc = ensure_shoup(ctx, invstd);
     if (rc) return rc;
     crcnn_tensor *o = nullptr;
     rc = new_tensor(ctx, in->count, 2, 1, &o);
     if (rc) return rc;
     {
-        ProfScope ps(ctx, KC_BN);
-        cudaError_t e = launch_bn(ctx->dP, ctx->n, ctx->K, in->d, in->count, xd * yd, zd, mean->ntt_add, invstd->ntt_mul, o->d, ctx->stream);
+        ProfScope ps(ctx, KC_BN, lp_bytes(ctx, (double)in->count * 4 * ctx->K), (double)in->count * 2 * ctx->K * ctx->n);
+        cudaError_t e = launch_bn(ctx->dP, ctx->n, ctx->K, in->d, in->count, xd * yd, zd, mean->ntt_add, invstd->ntt_mul, invstd->ntt_mul_sh, o->d, ctx->stream);
         if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
     }
     *out = o;
@@ -850,11 +914,12 @@ int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3) {
     for (long c0 = 0; c0 < in->count && !rc; c0 += step) {
         const long cur = std::min<long>(step, in->count - c0);
         cudaError_t e;
-        { ProfScope ps(ctx, KC_BEHZ_LIFT); e = launch_behz_lift(ctx->dP, ctx->n, in->d + c0 * 2 * pw, cur, ext, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_FWD); e = launch_ntt(ctx->dP, ctx->logn, ext, cur * 2 * KS, 0, KS, false, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_SQ_TENSOR); e = launch_square_tensor(ctx->dP, ctx->n, KS, ext, cur, prod, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV); e = launch_ntt(ctx->dP, ctx->logn, prod, cur * 3 * KS, 0, KS, true, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_FLOOR); e = launch_behz_floor(ctx->dP, ctx->n, prod, cur, o->d + c0 * 3 * pw, ctx->stream); }
+        { ProfScope ps(ctx, KC_BEHZ_LIFT, lp_bytes(ctx, (double)cur * 2 * (ctx->K + KS)), (double)cur * 2 * n * ctx->S * (ctx->K + 1)); e = launch_behz_lift(ctx->hp.d, ctx->n, in->d + c0 * 2 * pw, cur, ext, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_FWD, 2 * lp_bytes(ctx, (double)cur * 2 * KS), lp_bfly(ctx, (double)cur * 2 * KS)); e = launch_ntt(ctx->dP, ctx->logn, ext, cur * 2 * KS, 0, KS, false, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_SQ_TENSOR, lp_bytes(ctx, (double)cur * 5 * KS), (double)cur * 3 * KS * n); e = launch_square_tensor(ctx->dP, ctx->n, KS, ext, cur, prod, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)cur * 3 * KS), lp_bfly(ctx, (double)cur * 3 * KS)); e = launch_ntt(ctx->dP, ctx->logn, prod, cur * 3 * KS, 0, KS, true, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_FLOOR, lp_bytes(ctx, (double)cur * 3 * (KS + ctx->K)),
+                                                     (double)cur * 3 * n * (ctx->S * (ctx->K + 1) + ctx->S + ctx->K * ctx->S)); e = launch_behz_floor(ctx->hp.d, ctx->n, prod, cur, o->d + c0 * 3 * pw, ctx->stream); }
         if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
     }
     dev_free(ctx, ext); dev_free(ctx, prod);
@@ -899,9 +964,9 @@ int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_t
         a.in3 = in3->d + c0 * 3 * pw;
         a.out = o->d + c0 * 2 * pw;
         cudaError_t e;
-        { ProfScope ps(ctx, KC_RELIN); e = launch_relin(ctx->dP, ctx->logn, ctx->K, a, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV); e = launch_ntt(ctx->dP, ctx->logn, a.acc, a.count * 2 * ctx->K, 0, ctx->K, true, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_PLAIN_OP); e = launch_relin_finish(ctx->dP, ctx->n, ctx->K, a, ctx->stream); }
+        { ProfScope ps(ctx, KC_RELIN, lp_bytes(ctx, (double)a.count * 3 * ctx->K), lp_bfly(ctx, (double)a.count * total_digits * ctx->K)); e = launch_relin(ctx->dP, ctx->logn, ctx->K, a, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)a.count * 2 * ctx->K), lp_bfly(ctx, (double)a.count * 2 * ctx->K)); e = launch_ntt(ctx->dP, ctx->logn, a.acc, a.count * 2 * ctx->K, 0, ctx->K, true, ctx->stream); }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_PLAIN_OP, lp_bytes(ctx, (double)a.count * 6 * ctx->K), (double)a.count * 2 * ctx->K * ctx->n); e = launch_relin_finish(ctx->dP, ctx->n, ctx->K, a, ctx->stream); }
         if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
     }
     dev_free(ctx, scratch);
@@ -952,7 +1017,7 @@ int crcnn_plain_op(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_plain *p, long index, 
         if (rc) return rc;
         pl = (t->ntt ? p->ntt_add : p->coef_add) + index * poly_words(ctx);
     }
-    ProfScope ps(ctx, KC_PLAIN_OP);
+    ProfScope ps(ctx, KC_PLAIN_OP, lp_bytes(ctx, (double)t->count * (op == 0 ? t->size : 1) * 2 * ctx->K), (double)t->count * (op == 0 ? t->size : 1) * ctx->K * ctx->n);
     CU(launch_plain_op(ctx->dP, ctx->n, ctx->K, t->d, t->count, t->size, pl, op, ctx->stream));
     return CRCNN_OK;
 }
@@ -976,8 +1041,9 @@ int crcnn_add_many(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_tensor **out) {
     crcnn_tensor *o = nullptr;
     int rc = new_tensor(ctx, 1, 2, t->ntt, &o);
     if (rc) return rc;
-    ProfScope ps(ctx, KC_POOL);
-    cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, t->d, d_index, 1, (int)t->count, nullptr, o->d, ctx->stream);
+    ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)t->count + 1) * 2 * ctx->K), (double)t->count * 2 * ctx->K * ctx->n);
+    cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, t->d, d_index, 1, (int)t->count, nullptr, nullptr,
+                                sum_fits_64(ctx, t->count), o->d, ctx->stream);
     if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
     *out = o;
     return CRCNN_OK;
@@ -992,7 +1058,7 @@ int crcnn_prof_enable(crcnn_ctx *ctx, int on) {
 int crcnn_prof_reset(crcnn_ctx *ctx) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     prof_collect(ctx);
-    for (int i = 0; i < KC_COUNT; i++) { ctx->launches[i] = 0; ctx->ms[i] = 0; }
+    for (int i = 0; i < KC_COUNT; i++) { ctx->launches[i] = 0; ctx->ms[i] = 0; ctx->work_bytes[i] = 0; ctx->work_ops[i] = 0; }
     return CRCNN_OK;
 }
 int crcnn_prof_count(crcnn_ctx *ctx) { return ctx ? KC_COUNT : CRCNN_ERR_INVALID_ARGUMENT; }
@@ -1003,6 +1069,14 @@ int crcnn_prof_get(crcnn_ctx *ctx, int cls, char *name, long *launches, double *
     if (name) { strncpy(name, kClassNames[cls], 31); name[31] = 0; }
     if (launches) *launches = ctx->launches[cls];
     if (ms) *ms = ctx->ms[cls];
+    return CRCNN_OK;
+}
+
+int crcnn_prof_get_work(crcnn_ctx *ctx, int cls, double *bytes, double *ops) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(cls >= 0 && cls < KC_COUNT, "bad kernel class");
+    if (bytes) *bytes = ctx->work_bytes[cls];
+    if (ops) *ops = ctx->work_ops[cls];
     return CRCNN_OK;
 }
 

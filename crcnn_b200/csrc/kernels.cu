@@ -289,29 +289,51 @@ cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t str
 // =====================================================================================
 // pooling (window sums, optional NTT-domain scale)
 // =====================================================================================
+// grid.x = 1 KB... (word chunk of 512 residues) fastest, then the output ciphertext: the CTAs resident together work on a
+// handful of neighbouring outputs, so overlapping windows (2x2 stride 1 reads every input 4 times) are served by L2.
+// SMALL: R * max(q) < 2^64, the window sum fits 64 bits.  scale_sh = Shoup companions of `scale` (floor(s * 2^64 / q)).
+template <bool SMALL>
 __global__ void __launch_bounds__(256)
 pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, const int *__restrict__ in_index,
-            int R, const uint64_t *__restrict__ scale, uint64_t *__restrict__ out) {
+            int R, const uint64_t *__restrict__ scale, const uint64_t *__restrict__ scale_sh, uint64_t *__restrict__ out) {
     // two adjacent residues per thread: 128-bit loads and stores
     const int n = P->n, K = P->K;
     const long ctw = 2L * K * n;
-    const long o = blockIdx.x;
-    const long word = ((long)blockIdx.y * 256 + threadIdx.x) * 2;  // within the ciphertext
+    const int chunks = (int)(ctw / 512);
+    const long o = blockIdx.x / chunks;
+    const long word = ((long)(blockIdx.x % chunks) * 256 + threadIdx.x) * 2;  // within the ciphertext
     const int j = (int)((word / n) % K);
     const Mod mod = P->tab[j].mod;
-    U128 s0{0, 0}, s1{0, 0};
-    for (int r = 0; r < R; r++) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word));
-        add128_64(s0, v.x);
-        add128_64(s1, v.y);
-    }
     ulonglong2 res;
-    res.x = barrett128(s0, mod);
-    res.y = barrett128(s1, mod);
+    if (SMALL) {
+        uint64_t s0 = 0, s1 = 0;
+        for (int r = 0; r < R; r++) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word));
+            s0 += v.x;
+            s1 += v.y;
+        }
+        res.x = s0; res.y = s1;  // reduced below (Shoup product and reduce64 accept any 64-bit value)
+    } else {
+        U128 s0{0, 0}, s1{0, 0};
+        for (int r = 0; r < R; r++) {
+            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word));
+            add128_64(s0, v.x);
+            add128_64(s1, v.y);
+        }
+        res.x = barrett128(s0, mod);
+        res.y = barrett128(s1, mod);
+    }
     if (scale) {
-        const ulonglong2 sc = __ldg(reinterpret_cast<const ulonglong2 *>(scale + (long)j * n + word % n));
-        res.x = mulmod(res.x, sc.x, mod);
-        res.y = mulmod(res.y, sc.y, mod);
+        const long lw = (long)j * n + word % n;
+        const ulonglong2 sc = __ldg(reinterpret_cast<const ulonglong2 *>(scale + lw));
+        const ulonglong2 sh = __ldg(reinterpret_cast<const ulonglong2 *>(scale_sh + lw));
+        res.x = mulshoup_lazy(res.x, sc.x, sh.x, mod.q);
+        res.y = mulshoup_lazy(res.y, sc.y, sh.y, mod.q);
+        res.x = res.x >= mod.q ? res.x - mod.q : res.x;
+        res.y = res.y >= mod.q ? res.y - mod.q : res.y;
+    } else if (SMALL) {
+        res.x = reduce64(res.x, mod);
+        res.y = reduce64(res.y, mod);
     }
     *reinterpret_cast<ulonglong2 *>(out + o * ctw + word) = res;
 }
@@ -319,28 +341,50 @@ pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in,
 // =====================================================================================
 // batch-norm and evaluator-level plaintext ops
 // =====================================================================================
+// invstd_sh = Shoup companions of invstd: the product is one mulhi + two mullo instead of a 128-bit Barrett,
+// which leaves the kernel bound by HBM instead of by the integer pipe.
 __global__ void __launch_bounds__(256)
 bn_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, int per_channel, int channels,
-          const uint64_t *__restrict__ mean, const uint64_t *__restrict__ invstd, uint64_t *__restrict__ out) {
+          const uint64_t *__restrict__ mean, const uint64_t *__restrict__ invstd, const uint64_t *__restrict__ invstd_sh,
+          uint64_t *__restrict__ out) {
     const int n = P->n, K = P->K;
     const long pw = (long)K * n, ctw = 2 * pw;
-    const long ct = blockIdx.x;
-    const long word = ((long)blockIdx.y * 256 + threadIdx.x) * 2;  // two adjacent residues per thread
+    const int chunks = (int)(ctw / 512);
+    const long ct = blockIdx.x / chunks;
+    const long word = ((long)(blockIdx.x % chunks) * 256 + threadIdx.x) * 2;  // two adjacent residues per thread
     const int poly = (int)(word / pw);
     const long lw = word - poly * pw;  // j*n + c
     const int j = (int)(lw / n);
     const int z = (int)((ct / per_channel) % channels);
-    const Mod mod = P->tab[j].mod;
+    const uint64_t q = P->tab[j].mod.q;
     ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(in + ct * ctw + word));
     if (poly == 0) {
         const ulonglong2 m = __ldg(reinterpret_cast<const ulonglong2 *>(mean + z * pw + lw));
-        x.x = submod(x.x, m.x, mod.q);
-        x.y = submod(x.y, m.y, mod.q);
+        x.x = submod(x.x, m.x, q);
+        x.y = submod(x.y, m.y, q);
     }
     const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(invstd + z * pw + lw));
-    x.x = mulmod(x.x, v.x, mod);
-    x.y = mulmod(x.y, v.y, mod);
+    const ulonglong2 vs = __ldg(reinterpret_cast<const ulonglong2 *>(invstd_sh + z * pw + lw));
+    x.x = mulshoup_lazy(x.x, v.x, vs.x, q);
+    x.y = mulshoup_lazy(x.y, v.y, vs.y, q);
+    x.x = x.x >= q ? x.x - q : x.x;
+    x.y = x.y >= q ? x.y - q : x.y;
     *reinterpret_cast<ulonglong2 *>(out + ct * ctw + word) = x;
+}
+
+// Shoup companions floor(v * 2^64 / q) of canonical residues v (data = [..][K][n]); runs once per plaintext pack.
+__global__ void __launch_bounds__(256)
+shoup_companion_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ data, long words, uint64_t *__restrict__ out) {
+    const long w = (long)blockIdx.x * 256 + threadIdx.x;
+    if (w >= words) return;
+    const uint64_t q = P->tab[(w / P->n) % P->K].mod.q;
+    out[w] = (uint64_t)((((unsigned __int128)__ldg(data + w)) << 64) / q);
+}
+
+cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, long words, uint64_t *out, cudaStream_t stream) {
+    if (words <= 0) return cudaSuccess;
+    shoup_companion_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(P, data, words, out);
+    return cudaGetLastError();
 }
 
 __global__ void __launch_bounds__(256)
@@ -367,33 +411,40 @@ plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data,
 // y_i = x_i * m_tilde*(q/q_i)^-1 mod q_i and r = -(sum_i y_i (q/q_i)) * q^-1 mod 2^32 (not centred), the
 // output residue mod p_k is ((sum_i y_i (q/q_i) + q r) * m_tilde^-1) mod p_k; the constant factors are
 // folded (lift_a, lift_b) so each residue is one lazy 128-bit sum and one Barrett reduction.
+// KT/ST > 0: K and S are compile-time (loops unroll exactly, every constant is an immediate constant-bank operand
+// because the parameter block is passed by value); KT == 0: any K <= MAXK, S <= MAXS at run time.
+template <int KT, int ST>
 __global__ void __launch_bounds__(128)
-behz_lift_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, uint64_t *__restrict__ ext) {
-    const int n = P->n, K = P->K, S = P->S;
+behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restrict__ in, uint64_t *__restrict__ ext) {
+    const int n = P.n, K = KT ? KT : P.K, S = KT ? ST : P.S;
+    constexpr int KB = KT ? KT : MAXK, SB = KT ? ST : MAXS;
     const int per = n / 128;
     const long poly = blockIdx.x / per;  // ct*2 + p
     const int c = (blockIdx.x % per) * 128 + threadIdx.x;
     const uint64_t *src = in + poly * K * n + c;
     uint64_t *dst = ext + poly * (K + S) * n + c;
-    uint64_t y[MAXK];
+    uint64_t y[KB];
     uint32_t zmt = 0;
 #pragma unroll
-    for (int i = 0; i < MAXK; i++) {
+    for (int i = 0; i < KB; i++) {
         if (i < K) {
             uint64_t x = __ldg(src + (long)i * n);
             dst[(long)i * n] = x;
-            y[i] = mulmod(x, P->mt_inv_qhat[i], P->tab[i].mod);
-            zmt += (uint32_t)y[i] * (uint32_t)P->qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
+            y[i] = mulmod(x, P.mt_inv_qhat[i], P.tab[i].mod);
+            zmt += (uint32_t)y[i] * (uint32_t)P.qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
         }
     }
-    const uint32_t r = zmt * (uint32_t)P->neg_inv_q_mod_mt;  // (-(z * q^-1)) mod 2^32, in [0, 2^32)
-    for (int k = 0; k < S; k++) {
-        Acc7 acc = acc7_zero();
+    const uint32_t r = zmt * (uint32_t)P.neg_inv_q_mod_mt;  // (-(z * q^-1)) mod 2^32, in [0, 2^32)
 #pragma unroll
-        for (int i = 0; i < MAXK; i++)
-            if (i < K) mac7(acc, y[i], P->lift_a[k][i]);
-        mac7(acc, (uint64_t)r, P->lift_b[k]);
-        dst[(long)(K + k) * n] = barrett128(acc7_value(acc), P->tab[K + k].mod);
+    for (int k = 0; k < SB; k++) {
+        if (k < S) {
+            Acc7 acc = acc7_zero();
+#pragma unroll
+            for (int i = 0; i < KB; i++)
+                if (i < K) mac7(acc, y[i], P.lift_a[k][i]);
+            mac7(acc, (uint64_t)r, P.lift_b[k]);
+            dst[(long)(K + k) * n] = barrett128(acc7_value(acc), P.tab[K + k].mod);
+        }
     }
 }
 
@@ -423,47 +474,51 @@ square_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restr
 //   g_k   = f_k (M/m_k)^-1                            mod m_k, k < L
 //   alpha = (sum_k g_k (M/m_k) - f_sk) M^-1           mod m_sk, centred
 //   out_j = sum_k g_k (M/m_k) - alpha M               mod q_j      (fastbconv_sk)
+template <int KT, int ST>
 __global__ void __launch_bounds__(128)
-behz_floor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ prod, uint64_t *__restrict__ out) {
-    const int n = P->n, K = P->K, S = P->S, L = P->L;
+behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restrict__ prod, uint64_t *__restrict__ out) {
+    const int n = P.n, K = KT ? KT : P.K, S = KT ? ST : P.S, L = S - 1;
+    constexpr int KB = KT ? KT : MAXK, SB = KT ? ST : MAXS;
     const int per = n / 128;
     const long poly = blockIdx.x / per;  // ct*3 + p
     const int c = (blockIdx.x % per) * 128 + threadIdx.x;
     const uint64_t *src = prod + poly * (K + S) * n + c;
     uint64_t *dst = out + poly * K * n + c;
-    uint64_t u[MAXK], g[MAXS];
+    uint64_t u[KB], g[SB];
 #pragma unroll
-    for (int i = 0; i < MAXK; i++)
-        if (i < K) u[i] = mulmod(__ldg(src + (long)i * n), P->fl_c[i], P->tab[i].mod);
+    for (int i = 0; i < KB; i++)
+        if (i < K) u[i] = mulmod(__ldg(src + (long)i * n), P.fl_c[i], P.tab[i].mod);
     uint64_t f_sk = 0;
 #pragma unroll
-    for (int k = 0; k < MAXS; k++)
+    for (int k = 0; k < SB; k++)
         if (k < S) {
             Acc7 acc = acc7_zero();
-            mac7(acc, __ldg(src + (long)(K + k) * n), P->fl_T[k]);
+            mac7(acc, __ldg(src + (long)(K + k) * n), P.fl_T[k]);
 #pragma unroll
-            for (int i = 0; i < MAXK; i++)
-                if (i < K) mac7(acc, u[i], P->fl_N[k][i]);
-            uint64_t v = barrett128(acc7_value(acc), P->tab[K + k].mod);
+            for (int i = 0; i < KB; i++)
+                if (i < K) mac7(acc, u[i], P.fl_N[k][i]);
+            uint64_t v = barrett128(acc7_value(acc), P.tab[K + k].mod);
             if (k < L) g[k] = v; else f_sk = v;
         }
-    const Mod msk = P->tab[K + L].mod;
+    const Mod msk = P.tab[K + L].mod;
     Acc7 acc = acc7_zero();
 #pragma unroll
-    for (int i = 0; i < MAXS; i++)
-        if (i < L) mac7(acc, g[i], P->fl_P[i]);
-    mac7(acc, msk.q - f_sk, P->inv_M_mod_msk);
+    for (int i = 0; i < SB; i++)
+        if (i < L) mac7(acc, g[i], P.fl_P[i]);
+    mac7(acc, msk.q - f_sk, P.inv_M_mod_msk);
     const uint64_t alpha = barrett128(acc7_value(acc), msk);
     const bool centered_neg = alpha > (msk.q >> 1);  // baseconverter.cpp:547-577
     const uint64_t alpha_mag = centered_neg ? msk.q - alpha : alpha;
-    for (int j = 0; j < K; j++) {
-        Acc7 e = acc7_zero();
 #pragma unroll
-        for (int i = 0; i < MAXS; i++)
-            if (i < L) mac7(e, g[i], P->Mhat_mod_q[j][i]);
-        mac7(e, alpha_mag, centered_neg ? P->M_mod_q[j] : P->neg_M_mod_q[j]);
-        dst[(long)j * n] = barrett128(acc7_value(e), P->tab[j].mod);
-    }
+    for (int j = 0; j < KB; j++)
+        if (j < K) {
+            Acc7 e = acc7_zero();
+#pragma unroll
+            for (int i = 0; i < SB; i++)
+                if (i < L) mac7(e, g[i], P.Mhat_mod_q[j][i]);
+            mac7(e, alpha_mag, centered_neg ? P.M_mod_q[j] : P.neg_M_mod_q[j]);
+            dst[(long)j * n] = barrett128(acc7_value(e), P.tab[j].mod);
+        }
 }
 
 // relinearize 3 -> 2 (evaluator.cpp:934-1069), staged so every transform runs in the tuned NTT
@@ -601,19 +656,21 @@ cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const Relin
 // simple launch wrappers
 // =====================================================================================
 cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout,
-                           int R, const uint64_t *scale_ntt, uint64_t *out, cudaStream_t stream) {
+                           int R, const uint64_t *scale_ntt, const uint64_t *scale_shoup, bool sum_fits_64, uint64_t *out,
+                           cudaStream_t stream) {
     if (Nout <= 0) return cudaSuccess;
-    dim3 grid(Nout, (unsigned)(2L * K * n / 512));
-    pool_kernel<<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, out);
+    const unsigned grid = (unsigned)((long)Nout * (2L * K * n / 512));
+    if (sum_fits_64) pool_kernel<true><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out);
+    else pool_kernel<false><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, long count, int per_channel,
-                         int channels, const uint64_t *mean_ntt, const uint64_t *invstd_ntt, uint64_t *out,
-                         cudaStream_t stream) {
+                         int channels, const uint64_t *mean_ntt, const uint64_t *invstd_ntt, const uint64_t *invstd_shoup,
+                         uint64_t *out, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    dim3 grid((unsigned)count, (unsigned)(2L * K * n / 512));
-    bn_kernel<<<grid, 256, 0, stream>>>(P, in, per_channel, channels, mean_ntt, invstd_ntt, out);
+    const unsigned grid = (unsigned)(count * (2L * K * n / 512));
+    bn_kernel<<<grid, 256, 0, stream>>>(P, in, per_channel, channels, mean_ntt, invstd_ntt, invstd_shoup, out);
     return cudaGetLastError();
 }
 
@@ -625,10 +682,20 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
     return cudaGetLastError();
 }
 
-cudaError_t launch_behz_lift(const DeviceParams *P, int n, const uint64_t *in, long count, uint64_t *ext,
+// K and S pairs of SEAL's default parameter sets get exact-size kernels (n = 4096: 2/3, 8192: 4/5, 16384: 8/9)
+#define CRCNN_BEHZ_DISPATCH(KERNEL, GRID, ...)                                                        \
+    do {                                                                                             \
+        if (hp.K == 2 && hp.S == 3) KERNEL<2, 3><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);          \
+        else if (hp.K == 4 && hp.S == 5) KERNEL<4, 5><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);     \
+        else if (hp.K == 8 && hp.S == 9) KERNEL<8, 9><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);     \
+        else KERNEL<0, 0><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);                                 \
+    } while (0)
+
+cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, long count, uint64_t *ext,
                                 cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    behz_lift_kernel<<<(unsigned)(count * 2 * (n / 128)), 128, 0, stream>>>(P, in, ext);
+    const unsigned grid = (unsigned)(count * 2 * (n / 128));
+    CRCNN_BEHZ_DISPATCH(behz_lift_kernel, grid, in, ext);
     return cudaGetLastError();
 }
 
@@ -640,10 +707,11 @@ cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uin
     return cudaGetLastError();
 }
 
-cudaError_t launch_behz_floor(const DeviceParams *P, int n, const uint64_t *prod, long count, uint64_t *out,
+cudaError_t launch_behz_floor(const DeviceParams &hp, int n, const uint64_t *prod, long count, uint64_t *out,
                                  cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    behz_floor_kernel<<<(unsigned)(count * 3 * (n / 128)), 128, 0, stream>>>(P, prod, out);
+    const unsigned grid = (unsigned)(count * 3 * (n / 128));
+    CRCNN_BEHZ_DISPATCH(behz_floor_kernel, grid, prod, out);
     return cudaGetLastError();
 }
 
@@ -663,6 +731,25 @@ canonicalize_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ d
 cudaError_t launch_canonicalize(const DeviceParams *P, uint64_t *data, long words, cudaStream_t stream) {
     if (words <= 0) return cudaSuccess;
     canonicalize_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(P, data, words);
+    return cudaGetLastError();
+}
+
+// =====================================================================================
+// SEAL host layout <-> device layout: a limb-polynomial is n+1 words on the host (trailing pad word),
+// n words on the device.  Uploads arrive as ONE contiguous copy (a strided cudaMemcpy2D from pinned memory
+// reaches only a fraction of the PCIe rate) and are re-strided here; rows start 8-byte aligned only.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+strip_pad_kernel(const uint64_t *__restrict__ src, uint64_t *__restrict__ dst, int n) {
+    const long row = blockIdx.x;
+    const uint64_t *s = src + row * (n + 1);
+    uint64_t *d = dst + row * n;
+    for (int i = threadIdx.x; i < n; i += 256) d[i] = __ldg(s + i);
+}
+
+cudaError_t launch_strip_pad(const uint64_t *src_padded, uint64_t *dst, long rows, int n, cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    strip_pad_kernel<<<(unsigned)rows, 256, 0, stream>>>(src_padded, dst, n);
     return cudaGetLastError();
 }
 

@@ -33,13 +33,19 @@ struct MacArgs {
 cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t stream);
 
 // ---- window sum (sum-pool / avg-pool): out[o] = (sum_r in[in_index[o][r]]) (* scale[K][n] if given)
+// scale_shoup = Shoup companions of scale_ntt (launch_shoup_companion); sum_fits_64: R * max(q) < 2^64
 cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout, int R,
-                        const uint64_t *scale_ntt, uint64_t *out, cudaStream_t stream);
+                        const uint64_t *scale_ntt, const uint64_t *scale_shoup, bool sum_fits_64, uint64_t *out,
+                        cudaStream_t stream);
 
 // ---- batch-norm, NTT domain: c0' = (c0 - mean_ntt[z]) * invstd_ntt[z], c1' = c1 * invstd_ntt[z]
 // ciphertext i belongs to channel (i / per_channel) % channels.
 cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, long count, int per_channel, int channels,
-                      const uint64_t *mean_ntt, const uint64_t *invstd_ntt, uint64_t *out, cudaStream_t stream);
+                      const uint64_t *mean_ntt, const uint64_t *invstd_ntt, const uint64_t *invstd_shoup, uint64_t *out,
+                      cudaStream_t stream);
+
+// ---- Shoup companions floor(v * 2^64 / q_j) of `words` canonical residues laid out [..][K][n]
+cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, long words, uint64_t *out, cudaStream_t stream);
 
 // ---- generic plaintext ops on `count` ciphertexts of `size` polys (evaluator-level API)
 // op 0: every poly *= pl (pl in NTT lifted form, data in NTT form); op 1/2: poly0 +=/-= pl (scaled form,
@@ -49,11 +55,13 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
 
 // ---- FV square (BEHZ), staged exactly as evaluator.cpp:742-883
 // lift:   in [count][2][K][n] (coefficient form) -> ext [count][2][K+S][n] (q limbs copied, Bsk limbs computed)
-cudaError_t launch_behz_lift(const DeviceParams *P, int n, const uint64_t *in, long count, uint64_t *ext, cudaStream_t stream);
+// (lift and floor take the HOST copy of the parameter block: it travels as a by-value kernel argument, so every
+// base-conversion constant is a constant-bank operand)
+cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, long count, uint64_t *ext, cudaStream_t stream);
 // tensor: ext (NTT form) -> prod [count][3][K+S][n] (NTT form): c0^2, 2 c0 c1, c1^2
 cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uint64_t *ext, long count, uint64_t *prod, cudaStream_t stream);
 // floor:  prod (coefficient form) -> out [count][3][K][n]: multiply by t, fast_floor, fastbconv_sk
-cudaError_t launch_behz_floor(const DeviceParams *P, int n, const uint64_t *prod, long count, uint64_t *out, cudaStream_t stream);
+cudaError_t launch_behz_floor(const DeviceParams &hp, int n, const uint64_t *prod, long count, uint64_t *out, cudaStream_t stream);
 
 // ---- relinearize 3 -> 2 with 16-bit digits (evaluator.cpp:934-1069)
 // in3 [count][3][K][n] (coefficient), keys: for prime i, digit k: polys (2k, 2k+1) at
@@ -75,6 +83,9 @@ cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const Relin
 
 // ---- residues stored lazily in [0,4q) (evaluation keys) -> canonical, in place; data = [..][K][n]
 cudaError_t launch_canonicalize(const DeviceParams *P, uint64_t *data, long words, cudaStream_t stream);
+
+// ---- host layout (limb stride n+1) -> device layout (stride n) for `rows` limb-polynomials already on the device
+cudaError_t launch_strip_pad(const uint64_t *src_padded, uint64_t *dst, long rows, int n, cudaStream_t stream);
 
 // ---- integer-pipe roofline probe: register-only 64x64->128 multiply-accumulate loop.
 // Returns nothing; caller times it.  total MACs = blocks * threads * iters * 8.

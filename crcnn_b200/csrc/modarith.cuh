@@ -145,4 +145,39 @@ CRCNN_HD uint64_t mulshoup_lazy(uint64_t y, uint64_t w, uint64_t wp, uint64_t q)
     return y * w - h * q;
 }
 
+// Cheaper Shoup product for the transforms: the quotient estimate drops the low partial products,
+//   h' = wp1*y1 + hi32(wp1*y0) + hi32(wp0*y1)  in  {h-2, h-1, h},   h = floor(wp*y / 2^64),
+// so the result  y*w - h'*q  (mod 2^64)  is w*y mod q as a representative in [0, 4q) for any 64-bit y
+// (q < 2^62).  nq = 2^64 - q turns the subtraction into a multiply-add: 3 IMAD.WIDE + 2 IMAD.HI + 4 IMAD and
+// two carry adds, against 6 IMAD.WIDE + 5 IMAD and ~9 adds for the exact form.
+CRCNN_HD uint64_t mulshoup_lazy4(uint64_t y, uint64_t w, uint64_t wp, uint64_t nq) {
+#if defined(__CUDA_ARCH__)
+    uint32_t y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32), p0 = (uint32_t)wp, p1 = (uint32_t)(wp >> 32);
+    uint32_t w0 = (uint32_t)w, w1 = (uint32_t)(w >> 32), n0 = (uint32_t)nq, n1 = (uint32_t)(nq >> 32);
+    uint32_t a, b, h0, h1, r0, r1;
+    asm("mul.hi.u32 %0, %2, %3;\n\t"
+        "mul.hi.u32 %1, %4, %5;\n\t"
+        : "=r"(a), "=r"(b) : "r"(p1), "r"(y0), "r"(p0), "r"(y1));
+    asm("mad.lo.cc.u32 %0, %2, %3, %4;\n\t"
+        "madc.hi.u32 %1, %2, %3, 0;\n\t"
+        "add.cc.u32 %0, %0, %5;\n\t"
+        "addc.u32 %1, %1, 0;\n\t"
+        : "=r"(h0), "=r"(h1) : "r"(p1), "r"(y1), "r"(a), "r"(b));
+    asm("mul.lo.u32 %0, %2, %3;\n\t"
+        "mul.hi.u32 %1, %2, %3;\n\t"
+        "mad.lo.cc.u32 %0, %4, %5, %0;\n\t"
+        "madc.hi.u32 %1, %4, %5, %1;\n\t"
+        "mad.lo.u32 %1, %2, %6, %1;\n\t"
+        "mad.lo.u32 %1, %7, %3, %1;\n\t"
+        "mad.lo.u32 %1, %4, %8, %1;\n\t"
+        "mad.lo.u32 %1, %9, %5, %1;\n\t"
+        : "=&r"(r0), "=&r"(r1) : "r"(y0), "r"(w0), "r"(h0), "r"(n0), "r"(w1), "r"(y1), "r"(n1), "r"(h1));
+    return ((uint64_t)r1 << 32) | r0;
+#else
+    uint64_t y0 = (uint32_t)y, y1 = y >> 32, p0 = (uint32_t)wp, p1 = wp >> 32;
+    uint64_t h = p1 * y1 + ((p1 * y0) >> 32) + ((p0 * y1) >> 32);
+    return y * w + h * nq;
+#endif
+}
+
 }  // namespace crcnn

@@ -6,11 +6,13 @@
 // bit-reversed output, Gentleman-Sande inverse, in the reference's own table order
 // (root_powers[bitrev(i)] = psi^i), so NTT-form data made by SEAL (evaluation keys, NTT plaintexts)
 // is interchangeable.  Outputs are canonical [0, q); only the lazy intermediate ranges differ:
-//   * forward: for q < 2^58 the Harvey correction of X is dropped altogether -- values grow by 2q per
-//     stage (< 30q < 2^63 after 14 stages) and are reduced once at the final store; the Shoup product
-//     accepts any 64-bit operand.  61-bit moduli (the Bsk primes of `square`) keep the correction.
+//   * forward: for q < 2^57 the Harvey correction of X is dropped altogether and the Shoup product uses an
+//     approximate quotient (modarith.cuh: mulshoup_lazy4, result in [0,4q)) -- values grow by at most 4q per
+//     stage (< 61q < 2^63 after 14 stages) and are reduced once at the final store.  61-bit moduli (the Bsk
+//     primes of `square`) keep the exact product and the correction.
 //   * inverse: the n^-1 factor is applied once at the end (one Shoup product per residue) instead of a
-//     halving in every butterfly, so the tables hold the plain inverse powers.
+//     halving in every butterfly, so the tables hold the plain inverse powers; for q < 2^57 the butterflies
+//     keep values in [0,4q) with the same approximate product.
 // Both remove ALU-pipe work, which ncu showed to be the binding pipe (profiles/r01b_*).
 //
 // Schedule: log2(n) stages are grouped into passes of 3 or 4 stages done in registers
@@ -46,31 +48,52 @@ struct NttPlan {
     }
 };
 
-// moduli below 2^58 never need the per-stage correction (2q growth per stage stays below 2^63)
-__device__ __forceinline__ bool ntt_needs_correction(uint64_t q) { return (q >> 58) != 0; }
+// Moduli below 2^57 (every coefficient prime SEAL picks for n <= 16384) take the lazy path: the approximate Shoup
+// product (mulshoup_lazy4, result in [0,4q)) and no per-stage correction in the forward transform -- values grow
+// by at most 4q per stage, < 61q < 2^63 after 14 stages, and are reduced once at the final store.  Larger moduli
+// (the 61-bit Bsk primes of `square`) keep the exact product and Harvey's correction.
+__device__ __forceinline__ bool ntt_needs_correction(uint64_t q) { return (q >> 57) != 0; }
 
+// c = nq (2^64 - q) and c2 = 4q on the lazy path; c = q and c2 = 2q on the exact path
 template <bool CORR>
-__device__ __forceinline__ void ct_butterfly(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twoq) {
-    // Harvey butterfly; with CORR x,y in [0,4q) -> [0,4q), without it the bound grows by 2q per stage
-    uint64_t X = (CORR && x >= twoq) ? x - twoq : x;
-    uint64_t Q = mulshoup_lazy(y, W, Wp, q);
-    x = X + Q;
-    y = X + twoq - Q;
+__device__ __forceinline__ void ct_butterfly(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t c, uint64_t c2) {
+    if (CORR) {
+        // Harvey butterfly: x,y in [0,4q) -> [0,4q)
+        uint64_t X = x >= c2 ? x - c2 : x;
+        uint64_t Q = mulshoup_lazy(y, W, Wp, c);
+        x = X + Q;
+        y = X + c2 - Q;
+    } else {
+        uint64_t Q = mulshoup_lazy4(y, W, Wp, c);
+        uint64_t X = x;
+        x = X + Q;
+        y = X + c2 - Q;
+    }
 }
 
-__device__ __forceinline__ void gs_butterfly(uint64_t &u, uint64_t &v, uint64_t W, uint64_t Wp, uint64_t q, uint64_t twoq) {
-    // u, v in [0,2q) -> [0,2q); W = psi^-k (no halving here, n^-1 is applied at the end)
-    uint64_t T = u + twoq - v;
-    uint64_t S = u + v;
-    u = S >= twoq ? S - twoq : S;
-    v = mulshoup_lazy(T, W, Wp, q);
+template <bool CORR>
+__device__ __forceinline__ void gs_butterfly(uint64_t &u, uint64_t &v, uint64_t W, uint64_t Wp, uint64_t c, uint64_t c2) {
+    // W = psi^-k (no halving here, n^-1 is applied at the end)
+    if (CORR) {
+        // exact: u, v in [0,2q) -> [0,2q); c = q, c2 = 2q
+        uint64_t T = u + c2 - v;
+        uint64_t S = u + v;
+        u = S >= c2 ? S - c2 : S;
+        v = mulshoup_lazy(T, W, Wp, c);
+    } else {
+        // lazy: u, v in [0,4q) -> [0,4q); c = nq, c2 = 4q
+        uint64_t T = u + c2 - v;
+        uint64_t S = u + v;
+        u = S >= c2 ? S - c2 : S;
+        v = mulshoup_lazy4(T, W, Wp, c);
+    }
 }
 
 // B forward stages on 2^B residues spaced g apart; m0 = number of blocks at the first stage,
 // blk = this group's block index at that stage.
 template <int B, bool CORR>
-__device__ __forceinline__ void fwd_group(uint64_t (&x)[1 << B], const uint64_t *__restrict__ w,
-                                          const uint64_t *__restrict__ wp, uint64_t q, uint64_t twoq, int m0, int blk) {
+__device__ __forceinline__ void fwd_group(uint64_t (&x)[1 << B], const ulonglong2 *__restrict__ w,
+                                          uint64_t q, uint64_t twoq, int m0, int blk) {
 #pragma unroll
     for (int s = 0; s < B; s++) {
         // stage s: pair distance 2^(B-1-s) (local index), 2^s local blocks each with its own twiddle
@@ -79,15 +102,16 @@ __device__ __forceinline__ void fwd_group(uint64_t (&x)[1 << B], const uint64_t 
             const int lb = pr >> (B - 1 - s), a = pr & ((1 << (B - 1 - s)) - 1);
             const int ia = (lb << (B - s)) + a, ib = ia + (1 << (B - 1 - s));
             const int tw = ((m0 + blk) << s) + lb;
-            ct_butterfly<CORR>(x[ia], x[ib], __ldg(w + tw), __ldg(wp + tw), q, twoq);
+            const ulonglong2 W = __ldg(w + tw);
+            ct_butterfly<CORR>(x[ia], x[ib], W.x, W.y, q, twoq);  // (q, twoq) = (c, c2) of ct_butterfly
         }
     }
 }
 
 // B inverse stages; h0 = n / (2 * distance of the first stage), blk = group index i.
-template <int B>
-__device__ __forceinline__ void inv_group(uint64_t (&x)[1 << B], const uint64_t *__restrict__ iw,
-                                          const uint64_t *__restrict__ iwp, uint64_t q, uint64_t twoq, int h0, int blk) {
+template <int B, bool CORR>
+__device__ __forceinline__ void inv_group(uint64_t (&x)[1 << B], const ulonglong2 *__restrict__ iw,
+                                          uint64_t q, uint64_t twoq, int h0, int blk) {
 #pragma unroll
     for (int s = 0; s < B; s++) {
         // stage s: pair distance 2^s, 2^(B-1-s) local blocks
@@ -96,7 +120,8 @@ __device__ __forceinline__ void inv_group(uint64_t (&x)[1 << B], const uint64_t 
             const int lb = pr >> s, a = pr & ((1 << s) - 1);
             const int ia = (lb << (s + 1)) + a, ib = ia + (1 << s);
             const int tw = (h0 >> s) + (blk << (B - 1 - s)) + lb;
-            gs_butterfly(x[ia], x[ib], __ldg(iw + tw), __ldg(iwp + tw), q, twoq);
+            const ulonglong2 W = __ldg(iw + tw);
+            gs_butterfly<CORR>(x[ia], x[ib], W.x, W.y, q, twoq);
         }
     }
 }
@@ -105,24 +130,25 @@ __device__ __forceinline__ void inv_group(uint64_t (&x)[1 << B], const uint64_t 
 template <int LOGN, int B, bool SRC_GLOBAL, bool CORR>
 __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restrict__ gsrc, const NttTable &tb, int m0, int g) {
     constexpr int N = 1 << LOGN;
-    const uint64_t q = tb.mod.q, twoq = 2 * q;
+    const uint64_t q = CORR ? tb.mod.q : 0 - tb.mod.q, twoq = CORR ? 2 * tb.mod.q : 4 * tb.mod.q;
     for (int G = threadIdx.x; G < (N >> B); G += blockDim.x) {
         int blk = G / g, o = G - blk * g;
         int base = blk * (g << B) + o;
         uint64_t x[1 << B];
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) x[k] = SRC_GLOBAL ? gsrc[base + k * g] : sm[ntt_pad(base + k * g)];
-        fwd_group<B, CORR>(x, tb.w, tb.wp, q, twoq, m0, blk);
+        fwd_group<B, CORR>(x, reinterpret_cast<const ulonglong2 *>(tb.w), q, twoq, m0, blk);
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) sm[ntt_pad(base + k * g)] = x[k];
     }
 }
 
 // DST_GLOBAL marks the last pass: the n^-1 scaling and the canonical store happen there.
-template <int LOGN, int B, bool DST_GLOBAL>
+template <int LOGN, int B, bool DST_GLOBAL, bool CORR>
 __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gdst, const NttTable &tb, int g) {
     constexpr int N = 1 << LOGN;
-    const uint64_t q = tb.mod.q, twoq = 2 * q;
+    const uint64_t q = tb.mod.q;
+    const uint64_t c = CORR ? q : 0 - q, c2 = CORR ? 2 * q : 4 * q;
     const int h0 = N / (2 * g);
     for (int G = threadIdx.x; G < (N >> B); G += blockDim.x) {
         int blk = G / g, o = G - blk * g;
@@ -130,11 +156,11 @@ __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gd
         uint64_t x[1 << B];
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) x[k] = sm[ntt_pad(base + k * g)];
-        inv_group<B>(x, tb.iw, tb.iwp, q, twoq, h0, blk);
+        inv_group<B, CORR>(x, reinterpret_cast<const ulonglong2 *>(tb.iw), c, c2, h0, blk);
 #pragma unroll
         for (int k = 0; k < (1 << B); k++) {
             if (DST_GLOBAL) {
-                uint64_t v = mulshoup_lazy(x[k], tb.ninv, tb.ninvp, q);
+                uint64_t v = mulshoup_lazy(x[k], tb.ninv, tb.ninvp, q);  // exact product: [0,2q) for any 64-bit input
                 gdst[base + k * g] = v >= q ? v - q : v;
             } else {
                 sm[ntt_pad(base + k * g)] = x[k];
@@ -177,19 +203,26 @@ __device__ __forceinline__ void ntt_forward_in_smem(uint64_t *sm, const NttTable
     else ntt_forward_passes<LOGN, FIRST_PASS, false>(sm, nullptr, tb);
 }
 
-// Inverse transform of the polynomial in padded shared memory (values < 2q) -> dst (global, canonical).
-// Pass order mirrors the forward plan (narrow passes first so the last, HBM-writing pass is strided).
-template <int LOGN>
-__device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb) {
+// Inverse transform of the polynomial in padded shared memory (values < 2q, < 4q on the lazy path) -> dst
+// (global, canonical).  Pass order mirrors the forward plan (narrow passes first so the last, HBM-writing pass
+// is strided).
+template <int LOGN, bool CORR>
+__device__ __forceinline__ void ntt_inverse_passes(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb) {
     using P = NttPlan<LOGN>;
     int g = 1;
 #pragma unroll
     for (int p = P::PASSES - 1; p >= 1; p--) {
-        if (P::bits(p) == 4) inv_pass<LOGN, 4, false>(sm, nullptr, tb, g); else inv_pass<LOGN, 3, false>(sm, nullptr, tb, g);
+        if (P::bits(p) == 4) inv_pass<LOGN, 4, false, CORR>(sm, nullptr, tb, g); else inv_pass<LOGN, 3, false, CORR>(sm, nullptr, tb, g);
         g <<= P::bits(p);
         __syncthreads();
     }
-    if (P::bits(0) == 4) inv_pass<LOGN, 4, true>(sm, dst, tb, g); else inv_pass<LOGN, 3, true>(sm, dst, tb, g);
+    if (P::bits(0) == 4) inv_pass<LOGN, 4, true, CORR>(sm, dst, tb, g); else inv_pass<LOGN, 3, true, CORR>(sm, dst, tb, g);
+}
+
+template <int LOGN>
+__device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb) {
+    if (ntt_needs_correction(tb.mod.q)) ntt_inverse_passes<LOGN, true>(sm, dst, tb);
+    else ntt_inverse_passes<LOGN, false>(sm, dst, tb);
 }
 
 // Coalesced copies between global (unpadded) and shared (padded).

@@ -26,10 +26,8 @@ constexpr int MAXDIG = 4;  // 16-bit relinearisation digits per prime (<= 60-bit
 // One NTT modulus with device pointers to its four n-entry tables.
 struct NttTable {
     Mod mod;
-    const uint64_t *w;    // root_powers            (psi^bitrev(i))
-    const uint64_t *wp;   // scaled_root_powers     floor(w * 2^64 / q)
-    const uint64_t *iw;   // inverse root powers psi^-bitrev(i) (NOT pre-halved: the kernels scale by n^-1 once at the end)
-    const uint64_t *iwp;  // its scaled companion
+    const uint64_t *w;    // interleaved (root_power, scaled_root_power) pairs: w[2i] = psi^bitrev(i), w[2i+1] = floor(w[2i] * 2^64 / q)
+    const uint64_t *iw;   // interleaved inverse pairs psi^-bitrev(i) (NOT pre-halved: the kernels scale by n^-1 once at the end)
     uint64_t ninv, ninvp; // n^-1 mod q and floor(n^-1 * 2^64 / q)
     const uint64_t *tf;   // top-block factors for the sparse-input forward transform (see ntt.cuh), 2^skip entries
 };

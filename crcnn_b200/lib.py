@@ -68,6 +68,7 @@ SYMBOLS = [
     ("crcnn_prof_reset", _I, [_vp]),
     ("crcnn_prof_count", _I, [_vp]),
     ("crcnn_prof_get", _I, [_vp, _I, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_double)]),
+    ("crcnn_prof_get_work", _I, [_vp, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("crcnn_probe_imad", _I, [_vp, _I, _I, _I, C.POINTER(C.c_double)]),
 ]
 
@@ -307,6 +308,17 @@ class Engine:
             n, ms = C.c_long(), C.c_double()
             self._chk(self.lib.crcnn_prof_get(self.h, i, name, C.byref(n), C.byref(ms)))
             out[name.value.decode()] = (n.value, ms.value)
+        return out
+
+    def prof_work(self):
+        """{class: (algorithmic bytes, algorithmic ops)} since the last reset (crcnn_prof_get_work)."""
+        out = {}
+        name = C.create_string_buffer(32)
+        for i in range(self.lib.crcnn_prof_count(self.h)):
+            n, ms, b, o = C.c_long(), C.c_double(), C.c_double(), C.c_double()
+            self._chk(self.lib.crcnn_prof_get(self.h, i, name, C.byref(n), C.byref(ms)))
+            self._chk(self.lib.crcnn_prof_get_work(self.h, i, C.byref(b), C.byref(o)))
+            out[name.value.decode()] = (b.value, o.value)
         return out
 
     def probe_imad(self, blocks, threads, iters):

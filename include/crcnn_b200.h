@@ -65,8 +65,10 @@ int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes);
 /* Weighted sums (conv / fc) whose weights are FractionalEncoder base-3 plaintexts with |w| < 1/2 (every
  * weight of the reference's models) and whose fan-in is >= min_fanin run as a u8 x s8 -> s32 GEMM on the
  * tcgen05 tensor cores in the coefficient domain (crcnn_b200/csrc/tc_mac.cuh); results are the same canonical
- * residues.  mode 0 forces the CUDA-core NTT-domain kernel (also the fallback for any other weights).
- * min_fanin <= 0 / scratch_bytes == 0 keep the current values (defaults 64, 12 GiB).  Env CRCNN_TC=0|1 sets the
+ * residues.  mode 0 forces the CUDA-core NTT-domain kernel (also the fallback for any other weights); mode 2 takes the
+ * tensor-core kernel for every eligible layer with fan-in >= min_fanin, however few outputs it has.
+ * min_fanin <= 0 / scratch_bytes == 0 keep the current values (defaults 256, 12 GiB; layers with fewer than 32 outputs also
+ * stay on the CUDA cores: measured on B200 the NTT-domain kernel wins for conv2 (fan-in 180) and fc4 (10 outputs)).  Env CRCNN_TC=0|1 sets the
  * initial mode. */
 int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size_t scratch_bytes);
 /* Derived constants, for cross-checking against SEAL: which = 0 root_powers, 1 scaled_root_powers,
@@ -179,6 +181,11 @@ int crcnn_prof_reset(crcnn_ctx *ctx);
 int crcnn_prof_count(crcnn_ctx *ctx); /* number of kernel classes */
 /* name: >= 32 bytes.  launches counts since the last reset (always maintained); ms only while enabled. */
 int crcnn_prof_get(crcnn_ctx *ctx, int cls, char *name, long *launches, double *ms);
+/* Algorithmic work enqueued for class `cls` since the last reset (SURVEY 8(d) figures, counted at launch time):
+ * bytes = compulsory HBM bytes (every distinct input and output once); ops = butterflies for the NTT classes
+ * (ntt_forward, ntt_inverse, plain_expand_ntt, relinearize), 64x64->128-bit multiply-accumulates or modular
+ * multiplies for the CUDA-core classes, int8 multiply-accumulates for weighted_sum_tc_i8. */
+int crcnn_prof_get_work(crcnn_ctx *ctx, int cls, double *bytes, double *ops);
 /* Register-only 64x64->128-bit multiply-accumulate probe (integer-pipe roofline): runs
  * blocks*threads*iters*8 MACs and returns the elapsed device time in ms. */
 int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms);
