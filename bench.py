@@ -336,6 +336,15 @@ def main_b200(args, rank, world, local_rank):
         ev2[1].record(stream)
         barrier()
         ms_e2e = ev2[0].elapsed_time(ev2[1])
+        # the host link by itself: one plain pinned H2D copy of a step's input (explains e2e when the link is the limit)
+        dev_buf = torch.empty(in_words, dtype=torch.int64, device="cuda")
+        ev3 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev3[0].record(stream)
+        dev_buf.copy_(host_in, non_blocking=True)
+        ev3[1].record(stream)
+        stream.synchronize()
+        h2d_gbs = h2d / ev3[0].elapsed_time(ev3[1]) / 1e6
+        del dev_buf
 
     # max over ranks
     t = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64)
@@ -423,7 +432,7 @@ def main_b200(args, rank, world, local_rank):
                    "l2": "inputs (%.1f GB per step) and weights exceed the 126 MB L2; no flush needed" % (h2d / 1e9),
                    "weights": "conv1/conv2/fc4: NTT-form plaintexts resident (CUDA-core weighted sum); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

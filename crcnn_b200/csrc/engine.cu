@@ -13,6 +13,7 @@
 #include "kernels.cuh"
 #include "params.h"
 #include "tc_mac.cuh"
+#include "tcn_mac.cuh"
 
 using namespace crcnn;
 
@@ -20,11 +21,12 @@ namespace {
 
 enum KernelClass {
     KC_NTT_FWD = 0, KC_NTT_INV, KC_MAC, KC_PLAIN_EXPAND, KC_POOL, KC_BN, KC_PLAIN_OP,
-    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_COUNT
+    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_TCN_SPLIT, KC_TCN_MAC, KC_COUNT
 };
 const char *kClassNames[KC_COUNT] = {"ntt_forward", "ntt_inverse", "weighted_sum_mac", "plain_expand_ntt", "pool_sum",
                                      "batch_norm", "plain_op", "behz_lift", "square_tensor", "behz_floor_sk",
-                                     "relinearize", "imad_probe", "tc_plane_split", "weighted_sum_tc_i8"};
+                                     "relinearize", "imad_probe", "tc_plane_split", "weighted_sum_tc_i8", "tcn_plane_split",
+                                     "weighted_sum_tcn_i8"};
 
 thread_local std::string g_create_error;
 
@@ -52,6 +54,9 @@ struct crcnn_plain {
     int tc_state = 0;              // 0 not examined, 1 eligible, -1 not (support outside x^(n-32..n-1) or digits other than +-1)
     int8_t *tc_A = nullptr;
     int tc_R = 0, tc_Kpad = 0;
+    // limb-split tensor-core form (tcn_mac.cuh): byte planes of the NTT-form weights [K*n][7][count/R][Kpad]
+    uint8_t *tcn_W = nullptr;
+    int tcn_R = 0;
 };
 
 struct crcnn_evk {
@@ -74,6 +79,7 @@ struct crcnn_ctx {
     int tc_mode = 1;                 // 1: weighted sums with fan-in >= tc_min_fanin and >= tc_min_outputs outputs run on tcgen05 kind::i8 when the weights allow it; 2: regardless of the output count
     int tc_min_fanin = 256;
     int tc_min_outputs = 32;
+    int tcn_mode = 1;                // 1: weighted sums whose staged weights fit the weight cache run as the NTT-domain limb-split GEMM (tcn_mac.cuh)
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
@@ -323,6 +329,70 @@ int run_weighted_sum_tc(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_
     return rc;
 }
 
+// Byte planes of the whole pack's NTT-form weights, staged once (tcn_mac.cuh); the dense NTT form is released afterwards.
+int ensure_tcn_weights(crcnn_ctx *ctx, crcnn_plain *w, int R) {
+    if (w->tcn_W && w->tcn_R == R) return CRCNN_OK;
+    int rc = ensure_form(ctx, w, PF_NTT_MUL);
+    if (rc) return rc;
+    if (w->tcn_W) { dev_free(ctx, w->tcn_W); w->tcn_W = nullptr; }
+    const int Mall = (int)(w->count / R), Kpad = tcn_kpad(R);
+    rc = dev_alloc(ctx, tcn_w_bytes(7, Mall, Kpad, ctx->K, ctx->n), (void **)&w->tcn_W);
+    if (rc) return rc;
+    TcnSplitArgs s{};
+    s.src = w->ntt_mul; s.index = nullptr; s.dst = w->tcn_W; s.item_polys = 1;
+    s.R = R; s.Kpad = Kpad; s.planes = 7; s.ncols = Mall; s.slot0 = 0; s.nslots = ctx->K * ctx->n; s.n = ctx->n; s.K = ctx->K;
+    {
+        ProfScope ps(ctx, KC_TCN_SPLIT, lp_bytes(ctx, (double)w->count * ctx->K) + (double)tcn_w_bytes(7, Mall, Kpad, ctx->K, ctx->n), 0);
+        CU(launch_tcn_split(s, ctx->stream));
+    }
+    dev_free(ctx, w->ntt_mul); w->ntt_mul = nullptr;
+    if (w->ntt_mul_sh) { dev_free(ctx, w->ntt_mul_sh); w->ntt_mul_sh = nullptr; }
+    w->tcn_R = R;
+    return CRCNN_OK;
+}
+
+// Weighted sum as the NTT-domain limb-split GEMM on the tensor cores: NTT-form inputs and outputs.
+int run_weighted_sum_tcn(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
+                         int Npos, int Pimg, int m_first, int M, crcnn_tensor *out) {
+    int rc = ensure_domain(ctx, in, 1);
+    if (!rc) rc = ensure_form(ctx, b, PF_NTT_ADD);
+    if (!rc) rc = ensure_tcn_weights(ctx, w, R);
+    if (rc) return rc;
+    const size_t pw = poly_words(ctx);
+    const int Kpad = tcn_kpad(R), ncols = 2 * Npos, total = ctx->K * ctx->n;
+    const size_t per_slot = tcn_x_bytes_per_slot(7, ncols, Kpad);
+    long chunk = (long)(ctx->tc_scratch_bytes / per_slot) / 32 * 32;
+    chunk = std::max<long>(32, std::min<long>(chunk, total));
+    uint8_t *scratch = nullptr;
+    rc = dev_alloc(ctx, (size_t)chunk * per_slot, (void **)&scratch);
+    if (rc) return rc;
+    TcnSplitArgs s{};
+    s.src = in->d; s.index = d_index; s.dst = scratch; s.item_polys = 2;
+    s.R = R; s.Kpad = Kpad; s.planes = 7; s.ncols = ncols; s.n = ctx->n; s.K = ctx->K;
+    TcnMacArgs a{};
+    a.W = w->tcn_W; a.X = scratch; a.bias = b->ntt_add + (size_t)m_first * pw; a.out = out->d;
+    a.Mall = (int)(w->count / R); a.m_first = m_first; a.M = M;
+    a.R = R; a.Kpad = Kpad; a.planes = 7; a.ncols = ncols;
+    a.Pimg = Pimg; a.Mtotal = M; a.m0 = 0; a.n = ctx->n; a.K = ctx->K;
+    a.variant = ctx->tcn_mode >= 2 ? ctx->tcn_mode - 1 : 0;
+    for (long s0 = 0; s0 < total && !rc; s0 += chunk) {
+        const int ns = (int)std::min<long>(chunk, total - s0);
+        s.slot0 = a.slot0 = (int)s0; s.nslots = a.nslots = ns;
+        const double xbytes = (double)ns * per_slot;
+        cudaError_t e;
+        { ProfScope ps(ctx, KC_TCN_SPLIT, (double)ncols * R * ns * 8.0 + xbytes, 0); e = launch_tcn_split(s, ctx->stream); }
+        if (e == cudaSuccess) {
+            // ops: int8 multiply-accumulates of the unpadded problem (49 plane pairs per residue product)
+            ProfScope ps(ctx, KC_TCN_MAC, xbytes + (double)ns * 7 * M * Kpad + (double)ncols * M * ns * 8.0, (double)ns * ncols * M * R * 49.0);
+            e = launch_tcn_mac(ctx->dP, a, ctx->sm_count, ctx->stream);
+        }
+        if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, std::string("limb-split tensor-core weighted sum: ") + cudaGetErrorString(e));
+    }
+    dev_free(ctx, scratch);
+    if (!rc) out->ntt = 1;
+    return rc;
+}
+
 int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
                      int Npos, int Pimg, int Mall, int m_first, int M, crcnn_tensor *out) {
     if (ctx->tc_mode && R >= ctx->tc_min_fanin && (ctx->tc_mode == 2 || M >= ctx->tc_min_outputs) && w->sparse_shape && tc_mac_available() == cudaSuccess) {
@@ -330,6 +400,10 @@ int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_pla
         if (rc) return rc;
         if (w->tc_state == 1) return run_weighted_sum_tc(ctx, in, w, b, d_index, R, Npos, Pimg, m_first, M, out);
     }
+    // any weights, NTT domain: the limb-split GEMM, as long as the staged weight planes fit the weight cache
+    if (ctx->tcn_mode && tcn_planes_for(ctx->hp.d) == 7 && R <= TCN_MAX_R && w->count % R == 0 && tc_mac_available() == cudaSuccess &&
+        (w->tcn_W || tcn_w_bytes(7, (int)(w->count / R), tcn_kpad(R), ctx->K, ctx->n) <= ctx->weight_cache_bytes))
+        return run_weighted_sum_tcn(ctx, in, w, b, d_index, R, Npos, Pimg, m_first, M, out);
     int rc = ensure_domain(ctx, in, 1);
     if (rc) return rc;
     rc = ensure_form(ctx, b, PF_NTT_ADD);
@@ -419,6 +493,7 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
     c->chunk_terms = spare >= 30 ? (1 << 30) : (1 << spare);
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *e = getenv("CRCNN_TC")) c->tc_mode = atoi(e);
+    if (const char *e = getenv("CRCNN_TCN")) c->tcn_mode = atoi(e);
     // stream-ordered allocator: keep freed blocks cached
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -501,6 +576,13 @@ int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size
     ctx->tc_mode = mode;
     if (min_fanin > 0) ctx->tc_min_fanin = min_fanin;
     if (scratch_bytes > 0) ctx->tc_scratch_bytes = scratch_bytes;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(mode >= 0 && mode <= 3, "limb-split mode must be 0 (off), 1 (on), 2 (row-major kernel) or 3 (column-major kernel)");
+    ctx->tcn_mode = mode;
     return CRCNN_OK;
 }
 
@@ -701,7 +783,7 @@ int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     if (!p) return CRCNN_OK;
     dev_free(ctx, p->d_off); dev_free(ctx, p->d_idx); dev_free(ctx, p->d_val);
-    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_mul_sh); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A);
+    dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_mul_sh); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A); dev_free(ctx, p->tcn_W);
     delete p;
     return CRCNN_OK;
 }

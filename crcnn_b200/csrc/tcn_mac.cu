@@ -1,0 +1,527 @@
+// NTT-domain limb-split weighted sum on tcgen05 kind::i8 (see tcn_mac.cuh for the algorithm and the exactness argument).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include "modarith.cuh"
+#include "tc_ptx.cuh"
+#include "tcn_mac.cuh"
+
+namespace crcnn {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int TCN_PLANES = 7;
+constexpr int TCN_CLASSES = 2 * TCN_PLANES - 1;       // weight classes a + b
+constexpr int TCN_EPI_WARPS = 8;
+constexpr int TCN_THREADS = 32 * (2 + TCN_EPI_WARPS);  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int TCN_TMEM_COLS = 512;                     // 13 classes x 32 columns = 416 used
+
+template <int BK> struct TcnCfg {
+    static constexpr int A_STAGE = TCN_PLANES * TCN_BM * BK;   // weight planes of one K block
+    static constexpr int B_STAGE = TCN_PLANES * TCN_NB * BK;   // input planes of one K block
+    static constexpr int STAGES = BK == 128 ? 2 : 4;
+    static constexpr size_t SMEM = 1024 + (size_t)STAGES * (A_STAGE + B_STAGE) + 8 * (2 * STAGES + 2) + 16;
+};
+
+// ------------------------------------------------------------------------------------ the GEMM kernel
+template <int BK>
+__global__ void __launch_bounds__(TCN_THREADS, 1)
+tcn_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+               const DeviceParams *__restrict__ P, TcnMacArgs a) {
+    using Cfg = TcnCfg<BK>;
+    constexpr int STAGES = Cfg::STAGES, A_STAGE = Cfg::A_STAGE, B_STAGE = Cfg::B_STAGE;
+    constexpr uint32_t IDESC_BASE = (2u << 4)   // accumulator format S32; A and B formats 0 = unsigned 8 bit, both K-major; N is added per MMA
+                                    | ((uint32_t)(TCN_BM >> 4) << 24);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sA = base, sB = base + STAGES * A_STAGE;
+    const uint32_t off_bar = STAGES * (A_STAGE + B_STAGE);
+    const uint32_t bar_full = base + off_bar, bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES, bar_tempty = bar_tfull + 8;
+    const uint32_t tmem_slot = bar_tempty + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + off_bar + 8 * (2 * STAGES + 2));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.n;
+    const int m_tiles = (a.M + TCN_BM - 1) / TCN_BM;
+    const long items = (long)a.nslots * m_tiles;
+    const int chunks = (a.ncols + TCN_NB - 1) / TCN_NB;
+    const int ksteps = (a.R + 31) / 32;
+    const int KB = (ksteps * 32 + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, TCN_EPI_WARPS);
+        fence_barrier_init();
+        prefetch_tmap(&tmW);
+        prefetch_tmap(&tmX);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, TCN_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x) {
+                const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+                for (int ch = 0; ch < chunks; ch++)
+                    for (int kb = 0; kb < KB; kb++) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, A_STAGE + B_STAGE);
+                        tma_load_4d(sA + stage * A_STAGE, &tmW, bar_full + 8 * stage, kb * BK, mt * TCN_BM, 0, a.slot0 + sl);
+                        tma_load_4d(sB + stage * B_STAGE, &tmX, bar_full + 8 * stage, kb * BK, ch * TCN_NB, 0, sl);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x)
+                for (int ch = 0; ch < chunks; ch++) {
+                    mbar_wait(bar_tempty, acc_phase ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < KB; kb++) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t aS = sA + stage * A_STAGE, bS = sB + stage * B_STAGE;
+                        const int nks = BK == 128 ? min(4, ksteps - kb * 4) : 1;
+                        // One MMA per weight plane pa: its B operand is ALL input planes stacked (N = 7 x 32), so the product with
+                        // input plane pb lands in columns [32 (pa + pb), +32) = weight class pa + pb.  The first K step of a chunk
+                        // must overwrite: plane 0 initialises classes 0-6, plane 6 against input planes 1-6 initialises 7-12.
+                        for (int ks = 0; ks < nks; ks++) {
+                            const bool fresh = (kb | ks) == 0;
+                            auto descA = [&](int pa) { return (BK == 128 ? umma_desc_sw128(aS + pa * (TCN_BM * BK)) : umma_desc_sw32(aS + pa * (TCN_BM * BK))) + 2 * ks; };
+                            auto descB = [&](int pb) { return (BK == 128 ? umma_desc_sw128(bS + pb * (TCN_NB * BK)) : umma_desc_sw32(bS + pb * (TCN_NB * BK))) + 2 * ks; };
+                            constexpr uint32_t ID_ALL = IDESC_BASE | ((uint32_t)((TCN_PLANES * TCN_NB) >> 3) << 17);
+                            constexpr uint32_t ID_HI = IDESC_BASE | ((uint32_t)(((TCN_PLANES - 1) * TCN_NB) >> 3) << 17);
+                            constexpr uint32_t ID_ONE = IDESC_BASE | ((uint32_t)(TCN_NB >> 3) << 17);
+                            if (fresh) {
+                                umma_i8(tmem_base, descA(0), descB(0), ID_ALL, 0u);
+                                umma_i8(tmem_base + TCN_PLANES * TCN_NB, descA(TCN_PLANES - 1), descB(1), ID_HI, 0u);
+                                umma_i8(tmem_base + (TCN_PLANES - 1) * TCN_NB, descA(TCN_PLANES - 1), descB(0), ID_ONE, 1u);
+#pragma unroll
+                                for (int pa = 1; pa < TCN_PLANES - 1; pa++) umma_i8(tmem_base + pa * TCN_NB, descA(pa), descB(0), ID_ALL, 1u);
+                            } else {
+#pragma unroll
+                                for (int pa = 0; pa < TCN_PLANES; pa++) umma_i8(tmem_base + pa * TCN_NB, descA(pa), descB(0), ID_ALL, 1u);
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * stage);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_tfull);
+                    acc_phase ^= 1;
+                }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================================== epilogue
+        // UMMA M = 64 keeps output row m in TMEM lane (m % 16) + 32 * (m / 16): a warp owns lane quadrant warp % 4,
+        // lanes 0-15 of it hold rows; the two warps of a quadrant split the chunk's 8 groups of 4 columns
+        const int qd = warp & 3, half = (warp - 2) >> 2;
+        const long pw = (long)a.K * n;
+        uint32_t acc_phase = 0;
+        for (long item = blockIdx.x; item < items; item += gridDim.x) {
+            const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+            const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;
+            const Mod mod = P->tab[j].mod;
+            const int m = mt * TCN_BM + qd * 16 + lane;     // output row of this thread (lanes >= 16 hold nothing)
+            const bool valid = lane < 16 && m < a.M;
+            const uint64_t bias = (a.bias && valid) ? __ldg(a.bias + (long)m * pw + (long)j * n + c) : 0;
+            const long row_off = (long)(a.m0 + m) * a.Pimg;
+            for (int ch = 0; ch < chunks; ch++) {
+                mbar_wait(bar_tfull, acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int g = 0; g < 4; g++) {
+                    const int col0 = ch * TCN_NB + (half * 4 + g) * 4;
+                    uint32_t S[TCN_CLASSES][4];
+#pragma unroll
+                    for (int w = 0; w < TCN_CLASSES; w++)
+                        tmem_ld4(tmem_base + ((uint32_t)(qd * 32) << 16) + w * TCN_NB + (half * 4 + g) * 4, S[w]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int col = col0 + i;
+                        if (!valid || col >= a.ncols) continue;
+                        // sum_w S_w 2^(8w): classes w = 0,4,8,12 / 1,5,9 / 2,6,10 / 3,7,11 are word aligned among themselves
+                        typedef unsigned __int128 u128;
+                        const u128 t0 = ((u128)(((uint64_t)S[12][i] << 32) | S[8][i]) << 64) | (((uint64_t)S[4][i] << 32) | S[0][i]);
+                        const u128 t1 = ((u128)S[9][i] << 64) | (((uint64_t)S[5][i] << 32) | S[1][i]);
+                        const u128 t2 = ((u128)S[10][i] << 64) | (((uint64_t)S[6][i] << 32) | S[2][i]);
+                        const u128 t3 = ((u128)S[11][i] << 64) | (((uint64_t)S[7][i] << 32) | S[3][i]);
+                        const u128 tot = t0 + (t1 << 8) + (t2 << 16) + (t3 << 24);
+                        U128 z;
+                        z.lo = (uint64_t)tot;
+                        z.hi = (uint64_t)(tot >> 64);
+                        uint64_t r = barrett128(z, mod);
+                        const int p = col >> 1, poly = col & 1;
+                        if (poly == 0 && a.bias) r = addmod(r, bias, mod.q);
+                        const long oct = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + row_off + p % a.Pimg;
+                        a.out[((oct * 2 + poly) * a.K + j) * (long)n + c] = r;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty);
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TCN_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------ the GEMM kernel, column-major variant
+// For layers with many columns and few outputs (convolutions: 576 / 3136 columns, 50 / 20 outputs) the roles swap:
+// the COLUMNS fill the 128 UMMA rows (A operand = one input plane, [128 columns][BK]) and the outputs sit on the N
+// side (B operand = all 7 weight planes of a tile of 32 outputs stacked, N = 224), so one MMA per input plane and K
+// step covers 128 columns -- 4x the work per tensor-pipe cycle of the 64-row form for these shapes -- and every
+// epilogue lane holds a column.  The weights of a work item (slot, 32 outputs) stay resident in shared memory
+// (fan-in of at most 2 K blocks); input planes stream through a ring, one plane tile per stage.
+constexpr int TCN2_CB = 128;   // columns per chunk (UMMA M)
+constexpr int TCN2_MT = 32;    // outputs per tile (N per weight class)
+constexpr int TCN2_KBMAX = 2;
+
+template <int BK> struct Tcn2Cfg {
+    static constexpr int W_BLOCK = TCN_PLANES * TCN2_MT * BK;   // weight planes of one K block: [7][32][BK]
+    static constexpr int X_STAGE = TCN2_CB * BK;                // one input plane of one K block: [128][BK]
+    static constexpr int STAGES = BK == 128 ? 6 : 8;
+    static constexpr size_t SMEM = 1024 + (size_t)TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE + 8 * (2 * STAGES + 4) + 16;
+};
+
+template <int BK>
+__global__ void __launch_bounds__(TCN_THREADS, 1)
+tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
+                const DeviceParams *__restrict__ P, TcnMacArgs a) {
+    using Cfg = Tcn2Cfg<BK>;
+    constexpr int STAGES = Cfg::STAGES, W_BLOCK = Cfg::W_BLOCK, X_STAGE = Cfg::X_STAGE;
+    constexpr uint32_t IDESC_BASE = (2u << 4) | ((uint32_t)(TCN2_CB >> 4) << 24);  // S32 accumulators, u8 x u8, K-major, M = 128
+    constexpr uint32_t ID_ALL = IDESC_BASE | ((uint32_t)((TCN_PLANES * TCN2_MT) >> 3) << 17);
+    constexpr uint32_t ID_HI = IDESC_BASE | ((uint32_t)(((TCN_PLANES - 1) * TCN2_MT) >> 3) << 17);
+    constexpr uint32_t ID_ONE = IDESC_BASE | ((uint32_t)(TCN2_MT >> 3) << 17);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sW = base, sX = base + TCN2_KBMAX * W_BLOCK;
+    const uint32_t off_bar = TCN2_KBMAX * W_BLOCK + STAGES * X_STAGE;
+    const uint32_t bar_full = base + off_bar, bar_empty = bar_full + 8 * STAGES;
+    const uint32_t bar_wfull = bar_empty + 8 * STAGES, bar_wempty = bar_wfull + 8;
+    const uint32_t bar_tfull = bar_wempty + 8, bar_tempty = bar_tfull + 8;
+    const uint32_t tmem_slot = bar_tempty + 8;
+    volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + off_bar + 8 * (2 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = a.n;
+    const int m_tiles = (a.M + TCN2_MT - 1) / TCN2_MT;
+    const long items = (long)a.nslots * m_tiles;
+    const int chunks = (a.ncols + TCN2_CB - 1) / TCN2_CB;
+    const int ksteps = (a.R + 31) / 32;
+    const int KB = (ksteps * 32 + BK - 1) / BK;   // <= TCN2_KBMAX (checked by the launcher)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_wfull, 1);
+        mbar_init(bar_wempty, 1);
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, TCN_EPI_WARPS);
+        fence_barrier_init();
+        prefetch_tmap(&tmW);
+        prefetch_tmap(&tmX);
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, TCN_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    // input planes are streamed in the order 0, 6, 1, 2, 3, 4, 5: planes 0 and 6 initialise the 13 weight classes
+    auto plane_of = [](int bi) { return bi == 0 ? 0 : (bi == 1 ? TCN_PLANES - 1 : bi - 1); };
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, wphase = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x) {
+                const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+                mbar_wait(bar_wempty, wphase ^ 1);
+                mbar_expect_tx(bar_wfull, KB * W_BLOCK);
+                for (int kb = 0; kb < KB; kb++)
+                    tma_load_4d(sW + kb * W_BLOCK, &tmW, bar_wfull, kb * BK, mt * TCN2_MT, 0, a.slot0 + sl);
+                wphase ^= 1;
+                for (int ch = 0; ch < chunks; ch++)
+                    for (int kb = 0; kb < KB; kb++)
+                        for (int bi = 0; bi < TCN_PLANES; bi++) {
+                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            mbar_expect_tx(bar_full + 8 * stage, X_STAGE);
+                            tma_load_4d(sX + stage * X_STAGE, &tmX, bar_full + 8 * stage, kb * BK, ch * TCN2_CB, plane_of(bi), sl);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, acc_phase = 0, wphase = 0;
+            for (long item = blockIdx.x; item < items; item += gridDim.x) {
+                mbar_wait(bar_wfull, wphase);
+                wphase ^= 1;
+                tc_fence_after();
+                for (int ch = 0; ch < chunks; ch++) {
+                    mbar_wait(bar_tempty, acc_phase ^ 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < KB; kb++) {
+                        const uint32_t wS = sW + kb * W_BLOCK;
+                        const int nks = BK == 128 ? min(4, ksteps - kb * 4) : 1;
+                        for (int bi = 0; bi < TCN_PLANES; bi++) {
+                            const int pb = plane_of(bi);
+                            mbar_wait(bar_full + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint32_t xS = sX + stage * X_STAGE;
+                            for (int ks = 0; ks < nks; ks++) {
+                                const uint64_t dx = (BK == 128 ? umma_desc_sw128(xS) : umma_desc_sw32(xS)) + 2 * ks;
+                                auto descW = [&](int pa) { return (BK == 128 ? umma_desc_sw128(wS + pa * (TCN2_MT * BK)) : umma_desc_sw32(wS + pa * (TCN2_MT * BK))) + 2 * ks; };
+                                // D[column, (class, output)]: input plane pb against all weight planes lands in classes pb .. pb+6
+                                if ((kb | ks) == 0 && pb == 0) {
+                                    umma_i8(tmem_base, dx, descW(0), ID_ALL, 0u);
+                                } else if ((kb | ks) == 0 && pb == TCN_PLANES - 1) {
+                                    umma_i8(tmem_base + TCN_PLANES * TCN2_MT, dx, descW(1), ID_HI, 0u);         // classes 7-12: overwrite
+                                    umma_i8(tmem_base + (TCN_PLANES - 1) * TCN2_MT, dx, descW(0), ID_ONE, 1u);  // class 6: accumulate
+                                } else {
+                                    umma_i8(tmem_base + pb * TCN2_MT, dx, descW(0), ID_ALL, 1u);
+                                }
+                            }
+                            umma_commit(bar_empty + 8 * stage);
+                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    umma_commit(bar_tfull);
+                    acc_phase ^= 1;
+                }
+                umma_commit(bar_wempty);   // every MMA that reads this item's weights has been issued before this commit
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================================== epilogue
+        // UMMA M = 128: TMEM lane = column of the chunk; a warp owns lane quadrant warp % 4, the two warps of a quadrant
+        // split the tile's 32 outputs
+        const int qd = warp & 3, half = (warp - 2) >> 2;
+        const long pw = (long)a.K * n;
+        uint32_t acc_phase = 0;
+        for (long item = blockIdx.x; item < items; item += gridDim.x) {
+            const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+            const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;
+            const Mod mod = P->tab[j].mod;
+            const long slot_off = (long)j * n + c;
+            for (int ch = 0; ch < chunks; ch++) {
+                const int col = ch * TCN2_CB + qd * 32 + lane;
+                const bool valid = col < a.ncols;
+                const int p = col >> 1, poly = col & 1;
+                const long colbase = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + p % a.Pimg;
+                mbar_wait(bar_tfull, acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int g = 0; g < 4; g++) {
+                    const int mloc = half * 16 + g * 4;
+                    if (mt * TCN2_MT + mloc >= a.M) break;   // warp-uniform: the rest of the tile holds no output
+                    uint32_t S[TCN_CLASSES][4];
+#pragma unroll
+                    for (int w = 0; w < TCN_CLASSES; w++)
+                        tmem_ld4(tmem_base + ((uint32_t)(qd * 32) << 16) + w * TCN2_MT + mloc, S[w]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int m = mt * TCN2_MT + mloc + i;
+                        if (!valid || m >= a.M) continue;
+                        typedef unsigned __int128 u128;
+                        const u128 t0 = ((u128)(((uint64_t)S[12][i] << 32) | S[8][i]) << 64) | (((uint64_t)S[4][i] << 32) | S[0][i]);
+                        const u128 t1 = ((u128)S[9][i] << 64) | (((uint64_t)S[5][i] << 32) | S[1][i]);
+                        const u128 t2 = ((u128)S[10][i] << 64) | (((uint64_t)S[6][i] << 32) | S[2][i]);
+                        const u128 t3 = ((u128)S[11][i] << 64) | (((uint64_t)S[7][i] << 32) | S[3][i]);
+                        const u128 tot = t0 + (t1 << 8) + (t2 << 16) + (t3 << 24);
+                        U128 z;
+                        z.lo = (uint64_t)tot;
+                        z.hi = (uint64_t)(tot >> 64);
+                        uint64_t r = barrett128(z, mod);
+                        if (poly == 0 && a.bias) r = addmod(r, __ldg(a.bias + (long)m * pw + slot_off), mod.q);
+                        const long oct = colbase + (long)(a.m0 + m) * a.Pimg;
+                        a.out[(oct * 2 + poly) * pw + slot_off] = r;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty);
+                acc_phase ^= 1;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TCN_TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------ operand staging
+// dst[slot - slot0][l][col][r] = byte l of src item (col group, r), polynomial col % item_polys, residue of `slot`.
+// One CTA: 32 consecutive slots x 128 consecutive (column, term) bytes of a plane row -- one column x 128 terms, or
+// four columns x 32 terms when rows are 32 bytes -- transposed through shared memory, so every store is 128 B wide.
+__global__ void __launch_bounds__(256)
+tcn_split_kernel(TcnSplitArgs a) {
+    __shared__ uint64_t tile[32][133];    // [slot][(e & 3) * 33 + (e >> 2)], e = byte within the 128; row stride 133 = 5 mod 16: conflict free both ways
+    const int n = a.n, K = a.K;
+    const int rows_per = a.Kpad < 128 ? 128 / a.Kpad : 1;   // columns per CTA
+    const int col0 = blockIdx.x * rows_per;
+    const int st = blockIdx.y;            // tile of 32 slots
+    const int r0 = blockIdx.z * 128;      // only rows of >= 128 bytes have more than one z block
+    const int slot = a.slot0 + st * 32;
+    const int j = slot / n, c0 = slot - j * n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = warp; e < 128; e += 8) {
+        const int col = col0 + (rows_per > 1 ? e / a.Kpad : 0);
+        const int r = rows_per > 1 ? e % a.Kpad : r0 + e;
+        uint64_t v = 0;
+        if (r < a.R && col < a.ncols) {
+            const int group = col / a.item_polys, poly = col - group * a.item_polys;
+            const long item = a.index ? (long)__ldg(a.index + (long)group * a.R + r) : (long)group * a.R + r;
+            v = __ldg(a.src + ((item * a.item_polys + poly) * K + j) * (long)n + c0 + lane);
+        }
+        tile[lane][(e & 3) * 33 + (e >> 2)] = v;
+    }
+    __syncthreads();
+    const long plane_stride = (long)a.ncols * a.Kpad;
+    const long row_bytes = plane_stride - (long)col0 * a.Kpad - r0;   // bytes left in the plane row from this CTA's start
+    uint8_t *dst = a.dst + ((long)st * 32 * a.planes) * plane_stride + (long)col0 * a.Kpad + r0;
+    for (int w = threadIdx.x; w < a.planes * 1024; w += 256) {
+        const int l = w >> 10, c = (w >> 5) & 31, rw = w & 31;
+        if (rows_per > 1 ? 4 * rw >= row_bytes : r0 + 4 * rw >= a.Kpad) continue;
+        const int sh = 8 * l;
+        const uint32_t word = (uint32_t)((tile[c][rw] >> sh) & 0xff) | (uint32_t)((tile[c][33 + rw] >> sh) & 0xff) << 8 |
+                              (uint32_t)((tile[c][66 + rw] >> sh) & 0xff) << 16 | (uint32_t)((tile[c][99 + rw] >> sh) & 0xff) << 24;
+        *reinterpret_cast<uint32_t *>(dst + ((long)c * a.planes + l) * plane_stride + 4 * rw) = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+template <int BK>
+cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    const CUtensorMapSwizzle sw = BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUtensorMap tmW, tmX;
+    {
+        // rows m of the shard only: tiles that reach past M are zero filled by TMA, no padding rows in memory
+        const cuuint64_t rowsW = (cuuint64_t)a.Mall * a.Kpad;
+        cuuint64_t dims[4] = {(cuuint64_t)a.Kpad, (cuuint64_t)a.M, (cuuint64_t)TCN_PLANES, (cuuint64_t)a.K * a.n};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Kpad, rowsW, rowsW * TCN_PLANES};
+        cuuint32_t box[4] = {BK, TCN_BM, TCN_PLANES, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)(a.W + (size_t)a.m_first * a.Kpad), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t rowsX = (cuuint64_t)a.ncols * a.Kpad;
+        cuuint64_t dims[4] = {(cuuint64_t)a.Kpad, (cuuint64_t)a.ncols, (cuuint64_t)TCN_PLANES, (cuuint64_t)a.nslots};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Kpad, rowsX, rowsX * TCN_PLANES};
+        cuuint32_t box[4] = {BK, TCN_NB, TCN_PLANES, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.X, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    auto k = tcn_mac_kernel<BK>;
+    const size_t smem = TcnCfg<BK>::SMEM;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const long items = (long)a.nslots * ((a.M + TCN_BM - 1) / TCN_BM);
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    k<<<grid, TCN_THREADS, smem, stream>>>(tmW, tmX, P, a);
+    return cudaGetLastError();
+}
+
+template <int BK>
+cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return cudaErrorNotSupported;
+    const CUtensorMapSwizzle sw = BK == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+    CUtensorMap tmW, tmX;
+    {
+        const cuuint64_t rowsW = (cuuint64_t)a.Mall * a.Kpad;
+        cuuint64_t dims[4] = {(cuuint64_t)a.Kpad, (cuuint64_t)a.M, (cuuint64_t)TCN_PLANES, (cuuint64_t)a.K * a.n};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Kpad, rowsW, rowsW * TCN_PLANES};
+        cuuint32_t box[4] = {BK, TCN2_MT, TCN_PLANES, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)(a.W + (size_t)a.m_first * a.Kpad), dims, strides, box, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    {
+        const cuuint64_t rowsX = (cuuint64_t)a.ncols * a.Kpad;
+        cuuint64_t dims[4] = {(cuuint64_t)a.Kpad, (cuuint64_t)a.ncols, (cuuint64_t)TCN_PLANES, (cuuint64_t)a.nslots};
+        cuuint64_t strides[3] = {(cuuint64_t)a.Kpad, rowsX, rowsX * TCN_PLANES};
+        cuuint32_t box[4] = {BK, TCN2_CB, 1, 1}, es[4] = {1, 1, 1, 1};
+        if (enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)a.X, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    auto k = tcn2_mac_kernel<BK>;
+    const size_t smem = Tcn2Cfg<BK>::SMEM;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const long items = (long)a.nslots * ((a.M + TCN2_MT - 1) / TCN2_MT);
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    k<<<grid, TCN_THREADS, smem, stream>>>(tmW, tmX, P, a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t tcn_x_bytes_per_slot(int planes, int ncols, int Kpad) { return (size_t)planes * ncols * Kpad; }
+size_t tcn_w_bytes(int planes, int Mall, int Kpad, int K, int n) { return (size_t)K * n * planes * Mall * Kpad; }
+
+cudaError_t launch_tcn_split(const TcnSplitArgs &a, cudaStream_t stream) {
+    if (a.ncols <= 0 || a.nslots <= 0) return cudaSuccess;
+    if (a.nslots % 32 || a.slot0 % 32 || a.Kpad % 32 || a.planes != TCN_PLANES || a.nslots / 32 > 65535) return cudaErrorInvalidValue;
+    const int rows_per = a.Kpad < 128 ? 128 / a.Kpad : 1;
+    dim3 grid((unsigned)((a.ncols + rows_per - 1) / rows_per), (unsigned)(a.nslots / 32), (unsigned)((a.Kpad + 127) / 128));
+    tcn_split_kernel<<<grid, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
+    if (a.nslots <= 0 || a.M <= 0 || a.ncols <= 0) return cudaSuccess;
+    if (a.planes != TCN_PLANES || a.R > TCN_MAX_R || a.Kpad != tcn_kpad(a.R)) return cudaErrorInvalidValue;
+    const int forced = a.variant;   // 1 / 2 force the row-major / column-major kernel (tests, sweeps)
+    const int bk = tcn_bk(a.R);
+    const bool fits2 = ((a.R + 31) / 32 * 32 + bk - 1) / bk <= TCN2_KBMAX;
+    const bool use2 = fits2 && (forced == 2 || (forced != 1 && a.ncols >= 4 * a.M));
+    if (use2) return bk == 128 ? launch_tcn2_mac_t<128>(P, a, sm_count, stream) : launch_tcn2_mac_t<32>(P, a, sm_count, stream);
+    return bk == 128 ? launch_tcn_mac_t<128>(P, a, sm_count, stream) : launch_tcn_mac_t<32>(P, a, sm_count, stream);
+}
+
+}  // namespace crcnn

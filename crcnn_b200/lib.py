@@ -28,6 +28,7 @@ SYMBOLS = [
     ("crcnn_ctx_sync", _I, [_vp]),
     ("crcnn_ctx_set_weight_cache_bytes", _I, [_vp, C.c_size_t]),
     ("crcnn_ctx_set_tensor_core_mode", _I, [_vp, C.c_int, C.c_int, C.c_size_t]),
+    ("crcnn_ctx_set_limb_split_mode", _I, [_vp, C.c_int]),
     ("crcnn_ctx_ntt_table", _I, [_vp, _I, _I, _u64p]),
     ("crcnn_ctx_bsk_count", _I, [_vp]),
     ("crcnn_tensor_upload", _I, [_vp, _vp, _L, _I, _vpp]),
@@ -166,6 +167,9 @@ class Engine:
 
     def set_tensor_core_mode(self, mode, min_fanin=0, scratch_bytes=0):
         self._chk(self.lib.crcnn_ctx_set_tensor_core_mode(self.h, int(mode), int(min_fanin), int(scratch_bytes)))
+
+    def set_limb_split_mode(self, mode):
+        self._chk(self.lib.crcnn_ctx_set_limb_split_mode(self.h, int(mode)))
 
     def ntt_table(self, slot, which):
         out = np.zeros(self.n, dtype=np.uint64)

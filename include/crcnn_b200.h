@@ -71,6 +71,14 @@ int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes);
  * stay on the CUDA cores: measured on B200 the NTT-domain kernel wins for conv2 (fan-in 180) and fc4 (10 outputs)).  Env CRCNN_TC=0|1 sets the
  * initial mode. */
 int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size_t scratch_bytes);
+/* Every other weighted sum (any plaintext weights: convolutions, small fully connected layers) runs in the NTT domain
+ * as a limb-split GEMM on the same tensor cores: residues of weights and inputs are split into 7 byte planes, the 49
+ * plane products accumulate per weight class in TMEM and are recombined and reduced once
+ * (crcnn_b200/csrc/tcn_mac.cuh).  It needs primes of at most 56 bits and its staged weights (7 bytes per residue)
+ * within the weight cache; otherwise, or with mode 0, the CUDA-core kernel runs.  Modes 2 and 3 force one of its two
+ * kernel shapes (outputs / columns on the UMMA rows) instead of choosing by layer shape.  Env CRCNN_TCN sets the
+ * initial mode (default 1).  The scratch budget is the one of crcnn_ctx_set_tensor_core_mode. */
+int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode);
 /* Derived constants, for cross-checking against SEAL: which = 0 root_powers, 1 scaled_root_powers,
  * 2 inv_root_powers_div_two, 3 scaled_inv_root_powers_div_two (SEAL/seal/util/smallntt.cpp:37-92);
  * slot in [0,K) = coefficient primes, [K,K+S) = Bsk primes.  out has n words. */
