@@ -46,6 +46,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "shard"],
+                    help="replicas: every GPU runs its own image batch (default, weak scaling); shard: ONE image, the Approx "
+                         "network's conv / fc layers split by output neuron across the GPUs with NCCL all-gathers of the "
+                         "activation ciphertexts (BASELINE config 3, strong scaling)")
     return ap.parse_args()
 
 
@@ -244,6 +248,66 @@ def main_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def main_shard(args, rank, world, local_rank):
+    """BASELINE config 3: ApproxPlainModel.h5, n = 8192, one image, output-neuron sharding over the GPUs of one box.
+    A step is one sharded forward (latency path); value = images/s = 1 / step time."""
+    import torch
+    import torch.distributed as dist
+    from crcnn_b200.lib import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local_rank))
+    K, n = len(PRIMES), N_POLY
+    eng = Engine(n, PRIMES, T_PLAIN, device=local_rank)
+    rng = np.random.default_rng(1000)          # the same image and keys on every rank
+    evk_words, sizes, dbc = synth_evk(rng, PRIMES, n)
+    net = nets.ShardedNetwork(eng, "ApproxPlainModel", dist, evk=eng.evk_upload(evk_words, sizes, dbc))
+    zd, xd, yd = net.input_shape
+    x0 = eng.upload(synth_residues(rng, (zd * xd * yd, 2), PRIMES, n))
+    ct_bytes = 2 * K * n * W
+    # all-gather volume per image (bytes received per rank): activations before conv2, fc3, fc4 and the 10 scores
+    gathered = (20 * 11 * 11 + 800 + 500 + 10) * ct_bytes
+
+    def step():
+        x = eng.slice(x0, 0, zd * xd * yd)
+        y = net.forward(x)
+        y.free()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    eng.sync()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank); sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(args.steps):
+        step()
+    ev[1].record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    t = torch.tensor([ev[0].elapsed_time(ev[1])], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0]) / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "encrypted MNIST images/sec", "value": 1000.0 / ms, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic: uniform residues in SEAL ciphertext layout; weights = ApproxPlainModel.h5",
+            "config": {"workload": "ApproxPlainModel.h5 encoded net, n=8192, K=4, t=2^30, ONE image, conv/fc layers sharded by output neuron",
+                       "parallelism": "output-neuron shards x%d, NCCL all-gather of activation ciphertexts before conv2 / fc3 / fc4 and of the scores" % world,
+                       "all_gather_bytes_per_image": gathered},
+            "clocks": clocks}))
+    eng.close()
+    dist.destroy_process_group()
+
+
 def main_b200(args, rank, world, local_rank):
     import torch
     from crcnn_b200.lib import Engine
@@ -323,16 +387,23 @@ def main_b200(args, rank, world, local_rank):
         barrier()
         ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev2[0].record(stream)
-        # double-buffered: the H2D copy of step s+1 runs on a copy stream while step s computes
-        x_next = eng.upload_ptr_on(host_in.data_ptr(), B * per_image, copy_stream.cuda_stream)
+        # double-buffered: the H2D copy of step s+1 runs on a copy stream while step s computes; the two input
+        # tensors and the staging buffer are allocated once (crcnn_tensor_upload_into), nothing per step
+        bufs = [eng.alloc(B * per_image), eng.alloc(B * per_image)]
+        done = [None, None]                      # event: forward that consumed the buffer has finished
+        eng.upload_into(bufs[0], host_in.data_ptr(), copy_stream.cuda_stream)
         for s in range(args.steps):
+            cur = bufs[s & 1]
             eng.wait_stream(copy_stream.cuda_stream)
-            x = x_next
             if s + 1 < args.steps:
-                x_next = eng.upload_ptr_on(host_in.data_ptr(), B * per_image, copy_stream.cuda_stream)
-            y = net.forward(x, batch=B)
+                nxt = (s + 1) & 1
+                if done[nxt] is not None:
+                    copy_stream.wait_event(done[nxt])
+                eng.upload_into(bufs[nxt], host_in.data_ptr(), copy_stream.cuda_stream)
+            y = net.forward(cur, batch=B)
+            done[s & 1] = torch.cuda.Event(); done[s & 1].record(stream)
             eng.download_ptr(y, host_out.data_ptr())
-            x.free(); y.free()
+            y.free()
         ev2[1].record(stream)
         barrier()
         ms_e2e = ev2[0].elapsed_time(ev2[1])
@@ -475,6 +546,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         main_reference(args, rank, world)
+    elif args.mode == "shard":
+        main_shard(args, rank, world, local_rank)
     else:
         main_b200(args, rank, world, local_rank)
 

@@ -83,6 +83,8 @@ struct crcnn_ctx {
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
+    uint64_t *stage = nullptr;       // persistent H2D staging buffer of crcnn_tensor_upload_into (host layout, pad words included)
+    size_t stage_bytes = 0;
     // profiling
     bool prof_on = false;
     long launches[KC_COUNT] = {0};
@@ -544,6 +546,7 @@ int crcnn_ctx_destroy(crcnn_ctx *ctx) {
     prof_collect(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     for (auto &kv : ctx->index_cache) cudaFree(kv.second);
+    if (ctx->stage) cudaFree(ctx->stage);
     for (void *p : ctx->owned) cudaFree(p);
     cudaFree(ctx->dP);
     delete ctx;
@@ -629,6 +632,26 @@ int crcnn_tensor_upload_on(crcnn_ctx *ctx, const uint64_t *host, long count, int
         if (rc2) { cudaFreeAsync(t->d, cs); delete t; return rc2; }
     }
     *out = t;
+    return CRCNN_OK;
+}
+
+int crcnn_tensor_upload_into(crcnn_ctx *ctx, const uint64_t *host, crcnn_tensor *t, int ntt_form, void *copy_stream) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(host && t, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t cs = copy_stream ? (cudaStream_t)copy_stream : ctx->stream;
+    const size_t n = ctx->n, rows = (size_t)t->count * t->size * ctx->K;
+    const size_t need = rows * (n + 1) * 8;
+    if (need > ctx->stage_bytes) {   // grows only: steady-state uploads allocate nothing
+        if (ctx->stage) { CU(cudaStreamSynchronize(cs)); CU(cudaFree(ctx->stage)); ctx->stage = nullptr; ctx->stage_bytes = 0; }
+        CU(cudaMalloc((void **)&ctx->stage, need));
+        ctx->stage_bytes = need;
+    }
+    if (rows) {
+        CU(cudaMemcpyAsync(ctx->stage, host, need, cudaMemcpyHostToDevice, cs));
+        CU(launch_strip_pad(ctx->stage, t->d, (long)rows, (int)n, cs));
+    }
+    t->ntt = ntt_form ? 1 : 0;
     return CRCNN_OK;
 }
 

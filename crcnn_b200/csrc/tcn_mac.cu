@@ -19,6 +19,25 @@ constexpr int TCN_EPI_WARPS = 8;
 constexpr int TCN_THREADS = 32 * (2 + TCN_EPI_WARPS);  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
 constexpr int TCN_TMEM_COLS = 512;                     // 13 classes x 32 columns = 416 used
 
+// sum_w S_w 2^(8w) of the 13 weight classes of one output as a 128-bit integer.  Classes 0,4,8,12 are whole words;
+// 1,5,9 / 2,6,10 / 3,7,11 are three more word-aligned numbers shifted by 8 / 16 / 24 bits: 9 funnel shifts and three
+// 4-word carry chains.
+__device__ __forceinline__ U128 tcn_combine(const uint32_t (&S)[TCN_CLASSES][4], int i) {
+    uint32_t z0 = S[0][i], z1 = S[4][i], z2 = S[8][i], z3 = S[12][i];
+#define CRCNN_ADD4(a0, a1, a2, a3)                                                                                     \
+    asm("add.cc.u32 %0, %0, %4;\n\taddc.cc.u32 %1, %1, %5;\n\taddc.cc.u32 %2, %2, %6;\n\taddc.u32 %3, %3, %7;"          \
+        : "+r"(z0), "+r"(z1), "+r"(z2), "+r"(z3)                                                                       \
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3))
+    CRCNN_ADD4(S[1][i] << 8, __funnelshift_l(S[1][i], S[5][i], 8), __funnelshift_l(S[5][i], S[9][i], 8), S[9][i] >> 24);
+    CRCNN_ADD4(S[2][i] << 16, __funnelshift_l(S[2][i], S[6][i], 16), __funnelshift_l(S[6][i], S[10][i], 16), S[10][i] >> 16);
+    CRCNN_ADD4(S[3][i] << 24, __funnelshift_l(S[3][i], S[7][i], 24), __funnelshift_l(S[7][i], S[11][i], 24), S[11][i] >> 8);
+#undef CRCNN_ADD4
+    U128 z;
+    z.lo = ((uint64_t)z1 << 32) | z0;
+    z.hi = ((uint64_t)z3 << 32) | z2;
+    return z;
+}
+
 template <int BK> struct TcnCfg {
     static constexpr int A_STAGE = TCN_PLANES * TCN_BM * BK;   // weight planes of one K block
     static constexpr int B_STAGE = TCN_PLANES * TCN_NB * BK;   // input planes of one K block
@@ -159,17 +178,7 @@ tcn_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     for (int i = 0; i < 4; i++) {
                         const int col = col0 + i;
                         if (!valid || col >= a.ncols) continue;
-                        // sum_w S_w 2^(8w): classes w = 0,4,8,12 / 1,5,9 / 2,6,10 / 3,7,11 are word aligned among themselves
-                        typedef unsigned __int128 u128;
-                        const u128 t0 = ((u128)(((uint64_t)S[12][i] << 32) | S[8][i]) << 64) | (((uint64_t)S[4][i] << 32) | S[0][i]);
-                        const u128 t1 = ((u128)S[9][i] << 64) | (((uint64_t)S[5][i] << 32) | S[1][i]);
-                        const u128 t2 = ((u128)S[10][i] << 64) | (((uint64_t)S[6][i] << 32) | S[2][i]);
-                        const u128 t3 = ((u128)S[11][i] << 64) | (((uint64_t)S[7][i] << 32) | S[3][i]);
-                        const u128 tot = t0 + (t1 << 8) + (t2 << 16) + (t3 << 24);
-                        U128 z;
-                        z.lo = (uint64_t)tot;
-                        z.hi = (uint64_t)(tot >> 64);
-                        uint64_t r = barrett128(z, mod);
+                        uint64_t r = barrett128(tcn_combine(S, i), mod);
                         const int p = col >> 1, poly = col & 1;
                         if (poly == 0 && a.bias) r = addmod(r, bias, mod.q);
                         const long oct = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + row_off + p % a.Pimg;
@@ -198,6 +207,8 @@ tcn_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
 constexpr int TCN2_CB = 128;   // columns per chunk (UMMA M)
 constexpr int TCN2_MT = 32;    // outputs per tile (N per weight class)
 constexpr int TCN2_KBMAX = 2;
+constexpr int TCN2_EPI_WARPS = 12;                      // three per TMEM lane quadrant
+constexpr int TCN2_THREADS = 32 * (2 + TCN2_EPI_WARPS);
 
 template <int BK> struct Tcn2Cfg {
     static constexpr int W_BLOCK = TCN_PLANES * TCN2_MT * BK;   // weight planes of one K block: [7][32][BK]
@@ -207,7 +218,7 @@ template <int BK> struct Tcn2Cfg {
 };
 
 template <int BK>
-__global__ void __launch_bounds__(TCN_THREADS, 1)
+__global__ void __launch_bounds__(TCN2_THREADS, 1)
 tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                 const DeviceParams *__restrict__ P, TcnMacArgs a) {
     using Cfg = Tcn2Cfg<BK>;
@@ -241,7 +252,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         mbar_init(bar_wfull, 1);
         mbar_init(bar_wempty, 1);
         mbar_init(bar_tfull, 1);
-        mbar_init(bar_tempty, TCN_EPI_WARPS);
+        mbar_init(bar_tempty, TCN2_EPI_WARPS);
         fence_barrier_init();
         prefetch_tmap(&tmW);
         prefetch_tmap(&tmX);
@@ -324,49 +335,48 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         __syncwarp();
     } else {
         // ===================================================================== epilogue
-        // UMMA M = 128: TMEM lane = column of the chunk; a warp owns lane quadrant warp % 4, the two warps of a quadrant
-        // split the tile's 32 outputs
-        const int qd = warp & 3, half = (warp - 2) >> 2;
+        // UMMA M = 128: TMEM lane = column of the chunk; a warp owns lane quadrant warp % 4, the three warps of a
+        // quadrant take the tile's groups of 4 outputs round robin
+        const int qd = warp & 3, sub = (warp - 2) >> 2;
         const long pw = (long)a.K * n;
+        const long m_stride = 2L * a.Pimg * pw;      // words between consecutive outputs of one column
         uint32_t acc_phase = 0;
         for (long item = blockIdx.x; item < items; item += gridDim.x) {
             const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
             const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;
             const Mod mod = P->tab[j].mod;
             const long slot_off = (long)j * n + c;
+            const int m_valid = min(TCN2_MT, a.M - mt * TCN2_MT);
+            const int groups = (m_valid + 3) >> 2;
+            const uint64_t *bias_p = a.bias ? a.bias + (long)(mt * TCN2_MT) * pw + slot_off : nullptr;
             for (int ch = 0; ch < chunks; ch++) {
                 const int col = ch * TCN2_CB + qd * 32 + lane;
                 const bool valid = col < a.ncols;
                 const int p = col >> 1, poly = col & 1;
                 const long colbase = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + p % a.Pimg;
+                uint64_t *out_col = a.out + (colbase * 2 + poly) * pw + slot_off + (long)(a.m0 + mt * TCN2_MT) * m_stride;
+                const bool add_bias = bias_p != nullptr && poly == 0;
                 mbar_wait(bar_tfull, acc_phase);
                 tc_fence_after();
 #pragma unroll 1
-                for (int g = 0; g < 4; g++) {
-                    const int mloc = half * 16 + g * 4;
-                    if (mt * TCN2_MT + mloc >= a.M) break;   // warp-uniform: the rest of the tile holds no output
+                for (int g = sub; g < groups; g += TCN2_EPI_WARPS / 4) {
+                    const int mloc = g * 4;
                     uint32_t S[TCN_CLASSES][4];
 #pragma unroll
                     for (int w = 0; w < TCN_CLASSES; w++)
                         tmem_ld4(tmem_base + ((uint32_t)(qd * 32) << 16) + w * TCN2_MT + mloc, S[w]);
                     tmem_ld_wait();
+                    uint64_t *op = out_col + (long)mloc * m_stride;
+                    const uint64_t *bp = bias_p + (long)mloc * pw;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const int m = mt * TCN2_MT + mloc + i;
-                        if (!valid || m >= a.M) continue;
-                        typedef unsigned __int128 u128;
-                        const u128 t0 = ((u128)(((uint64_t)S[12][i] << 32) | S[8][i]) << 64) | (((uint64_t)S[4][i] << 32) | S[0][i]);
-                        const u128 t1 = ((u128)S[9][i] << 64) | (((uint64_t)S[5][i] << 32) | S[1][i]);
-                        const u128 t2 = ((u128)S[10][i] << 64) | (((uint64_t)S[6][i] << 32) | S[2][i]);
-                        const u128 t3 = ((u128)S[11][i] << 64) | (((uint64_t)S[7][i] << 32) | S[3][i]);
-                        const u128 tot = t0 + (t1 << 8) + (t2 << 16) + (t3 << 24);
-                        U128 z;
-                        z.lo = (uint64_t)tot;
-                        z.hi = (uint64_t)(tot >> 64);
-                        uint64_t r = barrett128(z, mod);
-                        if (poly == 0 && a.bias) r = addmod(r, __ldg(a.bias + (long)m * pw + slot_off), mod.q);
-                        const long oct = colbase + (long)(a.m0 + m) * a.Pimg;
-                        a.out[(oct * 2 + poly) * pw + slot_off] = r;
+                        if (mloc + i < m_valid) {                // warp uniform
+                            uint64_t r = barrett128(tcn_combine(S, i), mod);
+                            if (add_bias) r = addmod(r, __ldg(bp), mod.q);
+                            if (valid) *op = r;
+                        }
+                        op += m_stride;
+                        bp += pw;
                     }
                 }
                 tc_fence_before();
@@ -495,7 +505,7 @@ cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm
     }
     const long items = (long)a.nslots * ((a.M + TCN2_MT - 1) / TCN2_MT);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
-    k<<<grid, TCN_THREADS, smem, stream>>>(tmW, tmX, P, a);
+    k<<<grid, TCN2_THREADS, smem, stream>>>(tmW, tmX, P, a);
     return cudaGetLastError();
 }
 

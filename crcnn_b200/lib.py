@@ -34,6 +34,7 @@ SYMBOLS = [
     ("crcnn_tensor_upload", _I, [_vp, _vp, _L, _I, _vpp]),
     ("crcnn_tensor_upload_ex", _I, [_vp, _vp, _L, _I, _I, _vpp]),
     ("crcnn_tensor_upload_on", _I, [_vp, _vp, _L, _I, _I, _vp, _vpp]),
+    ("crcnn_tensor_upload_into", _I, [_vp, _vp, _vp, _I, _vp]),
     ("crcnn_ctx_wait_stream", _I, [_vp, _vp]),
     ("crcnn_tensor_download", _I, [_vp, _vp, _vp]),
     ("crcnn_tensor_download_ex", _I, [_vp, _vp, _I, _vp]),
@@ -193,6 +194,10 @@ class Engine:
     def upload_ptr_on(self, host_ptr, count, copy_stream_ptr, size=2, ntt_form=False):
         """H2D on a separate copy stream (double buffering); call wait_stream() before using the tensor."""
         return self._new(self.lib.crcnn_tensor_upload_on, "tensor", host_ptr, count, size, int(ntt_form), C.c_void_p(copy_stream_ptr))
+
+    def upload_into(self, t, host_ptr, copy_stream_ptr=None, ntt_form=False):
+        """Overwrite an existing tensor from a raw (pinned) host address through the context's staging buffer."""
+        self._chk(self.lib.crcnn_tensor_upload_into(self.h, host_ptr, t.ptr, int(ntt_form), C.c_void_p(copy_stream_ptr)))
 
     def wait_stream(self, stream_ptr):
         self._chk(self.lib.crcnn_ctx_wait_stream(self.h, C.c_void_p(stream_ptr)))

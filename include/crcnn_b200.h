@@ -96,6 +96,11 @@ int crcnn_tensor_upload_ex(crcnn_ctx *ctx, const uint64_t *host_words, long coun
  * first use of the tensor.  host_words should be pinned and must stay valid until the copy has run. */
 int crcnn_tensor_upload_on(crcnn_ctx *ctx, const uint64_t *host_words, long count, int ct_size, int ntt_form,
                            void *copy_stream, crcnn_tensor **out);
+/* Steady-state form of the above: overwrite an EXISTING tensor (same count and ct_size) with new host data, through a
+ * staging buffer the context keeps, so a serving loop that alternates between two input tensors allocates nothing per
+ * request.  Enqueued on copy_stream (NULL: the context's stream); uploads sharing the staging buffer must use one
+ * copy stream.  The tensor must not be in use by work still running on the context's stream. */
+int crcnn_tensor_upload_into(crcnn_ctx *ctx, const uint64_t *host_words, crcnn_tensor *t, int ntt_form, void *copy_stream);
 /* Make the context's stream wait for everything enqueued so far on other_stream (event, no host sync). */
 int crcnn_ctx_wait_stream(crcnn_ctx *ctx, void *other_stream);
 /* Always delivers coefficient form unless want_ntt_form != 0. Blocks until the copy has finished. */
