@@ -384,14 +384,28 @@ def main_b200(args, rank, world, local_rank):
         work = eng.prof_work()
         eng.prof_enable(False)
         # ---- timed: end to end through the C ABI with host buffers
+        bufs = [eng.alloc(B * per_image), eng.alloc(B * per_image)]
+        # one untimed end-to-end step: the staging buffer and the two input tensors exist before the clock starts
+        for b_ in bufs:
+            eng.upload_into(b_, host_in.data_ptr(), copy_stream.cuda_stream)
+        eng.wait_stream(copy_stream.cuda_stream)
+        y = net.forward(bufs[0], batch=B)
+        eng.download_ptr(y, host_out.data_ptr())
+        y.free()
         barrier()
         ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         ev2[0].record(stream)
         # double-buffered: the H2D copy of step s+1 runs on a copy stream while step s computes; the two input
         # tensors and the staging buffer are allocated once (crcnn_tensor_upload_into), nothing per step
-        bufs = [eng.alloc(B * per_image), eng.alloc(B * per_image)]
         done = [None, None]                      # event: forward that consumed the buffer has finished
-        eng.upload_into(bufs[0], host_in.data_ptr(), copy_stream.cuda_stream)
+        up_ev = []                               # (start, end) of every upload on the copy stream
+        def upload(i):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record(copy_stream)
+            eng.upload_into(bufs[i], host_in.data_ptr(), copy_stream.cuda_stream)
+            b_.record(copy_stream)
+            up_ev.append((a_, b_))
+        upload(0)
         for s in range(args.steps):
             cur = bufs[s & 1]
             eng.wait_stream(copy_stream.cuda_stream)
@@ -399,7 +413,7 @@ def main_b200(args, rank, world, local_rank):
                 nxt = (s + 1) & 1
                 if done[nxt] is not None:
                     copy_stream.wait_event(done[nxt])
-                eng.upload_into(bufs[nxt], host_in.data_ptr(), copy_stream.cuda_stream)
+                upload(nxt)
             y = net.forward(cur, batch=B)
             done[s & 1] = torch.cuda.Event(); done[s & 1].record(stream)
             eng.download_ptr(y, host_out.data_ptr())
@@ -503,7 +517,9 @@ def main_b200(args, rank, world, local_rank):
                    "l2": "inputs (%.1f GB per step) and weights exceed the 126 MB L2; no flush needed" % (h2d / 1e9),
                    "weights": "conv1/conv2/fc4: NTT-form plaintexts resident (CUDA-core weighted sum); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs},
+                "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
+                "upload_ms": [round(a_.elapsed_time(b_), 1) for a_, b_ in up_ev],
+                "note": "H2D + re-stride of step s+1 overlap the forward of step s on a copy stream; the first upload is not overlapped"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -50,6 +50,7 @@ struct crcnn_plain {
     uint64_t *ntt_mul_sh = nullptr;  // Shoup companions of ntt_mul (small packs only: pooling scale, batch-norm factors)
     uint64_t *ntt_add = nullptr;   // [count][K][n] NTT(Delta-scaled)    (additive use, NTT-form data)
     uint64_t *coef_add = nullptr;  // [count][K][n] Delta-scaled         (additive use, coefficient-form data)
+    int tap_state = 0;             // 0 not examined, 1 every term is +-1 at an exponent in [0,64) U [n-32,n) (tapmul_kernel applies), -1 not
     // tensor-core form (tc_mac.cuh): ternary tap matrix [count/R * 32 (+128 pad rows)][Kpad] for fan-in R
     int tc_state = 0;              // 0 not examined, 1 eligible, -1 not (support outside x^(n-32..n-1) or digits other than +-1)
     int8_t *tc_A = nullptr;
@@ -79,6 +80,7 @@ struct crcnn_ctx {
     int tc_mode = 1;                 // 1: weighted sums with fan-in >= tc_min_fanin and >= tc_min_outputs outputs run on tcgen05 kind::i8 when the weights allow it; 2: regardless of the output count
     int tc_min_fanin = 256;
     int tc_min_outputs = 32;
+    int tap_mode = 1;                // 1: avg-pool / batch-norm on coefficient-form inputs multiply in the coefficient domain (tapmul_kernel); env CRCNN_TAP
     int tcn_mode = 1;                // 1: weighted sums whose staged weights fit the weight cache run as the NTT-domain limb-split GEMM (tcn_mac.cuh)
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
@@ -243,6 +245,19 @@ int get_index_table(crcnn_ctx *ctx, const std::vector<int> &key, const std::vect
     ctx->index_cache[key] = d;
     *out = d;
     return CRCNN_OK;
+}
+
+// The coefficient-domain multiply (tapmul_kernel) applies to this pack: FractionalEncoder digits only, primes below 2^56.
+bool tap_eligible(crcnn_ctx *ctx, crcnn_plain *p) {
+    if (p->tap_state == 0) {
+        p->tap_state = (p->sparse_shape && tcn_planes_for(ctx->hp.d) == 7 && ctx->n % 1024 == 0) ? 1 : -1;
+        const uint64_t t = ctx->hp.d.t;
+        for (size_t e = 0; e < p->val.size() && p->tap_state == 1; e++)
+            if (p->val[e] != 1 && p->val[e] != t - 1) p->tap_state = -1;
+        for (long i = 0; i < p->count && p->tap_state == 1; i++)
+            if (p->off[i + 1] - p->off[i] > 96) p->tap_state = -1;
+    }
+    return p->tap_state == 1;
 }
 
 // R residues of any coefficient prime add up below 2^64
@@ -496,6 +511,7 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *e = getenv("CRCNN_TC")) c->tc_mode = atoi(e);
     if (const char *e = getenv("CRCNN_TCN")) c->tcn_mode = atoi(e);
+    if (const char *e = getenv("CRCNN_TAP")) c->tap_mode = atoi(e);
     // stream-ordered allocator: keep freed blocks cached
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -956,6 +972,21 @@ int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int 
         d_index = ctx->index_cache[key];
     }
     int rc = CRCNN_OK;
+    if (scale && !in->ntt && ctx->tap_mode && tap_eligible(ctx, scale) && sum_fits_64(ctx, R)) {
+        // coefficient-form input (after the square activation): stay there, no transform in either direction
+        crcnn_tensor *o = nullptr;
+        rc = new_tensor(ctx, Nout, 2, 0, &o);
+        if (rc) return rc;
+        TapMulArgs a{};
+        a.in = in->d; a.in_index = d_index; a.R = R; a.sub = nullptr;
+        a.t_off = scale->d_off; a.t_idx = scale->d_idx; a.t_val = scale->d_val; a.per_channel = 1; a.channels = 1;
+        a.out = o->d; a.nout = Nout;
+        ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)in->count + Nout) * 2 * ctx->K), (double)Nout * R * 2 * ctx->K * ctx->n);
+        cudaError_t e = launch_tapmul(ctx->dP, ctx->n, ctx->K, a, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+        *out = o;
+        return CRCNN_OK;
+    }
     if (scale) {
         rc = ensure_domain(ctx, in, 1);
         if (!rc) rc = ensure_shoup(ctx, scale);
@@ -982,6 +1013,22 @@ int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd
     REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
     REQUIRE(mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
     CU(cudaSetDevice(ctx->device));
+    if (!in->ntt && ctx->tap_mode && tap_eligible(ctx, invstd)) {
+        int rc = ensure_form(ctx, mean, PF_COEF_ADD);
+        if (rc) return rc;
+        crcnn_tensor *o = nullptr;
+        rc = new_tensor(ctx, in->count, 2, 0, &o);
+        if (rc) return rc;
+        TapMulArgs a{};
+        a.in = in->d; a.in_index = nullptr; a.R = 1; a.sub = mean->coef_add;
+        a.t_off = invstd->d_off; a.t_idx = invstd->d_idx; a.t_val = invstd->d_val; a.per_channel = xd * yd; a.channels = zd;
+        a.out = o->d; a.nout = in->count;
+        ProfScope ps(ctx, KC_BN, lp_bytes(ctx, (double)in->count * 4 * ctx->K), (double)in->count * 2 * ctx->K * ctx->n);
+        cudaError_t e = launch_tapmul(ctx->dP, ctx->n, ctx->K, a, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+        *out = o;
+        return CRCNN_OK;
+    }
     int rc = ensure_domain(ctx, in, 1);
     if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
     if (!rc) rc = ensure_shoup(ctx, invstd);
@@ -1003,30 +1050,46 @@ int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3) {
     REQUIRE(in && out3, "null argument");
     REQUIRE(in->size == 2, "square expects size-2 ciphertexts");
     CU(cudaSetDevice(ctx->device));
-    int rc = ensure_domain(ctx, in, 0);
-    if (rc) return rc;
+    // An NTT-form input (the usual case: the convolution before the activation leaves NTT form) keeps its transformed q
+    // limbs: the base conversion works on an inverse-transformed COPY, and only the Bsk limbs are transformed again.
+    const bool have_ntt = in->ntt != 0;
     crcnn_tensor *o = nullptr;
-    rc = new_tensor(ctx, in->count, 3, 0, &o);
+    int rc = new_tensor(ctx, in->count, 3, 0, &o);
     if (rc) return rc;
     const int KS = ctx->K + ctx->S;
     const size_t n = ctx->n, pw = poly_words(ctx);
     // bound the scratch: chunks of at most `step` ciphertexts
     const long step = std::max<long>(1, std::min<long>(in->count, (long)((2ull << 30) / (5 * (size_t)KS * n * 8))));
-    uint64_t *ext = nullptr, *prod = nullptr;
+    uint64_t *ext = nullptr, *prod = nullptr, *coef = nullptr;
     rc = dev_alloc(ctx, (size_t)step * 2 * KS * n * 8, (void **)&ext);
     if (!rc) rc = dev_alloc(ctx, (size_t)step * 3 * KS * n * 8, (void **)&prod);
+    if (!rc && have_ntt) rc = dev_alloc(ctx, (size_t)step * 2 * pw * 8, (void **)&coef);
     if (rc) { crcnn_tensor_free(ctx, o); return rc; }
     for (long c0 = 0; c0 < in->count && !rc; c0 += step) {
         const long cur = std::min<long>(step, in->count - c0);
-        cudaError_t e;
-        { ProfScope ps(ctx, KC_BEHZ_LIFT, lp_bytes(ctx, (double)cur * 2 * (ctx->K + KS)), (double)cur * 2 * n * ctx->S * (ctx->K + 1)); e = launch_behz_lift(ctx->hp.d, ctx->n, in->d + c0 * 2 * pw, cur, ext, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_FWD, 2 * lp_bytes(ctx, (double)cur * 2 * KS), lp_bfly(ctx, (double)cur * 2 * KS)); e = launch_ntt(ctx->dP, ctx->logn, ext, cur * 2 * KS, 0, KS, false, ctx->stream); }
+        const uint64_t *src = in->d + c0 * 2 * pw;
+        cudaError_t e = cudaSuccess;
+        if (have_ntt) {
+            e = cudaMemcpyAsync(coef, src, (size_t)cur * 2 * pw * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)cur * 2 * ctx->K), lp_bfly(ctx, (double)cur * 2 * ctx->K)); e = launch_ntt(ctx->dP, ctx->logn, coef, cur * 2 * ctx->K, 0, ctx->K, true, ctx->stream); }
+        }
+        if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_LIFT, lp_bytes(ctx, (double)cur * 2 * (ctx->K + KS)), (double)cur * 2 * n * ctx->S * (ctx->K + 1)); e = launch_behz_lift(ctx->hp.d, ctx->n, have_ntt ? coef : src, have_ntt ? src : nullptr, cur, ext, ctx->stream); }
+        if (e == cudaSuccess) {
+            if (have_ntt) {   // Bsk limbs only
+                ProfScope ps(ctx, KC_NTT_FWD, 2 * lp_bytes(ctx, (double)cur * 2 * ctx->S), lp_bfly(ctx, (double)cur * 2 * ctx->S));
+                e = launch_ntt_grouped(ctx->dP, ctx->logn, ext, cur * 2 * ctx->S, ctx->K, ctx->S, false, KS, ctx->K, ctx->stream);
+            } else {
+                ProfScope ps(ctx, KC_NTT_FWD, 2 * lp_bytes(ctx, (double)cur * 2 * KS), lp_bfly(ctx, (double)cur * 2 * KS));
+                e = launch_ntt(ctx->dP, ctx->logn, ext, cur * 2 * KS, 0, KS, false, ctx->stream);
+            }
+        }
         if (e == cudaSuccess) { ProfScope ps(ctx, KC_SQ_TENSOR, lp_bytes(ctx, (double)cur * 5 * KS), (double)cur * 3 * KS * n); e = launch_square_tensor(ctx->dP, ctx->n, KS, ext, cur, prod, ctx->stream); }
         if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)cur * 3 * KS), lp_bfly(ctx, (double)cur * 3 * KS)); e = launch_ntt(ctx->dP, ctx->logn, prod, cur * 3 * KS, 0, KS, true, ctx->stream); }
         if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_FLOOR, lp_bytes(ctx, (double)cur * 3 * (KS + ctx->K)),
                                                      (double)cur * 3 * n * (ctx->S * (ctx->K + 1) + ctx->S + ctx->K * ctx->S)); e = launch_behz_floor(ctx->hp.d, ctx->n, prod, cur, o->d + c0 * 3 * pw, ctx->stream); }
         if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
     }
+    dev_free(ctx, coef);
     dev_free(ctx, ext); dev_free(ctx, prod);
     if (rc) { crcnn_tensor_free(ctx, o); return rc; }
     *out3 = o;

@@ -10,22 +10,25 @@ namespace crcnn {
 // =====================================================================================
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
-ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count) {
+ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count, int group_polys,
+               int group_off) {
     extern __shared__ uint64_t sm[];
     const long p = blockIdx.x;
     const NttTable tb = P->tab[slot_base + (int)(p % slot_count)];
-    uint64_t *poly = data + p * (1L << LOGN);
+    // polynomial p is the (p % slot_count)-th of a group of slot_count transformed polynomials inside a record of group_polys
+    uint64_t *poly = data + ((p / slot_count) * group_polys + group_off + p % slot_count) * (1L << LOGN);
     ntt_forward_to_smem<LOGN>(sm, poly, tb);
     smem_store_poly_canonical<LOGN>(sm, poly, tb.mod);
 }
 
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
-ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count) {
+ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count, int group_polys,
+               int group_off) {
     extern __shared__ uint64_t sm[];
     const long p = blockIdx.x;
     const NttTable tb = P->tab[slot_base + (int)(p % slot_count)];
-    uint64_t *poly = data + p * (1L << LOGN);
+    uint64_t *poly = data + ((p / slot_count) * group_polys + group_off + p % slot_count) * (1L << LOGN);
     smem_load_poly<LOGN>(sm, poly);
     __syncthreads();
     ntt_inverse_from_smem<LOGN>(sm, poly, tb);
@@ -33,7 +36,7 @@ ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, 
 
 template <int LOGN>
 static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npolys, int slot_base, int slot_count,
-                                bool inverse, cudaStream_t stream) {
+                                bool inverse, int group_polys, int group_off, cudaStream_t stream) {
     using Pl = NttPlan<LOGN>;
     size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto kf = ntt_fwd_kernel<LOGN>;
@@ -48,21 +51,26 @@ static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npol
         configured = true;
     }
     if (npolys <= 0) return cudaSuccess;
-    if (inverse) ki<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count);
-    else kf<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count);
+    if (inverse) ki<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count, group_polys, group_off);
+    else kf<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count, group_polys, group_off);
     return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_grouped(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
+                               bool inverse, int group_polys, int group_off, cudaStream_t stream) {
+    switch (logn) {
+        case 10: return launch_ntt_t<10>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
+        case 11: return launch_ntt_t<11>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
+        case 12: return launch_ntt_t<12>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
+        case 13: return launch_ntt_t<13>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
+        case 14: return launch_ntt_t<14>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_ntt(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
                        bool inverse, cudaStream_t stream) {
-    switch (logn) {
-        case 10: return launch_ntt_t<10>(P, data, npolys, slot_base, slot_count, inverse, stream);
-        case 11: return launch_ntt_t<11>(P, data, npolys, slot_base, slot_count, inverse, stream);
-        case 12: return launch_ntt_t<12>(P, data, npolys, slot_base, slot_count, inverse, stream);
-        case 13: return launch_ntt_t<13>(P, data, npolys, slot_base, slot_count, inverse, stream);
-        case 14: return launch_ntt_t<14>(P, data, npolys, slot_base, slot_count, inverse, stream);
-        default: return cudaErrorInvalidValue;
-    }
+    return launch_ntt_grouped(P, logn, data, npolys, slot_base, slot_count, inverse, slot_count, 0, stream);
 }
 
 // =====================================================================================
@@ -372,6 +380,118 @@ bn_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, i
     *reinterpret_cast<ulonglong2 *>(out + ct * ctw + word) = x;
 }
 
+// =====================================================================================
+// multiply_plain in the COEFFICIENT domain for FractionalEncoder plaintexts (pooling scale, batch-norm factor).
+// Such a plaintext is sum_e s_e x^(i_e) with s_e = +-1 (values 1 / t-1, lifted to +-1 mod every q_j by
+// Evaluator::transform_to_ntt, evaluator.cpp:1465-1486) and at most 96 terms (64 integer, 32 fraction digits), so
+//       (X * w)[c] = sum_e s_e * X~[c - i_e],     X~ = X extended negacyclically (X~[c +- n] = -X[c]),
+// a few dozen additions per residue instead of a forward transform, a pointwise product and an inverse transform.
+// Fused in front of it: the window sum of a pooling layer (in_index, R) and the mean subtraction of batch-norm
+// (sub: Delta-scaled mean, polynomial 0 only).  One CTA = 256 consecutive coefficients of one output limb-polynomial;
+// needs q < 2^56 (96 residues add up below 2^63).
+// =====================================================================================
+constexpr int TAP_CT = 1024;   // coefficients per CTA (4 consecutive ones per thread)
+
+__global__ void __launch_bounds__(256)
+tapmul_kernel(const DeviceParams *__restrict__ P, TapMulArgs a) {
+    __shared__ uint64_t sm[64 + TAP_CT + 32];
+    __shared__ short t_delta[96];          // positive terms first, then the negative ones
+    __shared__ int t_count[2];
+    const int n = P->n, K = P->K;
+    const int chunks = n / TAP_CT;
+    long b = blockIdx.x;
+    const int c0 = (int)(b % chunks) * TAP_CT; b /= chunks;
+    const int j = (int)(b % K); b /= K;
+    const int poly = (int)(b & 1);
+    const long o = b >> 1;
+    const int z = a.channels > 1 ? (int)((o / a.per_channel) % a.channels) : 0;
+    const Mod mod = P->tab[j].mod;
+    const long pw = (long)K * n, ctw = 2 * pw;
+    const uint32_t lo = a.t_off[z], hi = a.t_off[z + 1];
+    const int ntaps = (int)(hi - lo);
+    if (threadIdx.x < 32) {
+        // low index: X~[c - ix] with sign s; high index ix = n - tap: x^ix = -x^(-tap), X~[c + tap] with sign -s.
+        // One warp sorts the terms by sign with ballots (at most 96 terms = 3 rounds).
+        int npos = 0, nneg = 0;
+        for (int e0 = 0; e0 < ntaps; e0 += 32) {
+            const int e = e0 + threadIdx.x;
+            int ix = 0, sgn = 0;
+            if (e < ntaps) {
+                ix = (int)a.t_idx[lo + e];
+                const int s1 = a.t_val[lo + e] == 1 ? 1 : -1;
+                sgn = ix < 64 ? s1 : -s1;
+            }
+            const unsigned mp = __ballot_sync(0xffffffffu, sgn > 0), mn = __ballot_sync(0xffffffffu, sgn < 0);
+            const unsigned below = (1u << threadIdx.x) - 1;
+            const short delta = (short)(ix < 64 ? -ix : n - ix);
+            if (sgn > 0) t_delta[npos + __popc(mp & below)] = delta;
+            npos += __popc(mp);
+            (void)mn;
+            nneg += __popc(mn);
+        }
+        // negatives go after all positives: second pass now that npos is known
+        int k = 0;
+        for (int e0 = 0; e0 < ntaps; e0 += 32) {
+            const int e = e0 + threadIdx.x;
+            int ix = 0, sgn = 0;
+            if (e < ntaps) {
+                ix = (int)a.t_idx[lo + e];
+                const int s1 = a.t_val[lo + e] == 1 ? 1 : -1;
+                sgn = ix < 64 ? s1 : -s1;
+            }
+            const unsigned mn = __ballot_sync(0xffffffffu, sgn < 0);
+            const unsigned below = (1u << threadIdx.x) - 1;
+            if (sgn < 0) t_delta[npos + k + __popc(mn & below)] = (short)(ix < 64 ? -ix : n - ix);
+            k += __popc(mn);
+        }
+        if (threadIdx.x == 0) { t_count[0] = npos; t_count[1] = nneg; }
+    }
+    const uint64_t *subp = (a.sub && poly == 0) ? a.sub + (long)z * pw + (long)j * n : nullptr;
+    for (int i = threadIdx.x; i < 64 + TAP_CT + 32; i += 256) {
+        int cc = c0 - 64 + i;
+        const bool wrapped = cc < 0 || cc >= n;
+        cc = cc < 0 ? cc + n : (cc >= n ? cc - n : cc);
+        uint64_t v = 0;
+        const long word = (long)poly * pw + (long)j * n + cc;
+        if (a.in_index) {
+            for (int r = 0; r < a.R; r++) v += __ldg(a.in + (long)__ldg(a.in_index + o * a.R + r) * ctw + word);
+            v = reduce64(v, mod);
+        } else {
+            v = __ldg(a.in + o * ctw + word);
+        }
+        if (subp) v = submod(v, __ldg(subp + cc), mod.q);
+        sm[i] = wrapped ? negmod(v, mod.q) : v;
+    }
+    __syncthreads();
+    const int npos = t_count[0], nneg = t_count[1];
+    // thread t owns coefficients t, t + 256, t + 512, t + 768 of the CTA's 1024: every shared-memory access of a warp
+    // touches 32 consecutive words (conflict free for any tap offset)
+    const uint64_t *base = sm + 64 + threadIdx.x;
+    uint64_t pos[4] = {0, 0, 0, 0}, neg[4] = {0, 0, 0, 0};
+    for (int e = 0; e < npos; e++) {
+        const uint64_t *v = base + t_delta[e];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pos[k] += v[256 * k];
+    }
+    for (int e = npos; e < npos + nneg; e++) {
+        const uint64_t *v = base + t_delta[e];
+#pragma unroll
+        for (int k = 0; k < 4; k++) neg[k] += v[256 * k];
+    }
+    const uint64_t off = (uint64_t)nneg * mod.q;
+    uint64_t *op = a.out + o * ctw + (long)poly * pw + (long)j * n + c0 + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) op[256 * k] = reduce64(pos[k] + off - neg[k], mod);
+}
+
+cudaError_t launch_tapmul(const DeviceParams *P, int n, int K, const TapMulArgs &a, cudaStream_t stream) {
+    if (a.nout <= 0) return cudaSuccess;
+    const long blocks = a.nout * 2 * K * (n / TAP_CT);
+    if (n % TAP_CT || blocks > 0x7fffffffL) return cudaErrorInvalidValue;
+    tapmul_kernel<<<(unsigned)blocks, 256, 0, stream>>>(P, a);
+    return cudaGetLastError();
+}
+
 // Shoup companions floor(v * 2^64 / q) of canonical residues v (data = [..][K][n]); runs once per plaintext pack.
 __global__ void __launch_bounds__(256)
 shoup_companion_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ data, long words, uint64_t *__restrict__ out) {
@@ -415,7 +535,8 @@ plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data,
 // because the parameter block is passed by value); KT == 0: any K <= MAXK, S <= MAXS at run time.
 template <int KT, int ST>
 __global__ void __launch_bounds__(128)
-behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restrict__ in, uint64_t *__restrict__ ext) {
+behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restrict__ in, const uint64_t *__restrict__ in_ntt,
+                 uint64_t *__restrict__ ext) {
     const int n = P.n, K = KT ? KT : P.K, S = KT ? ST : P.S;
     constexpr int KB = KT ? KT : MAXK, SB = KT ? ST : MAXS;
     const int per = n / 128;
@@ -429,7 +550,8 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
     for (int i = 0; i < KB; i++) {
         if (i < K) {
             uint64_t x = __ldg(src + (long)i * n);
-            dst[(long)i * n] = x;
+            // the q limbs of ext are transformed next: take them already transformed when the caller has them
+            dst[(long)i * n] = in_ntt ? __ldg(in_ntt + poly * K * n + c + (long)i * n) : x;
             y[i] = mulmod(x, P.mt_inv_qhat[i], P.tab[i].mod);
             zmt += (uint32_t)y[i] * (uint32_t)P.qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
         }
@@ -691,11 +813,11 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
         else KERNEL<0, 0><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);                                 \
     } while (0)
 
-cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, long count, uint64_t *ext,
+cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, const uint64_t *in_ntt, long count, uint64_t *ext,
                                 cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)(count * 2 * (n / 128));
-    CRCNN_BEHZ_DISPATCH(behz_lift_kernel, grid, in, ext);
+    CRCNN_BEHZ_DISPATCH(behz_lift_kernel, grid, in, in_ntt, ext);
     return cudaGetLastError();
 }
 

@@ -12,6 +12,11 @@ namespace crcnn {
 cudaError_t launch_ntt(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
                        bool inverse, cudaStream_t stream);
 
+// Same for polynomials that sit `slot_count` in a row at offset group_off inside records of group_polys polynomials
+// (e.g. only the Bsk limbs of [count][2][K+S][n]).
+cudaError_t launch_ntt_grouped(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
+                               bool inverse, int group_polys, int group_off, cudaStream_t stream);
+
 // ---- plaintext packs: sparse coefficient form -> dense NTT form, one CTA per (plaintext, limb).
 // mode 0: lifted residues (multiplicative use: weights, scale factors)  [evaluator.cpp:1465-1486]
 // mode 1: Delta-scaled residues (additive use: biases, means)           [evaluator.cpp:1169-1191]
@@ -44,6 +49,21 @@ cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, l
                       const uint64_t *mean_ntt, const uint64_t *invstd_ntt, const uint64_t *invstd_shoup, uint64_t *out,
                       cudaStream_t stream);
 
+// ---- coefficient-domain multiply_plain by a +-1-digit plaintext, fused with a window sum and a plaintext subtraction
+struct TapMulArgs {
+    const uint64_t *in;       // ciphertexts [..][2][K][n], COEFFICIENT form
+    const int *in_index;      // [nout][R] inputs summed for output o (pooling); null: input o itself, R ignored
+    int R;
+    const uint64_t *sub;      // [channels][K][n] Delta-scaled plaintext subtracted from polynomial 0 first (batch-norm mean); may be null
+    const uint32_t *t_off;    // sparse form of the multiplier pack: plaintext z has terms [t_off[z], t_off[z+1])
+    const uint32_t *t_idx;    //   exponents, in [0,64) U [n-32,n)
+    const uint64_t *t_val;    //   values, 1 or t-1
+    int per_channel, channels;  // output o uses plaintext z = (o / per_channel) % channels (channels == 1: always plaintext 0)
+    uint64_t *out;            // [nout][2][K][n] coefficient form
+    long nout;
+};
+cudaError_t launch_tapmul(const DeviceParams *P, int n, int K, const TapMulArgs &a, cudaStream_t stream);
+
 // ---- Shoup companions floor(v * 2^64 / q_j) of `words` canonical residues laid out [..][K][n]
 cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, long words, uint64_t *out, cudaStream_t stream);
 
@@ -57,7 +77,10 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
 // lift:   in [count][2][K][n] (coefficient form) -> ext [count][2][K+S][n] (q limbs copied, Bsk limbs computed)
 // (lift and floor take the HOST copy of the parameter block: it travels as a by-value kernel argument, so every
 // base-conversion constant is a constant-bank operand)
-cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, long count, uint64_t *ext, cudaStream_t stream);
+// in_ntt (optional): the same ciphertexts in NTT form; the q limbs of ext are then copied from it and only the Bsk
+// limbs still need the forward transform
+cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, const uint64_t *in_ntt, long count, uint64_t *ext,
+                             cudaStream_t stream);
 // tensor: ext (NTT form) -> prod [count][3][K+S][n] (NTT form): c0^2, 2 c0 c1, c1^2
 cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uint64_t *ext, long count, uint64_t *prod, cudaStream_t stream);
 // floor:  prod (coefficient form) -> out [count][3][K][n]: multiply by t, fast_floor, fastbconv_sk

@@ -398,6 +398,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 __global__ void __launch_bounds__(256)
 tcn_split_kernel(TcnSplitArgs a) {
     __shared__ uint64_t tile[32][133];    // [slot][(e & 3) * 33 + (e >> 2)], e = byte within the 128; row stride 133 = 5 mod 16: conflict free both ways
+    __shared__ long src_off[128];         // word offset of source row e (-1: padding)
     const int n = a.n, K = a.K;
     const int rows_per = a.Kpad < 128 ? 128 / a.Kpad : 1;   // columns per CTA
     const int col0 = blockIdx.x * rows_per;
@@ -406,28 +407,44 @@ tcn_split_kernel(TcnSplitArgs a) {
     const int slot = a.slot0 + st * 32;
     const int j = slot / n, c0 = slot - j * n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int e = warp; e < 128; e += 8) {
+    if (threadIdx.x < 128) {
+        const int e = threadIdx.x;
         const int col = col0 + (rows_per > 1 ? e / a.Kpad : 0);
         const int r = rows_per > 1 ? e % a.Kpad : r0 + e;
-        uint64_t v = 0;
+        long off = -1;
         if (r < a.R && col < a.ncols) {
             const int group = col / a.item_polys, poly = col - group * a.item_polys;
             const long item = a.index ? (long)__ldg(a.index + (long)group * a.R + r) : (long)group * a.R + r;
-            v = __ldg(a.src + ((item * a.item_polys + poly) * K + j) * (long)n + c0 + lane);
+            off = ((item * a.item_polys + poly) * K + j) * (long)n + c0;
         }
-        tile[lane][(e & 3) * 33 + (e >> 2)] = v;
+        src_off[e] = off;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int e = warp; e < 128; e += 8) {
+        const long off = src_off[e];
+        tile[lane][(e & 3) * 33 + (e >> 2)] = off >= 0 ? __ldg(a.src + off + lane) : 0;
     }
     __syncthreads();
     const long plane_stride = (long)a.ncols * a.Kpad;
     const long row_bytes = plane_stride - (long)col0 * a.Kpad - r0;   // bytes left in the plane row from this CTA's start
     uint8_t *dst = a.dst + ((long)st * 32 * a.planes) * plane_stride + (long)col0 * a.Kpad + r0;
-    for (int w = threadIdx.x; w < a.planes * 1024; w += 256) {
-        const int l = w >> 10, c = (w >> 5) & 31, rw = w & 31;
+    // one thread: 4 consecutive source rows of one slot -> one 32-bit word of each of the 7 planes (3 byte permutes per word)
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+        const int w = threadIdx.x + 256 * it;
+        const int c = w >> 5, rw = w & 31;
         if (rows_per > 1 ? 4 * rw >= row_bytes : r0 + 4 * rw >= a.Kpad) continue;
-        const int sh = 8 * l;
-        const uint32_t word = (uint32_t)((tile[c][rw] >> sh) & 0xff) | (uint32_t)((tile[c][33 + rw] >> sh) & 0xff) << 8 |
-                              (uint32_t)((tile[c][66 + rw] >> sh) & 0xff) << 16 | (uint32_t)((tile[c][99 + rw] >> sh) & 0xff) << 24;
-        *reinterpret_cast<uint32_t *>(dst + ((long)c * a.planes + l) * plane_stride + 4 * rw) = word;
+        const uint64_t x0 = tile[c][rw], x1 = tile[c][33 + rw], x2 = tile[c][66 + rw], x3 = tile[c][99 + rw];
+        uint8_t *d = dst + (long)c * a.planes * plane_stride + 4 * rw;
+#pragma unroll
+        for (int l = 0; l < 7; l++) {
+            const uint32_t a0 = l < 4 ? (uint32_t)x0 : (uint32_t)(x0 >> 32), a1 = l < 4 ? (uint32_t)x1 : (uint32_t)(x1 >> 32);
+            const uint32_t a2 = l < 4 ? (uint32_t)x2 : (uint32_t)(x2 >> 32), a3 = l < 4 ? (uint32_t)x3 : (uint32_t)(x3 >> 32);
+            const uint32_t sel = (uint32_t)(l & 3) | ((uint32_t)(4 + (l & 3)) << 4);
+            const uint32_t w01 = __byte_perm(a0, a1, sel), w23 = __byte_perm(a2, a3, sel);
+            *reinterpret_cast<uint32_t *>(d + (long)l * plane_stride) = __byte_perm(w01, w23, 0x5410);
+        }
     }
 }
 

@@ -114,6 +114,11 @@ def test_square_and_relinearize(env):
     assert np.array_equal(got2, orc.relinearize(want3, evk, sizes, dbc))
     got_layer = eng.download(eng.square_layer(eng.upload(x), k))
     assert np.array_equal(got_layer, got2)
+    # NTT-form input (what a convolution hands over): the q limbs skip their forward transform inside square
+    tn = eng.upload(x)
+    eng.to_ntt(tn)
+    assert np.array_equal(eng.download(eng.square(tn)), want3)
+    assert np.array_equal(eng.download(tn), x), "square must not change the value of its input"
 
 
 def _layer_params(orc, rng, count):
@@ -186,6 +191,11 @@ def test_pool_layers(env, avg):
             d, cc = orc.encode(1.0 / (xf * yf))
             want = orc.pool(x, xd, yd, zd, xs, ys, xf, yf, d, cc)
             got = eng.download(eng.pool(eng.upload(x), 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode([1.0 / (xf * yf)])))
+            # coefficient-form input takes the coefficient-domain multiply; NTT-form input the NTT-domain kernel
+            tn = eng.upload(x)
+            eng.to_ntt(tn)
+            got_n = eng.download(eng.pool(tn, 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode([1.0 / (xf * yf)])))
+            assert np.array_equal(got_n.reshape(want.shape), want)
         else:
             want = orc.pool(x, xd, yd, zd, xs, ys, xf, yf)
             got = eng.download(eng.pool(eng.upload(x), 1, xd, yd, zd, xs, ys, xf, yf))
@@ -202,6 +212,15 @@ def test_bn_layer(env):
     want = orc.bn(x, zd, xd, yd, mp, vp)
     got = eng.download(eng.bn(eng.upload(x), 1, zd, xd, yd, eng.plain_encode(mv), eng.plain_encode(vv)))
     assert np.array_equal(got.reshape(want.shape), want)
+    tn = eng.upload(x)       # NTT-form input: the NTT-domain kernel instead of the coefficient-domain multiply
+    eng.to_ntt(tn)
+    got_n = eng.download(eng.bn(tn, 1, zd, xd, yd, eng.plain_encode(mv), eng.plain_encode(vv)))
+    assert np.array_equal(got_n.reshape(want.shape), want)
+    # factors with an integer part (digits at x^0, x^1, ...) and negative ones
+    vv2 = np.array([7.25, -0.3, 26.9], dtype=np.float32)
+    want2 = orc.bn(x, zd, xd, yd, mp, orc.encode_many(vv2))
+    got2 = eng.download(eng.bn(eng.upload(x), 1, zd, xd, yd, eng.plain_encode(mv), eng.plain_encode(vv2)))
+    assert np.array_equal(got2.reshape(want2.shape), want2)
 
 
 def test_layer_chain_stays_exact(env):
