@@ -459,9 +459,10 @@ def main_b200(args, rank, world, local_rank):
     # integer pipe: 64x64->128-bit multiply-accumulates per second of a register-only loop, measured in this run
     probe_ms = eng.probe_imad(148 * 8, 256, 4096)
     probe_rate = 148 * 8 * 256 * 4096 * 8 / (probe_ms / 1000.0)
-    traffic = {}
+    traffic = {}   # measured DRAM bytes per launch of each class's main kernel, from the committed ncu capture (tools/make_traffic.py)
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = {k: v["dram_bytes_per_launch"] for k, v in tj["classes"].items()}
     except Exception:
         pass
     MAC_CLASSES = ("weighted_sum_mac", "behz_lift", "behz_floor_sk")

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""profiles/traffic.json from `ncu --set full` raw-page exports: measured DRAM bytes per launch of the main kernel of
+every kernel class bench.py reports (roofline.traffic).  usage: tools/make_traffic.py <tag> (reads gpurun_out/<tag>_*_raw.csv)"""
+import csv
+import re
+import glob
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLASS_OF = {"ntt_fwd_digits_kernel": "relinearize", "ntt_inv_kernel": "ntt_inverse", "ntt_fwd_kernel": "ntt_forward",
+            "tc_mac_kernel": "weighted_sum_tc_i8", "tcn2_mac_kernel": "weighted_sum_tcn_i8", "tcn_mac_kernel": "weighted_sum_tcn_i8_rowmajor", "tcn_split_kernel": "tcn_plane_split",
+            "behz_floor_kernel": "behz_floor_sk", "pool_kernel": "pool_sum", "bn_kernel": "batch_norm", "mac_kernel": "weighted_sum_mac"}
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def main():
+    tag = sys.argv[1]
+    out = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", tag + "_*_raw.csv"))):
+        rows = list(csv.reader(open(path)))
+        h, u = rows[0], rows[1]
+        for r in rows[2:]:
+            name = r[h.index("Kernel Name")]
+            key = next((k for k in CLASS_OF if re.search(r"(::|\s|^)%s[<(]" % k, name)), None)
+            if key is None:
+                continue
+            tot = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = h.index(m)
+                tot += float(r[i].replace(",", "")) * UNIT.get(u[i], 1.0)
+            d = float(r[h.index("gpu__time_duration.sum")].replace(",", ""))
+            ent = out.setdefault(CLASS_OF[key], {"kernel": key, "launches": []})
+            ent["launches"].append({"dram_bytes": tot, "duration": d, "duration_unit": u[h.index("gpu__time_duration.sum")],
+                                    "grid": r[h.index("launch__grid_size")]})
+    for ent in out.values():
+        ent["dram_bytes_per_launch"] = sum(l["dram_bytes"] for l in ent["launches"]) / len(ent["launches"])
+    json.dump({"source": "ncu --set full --clock-control none, one forward at batch 8 (tools/gpu_profile.sh %s)" % tag, "classes": out},
+              open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+    print(json.dumps({k: v["dram_bytes_per_launch"] for k, v in out.items()}, indent=1))
+
+
+if __name__ == "__main__":
+    main()
