@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0, help="CPU seconds for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default=None, choices=sorted(nets.TOPOLOGIES),
+                    help="network to run instead of the headline PlainModel (e.g. PlainModelTiny with --n 4096: BASELINE config 1)")
+    ap.add_argument("--n", type=int, default=None, choices=[4096, 8192, 16384], help="polynomial degree (default 8192)")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "shard"],
                     help="replicas: every GPU runs its own image batch (default, weak scaling); shard: ONE image, the Approx "
                          "network's conv / fc layers split by output neuron across the GPUs with NCCL all-gathers of the "
@@ -211,7 +214,7 @@ def run_reference_sample(budget_s, rng):
         full_times[name] = dt * scale
         total += dt * scale
         desc.append("%s x%.3g" % (name.split(".")[-1], scale))
-    sample = ("reference layer classes (SEAL 2.3.1, -O3) on a cropped PlainModel net, n=8192; per-layer time x "
+    sample = ("reference layer classes (SEAL 2.3.1, -O3) on a cropped %s net, n=%d; per-layer time x " % (MODEL, N_POLY) +
               "(full work / sample work): " + ", ".join(desc))
     return 1.0 / total, cores, sample, full_times
 
@@ -336,9 +339,10 @@ def main_b200(args, rank, world, local_rank):
     host_in = torch.empty(in_words, dtype=torch.int64, pin_memory=True)
     view = host_in.numpy().view(np.uint64).reshape(B * per_image, 2, K, n + 1)
     synth_residues(rng, (B * per_image, 2), PRIMES, n, out=view)
-    host_out = torch.empty(B * 10 * ct_words, dtype=torch.int64, pin_memory=True)
+    n_scores = nets.layer_io_counts(net.layers[-1])[1]
+    host_out = torch.empty(B * n_scores * ct_words, dtype=torch.int64, pin_memory=True)
     h2d = in_words * 8
-    d2h = B * 10 * ct_words * 8
+    d2h = B * n_scores * ct_words * 8
 
     layer_names = [l[1] for l in net.layers]
 
@@ -513,7 +517,8 @@ def main_b200(args, rank, world, local_rank):
         "metric": "encrypted MNIST images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic: uniform residues in SEAL ciphertext layout; weights = PlainModel.h5",
-        "config": {"workload": "PlainModel.h5 encoded net (conv-avgpool-bn-conv-square-avgpool-bn-fc-fc), n=8192, K=4, t=2^30, 32x32 zero-bordered input",
+        "config": {"workload": ("PlainModel.h5 encoded net (conv-avgpool-bn-conv-square-avgpool-bn-fc-fc), n=8192, K=4, t=2^30, 32x32 zero-bordered input"
+                                if (MODEL, N_POLY) == ("PlainModel", 8192) else "%s encoded net, n=%d, K=%d, t=2^%d" % (MODEL, N_POLY, K, T_PLAIN.bit_length() - 1)),
                    "images_per_step_per_gpu": B, "parallelism": "image replicas x%d (no collective)" % world,
                    "l2": "inputs (%.1f GB per step) and weights exceed the 126 MB L2; no flush needed" % (h2d / 1e9),
                    "weights": "conv1/conv2/fc4: NTT-form plaintexts resident (CUDA-core weighted sum); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
@@ -557,7 +562,14 @@ def port_baseline(budget_s):
 
 
 def main():
+    global MODEL, N_POLY, PRIMES, T_PLAIN
     args = parse()
+    if args.model:
+        MODEL = args.model
+    if args.n:
+        from oracle.port import DEFAULT_PRIMES_128   # the table of SEAL's default primes only
+        N_POLY, PRIMES = args.n, [int(q) for q in DEFAULT_PRIMES_128[args.n]]
+        T_PLAIN = (1 << 18) if args.n == 4096 else (1 << 30)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
