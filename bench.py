@@ -388,6 +388,7 @@ def main_b200(args, rank, world, local_rank):
         work = eng.prof_work()
         eng.prof_enable(False)
         # ---- timed: end to end through the C ABI with host buffers
+        mem_free = [torch.cuda.mem_get_info()[0] / 1e9]
         bufs = [eng.alloc(B * per_image), eng.alloc(B * per_image)]
         # one untimed end-to-end step: the staging buffer and the two input tensors exist before the clock starts
         for b_ in bufs:
@@ -425,6 +426,7 @@ def main_b200(args, rank, world, local_rank):
         ev2[1].record(stream)
         barrier()
         ms_e2e = ev2[0].elapsed_time(ev2[1])
+        mem_free.append(torch.cuda.mem_get_info()[0] / 1e9)
         # the host link by itself: one plain pinned H2D copy of a step's input (explains e2e when the link is the limit)
         dev_buf = torch.empty(in_words, dtype=torch.int64, device="cuda")
         ev3 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -525,6 +527,7 @@ def main_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
                 "upload_ms": [round(a_.elapsed_time(b_), 1) for a_, b_ in up_ev],
+                "device_mem_free_gb": {"after_resident_loop": round(mem_free[0], 1), "after_e2e_loop": round(mem_free[1], 1)},
                 "note": "H2D + re-stride of step s+1 overlap the forward of step s on a copy stream; the first upload is not overlapped"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,
     }

@@ -1070,8 +1070,8 @@ int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3) {
         const uint64_t *src = in->d + c0 * 2 * pw;
         cudaError_t e = cudaSuccess;
         if (have_ntt) {
-            e = cudaMemcpyAsync(coef, src, (size_t)cur * 2 * pw * 8, cudaMemcpyDeviceToDevice, ctx->stream);
-            if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)cur * 2 * ctx->K), lp_bfly(ctx, (double)cur * 2 * ctx->K)); e = launch_ntt(ctx->dP, ctx->logn, coef, cur * 2 * ctx->K, 0, ctx->K, true, ctx->stream); }
+            ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)cur * 2 * ctx->K), lp_bfly(ctx, (double)cur * 2 * ctx->K));
+            e = launch_ntt_grouped(ctx->dP, ctx->logn, coef, cur * 2 * ctx->K, 0, ctx->K, true, ctx->K, 0, ctx->stream, src);  // out of place
         }
         if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_LIFT, lp_bytes(ctx, (double)cur * 2 * (ctx->K + KS)), (double)cur * 2 * n * ctx->S * (ctx->K + 1)); e = launch_behz_lift(ctx->hp.d, ctx->n, have_ntt ? coef : src, have_ntt ? src : nullptr, cur, ext, ctx->stream); }
         if (e == cudaSuccess) {
@@ -1133,8 +1133,12 @@ int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_t
         a.out = o->d + c0 * 2 * pw;
         cudaError_t e;
         { ProfScope ps(ctx, KC_RELIN, lp_bytes(ctx, (double)a.count * 3 * ctx->K), lp_bfly(ctx, (double)a.count * total_digits * ctx->K)); e = launch_relin(ctx->dP, ctx->logn, ctx->K, a, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)a.count * 2 * ctx->K), lp_bfly(ctx, (double)a.count * 2 * ctx->K)); e = launch_ntt(ctx->dP, ctx->logn, a.acc, a.count * 2 * ctx->K, 0, ctx->K, true, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_PLAIN_OP, lp_bytes(ctx, (double)a.count * 6 * ctx->K), (double)a.count * 2 * ctx->K * ctx->n); e = launch_relin_finish(ctx->dP, ctx->n, ctx->K, a, ctx->stream); }
+        if (e == cudaSuccess) {
+            // inverse transform of the key products, written straight to the output with "+ (c0, c1)" fused into the last pass
+            ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)a.count * 2 * ctx->K) + lp_bytes(ctx, (double)a.count * 2 * ctx->K), lp_bfly(ctx, (double)a.count * 2 * ctx->K));
+            e = launch_ntt_grouped(ctx->dP, ctx->logn, a.out, a.count * 2 * ctx->K, 0, ctx->K, true, ctx->K, 0, ctx->stream, a.acc, a.in3,
+                                   2 * ctx->K, 3 * ctx->K);
+        }
         if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
     }
     dev_free(ctx, scratch);

@@ -24,19 +24,22 @@ ntt_fwd_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, 
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
 ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, int slot_base, int slot_count, int group_polys,
-               int group_off) {
+               int group_off, const uint64_t *__restrict__ src, const uint64_t *__restrict__ addend, int add_group, int add_stride) {
     extern __shared__ uint64_t sm[];
     const long p = blockIdx.x;
     const NttTable tb = P->tab[slot_base + (int)(p % slot_count)];
-    uint64_t *poly = data + ((p / slot_count) * group_polys + group_off + p % slot_count) * (1L << LOGN);
-    smem_load_poly<LOGN>(sm, poly);
+    const long off = ((p / slot_count) * group_polys + group_off + p % slot_count) * (1L << LOGN);
+    uint64_t *poly = data + off;
+    smem_load_poly<LOGN>(sm, src ? src + off : poly);   // src: out-of-place transform (same indexing), data is only written
     __syncthreads();
-    ntt_inverse_from_smem<LOGN>(sm, poly, tb);
+    // addend (relinearize): polynomial p adds polynomial (p / add_group) * add_stride + p % add_group of `addend`
+    ntt_inverse_from_smem<LOGN>(sm, poly, tb, addend ? addend + ((p / add_group) * add_stride + p % add_group) * (1L << LOGN) : nullptr);
 }
 
 template <int LOGN>
 static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npolys, int slot_base, int slot_count,
-                                bool inverse, int group_polys, int group_off, cudaStream_t stream) {
+                                bool inverse, int group_polys, int group_off, const uint64_t *src, const uint64_t *addend,
+                                int add_group, int add_stride, cudaStream_t stream) {
     using Pl = NttPlan<LOGN>;
     size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto kf = ntt_fwd_kernel<LOGN>;
@@ -51,19 +54,21 @@ static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npol
         configured = true;
     }
     if (npolys <= 0) return cudaSuccess;
-    if (inverse) ki<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count, group_polys, group_off);
+    if ((src || addend) && !inverse) return cudaErrorInvalidValue;
+    if (inverse) ki<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count, group_polys, group_off, src, addend, add_group, add_stride);
     else kf<<<(unsigned)npolys, Pl::THREADS, smem, stream>>>(data, P, slot_base, slot_count, group_polys, group_off);
     return cudaGetLastError();
 }
 
 cudaError_t launch_ntt_grouped(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
-                               bool inverse, int group_polys, int group_off, cudaStream_t stream) {
+                               bool inverse, int group_polys, int group_off, cudaStream_t stream, const uint64_t *src,
+                               const uint64_t *addend, int add_group, int add_stride) {
     switch (logn) {
-        case 10: return launch_ntt_t<10>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
-        case 11: return launch_ntt_t<11>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
-        case 12: return launch_ntt_t<12>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
-        case 13: return launch_ntt_t<13>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
-        case 14: return launch_ntt_t<14>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, stream);
+        case 10: return launch_ntt_t<10>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, src, addend, add_group, add_stride, stream);
+        case 11: return launch_ntt_t<11>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, src, addend, add_group, add_stride, stream);
+        case 12: return launch_ntt_t<12>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, src, addend, add_group, add_stride, stream);
+        case 13: return launch_ntt_t<13>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, src, addend, add_group, add_stride, stream);
+        case 14: return launch_ntt_t<14>(P, data, npolys, slot_base, slot_count, inverse, group_polys, group_off, src, addend, add_group, add_stride, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -300,50 +305,68 @@ cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t str
 // grid.x = 1 KB... (word chunk of 512 residues) fastest, then the output ciphertext: the CTAs resident together work on a
 // handful of neighbouring outputs, so overlapping windows (2x2 stride 1 reads every input 4 times) are served by L2.
 // SMALL: R * max(q) < 2^64, the window sum fits 64 bits.  scale_sh = Shoup companions of `scale` (floor(s * 2^64 / q)).
+// One CTA = EW_CHUNK consecutive residues of one output ciphertext (inside one limb: EW_CHUNK divides n), a thread owns
+// EW_PER groups of two residues, 512 words apart, with all its loads issued before the arithmetic.
+constexpr int EW_PER = 4;
+constexpr int EW_CHUNK = 512 * EW_PER;
+
 template <bool SMALL>
 __global__ void __launch_bounds__(256)
 pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, const int *__restrict__ in_index,
-            int R, const uint64_t *__restrict__ scale, const uint64_t *__restrict__ scale_sh, uint64_t *__restrict__ out) {
-    // two adjacent residues per thread: 128-bit loads and stores
+            int R, const uint64_t *__restrict__ scale, const uint64_t *__restrict__ scale_sh, uint64_t *__restrict__ out,
+            int chunks, int per) {
     const int n = P->n, K = P->K;
     const long ctw = 2L * K * n;
-    const int chunks = (int)(ctw / 512);
     const long o = blockIdx.x / chunks;
-    const long word = ((long)(blockIdx.x % chunks) * 256 + threadIdx.x) * 2;  // within the ciphertext
-    const int j = (int)((word / n) % K);
+    const long word0 = (long)(blockIdx.x % chunks) * (512L * per) + 2 * threadIdx.x;  // within the ciphertext
+    const int j = (int)((word0 / n) % K);
     const Mod mod = P->tab[j].mod;
-    ulonglong2 res;
+    const long lw0 = (long)j * n + word0 % n;
+    ulonglong2 res[EW_PER];
     if (SMALL) {
-        uint64_t s0 = 0, s1 = 0;
+#pragma unroll
+        for (int k = 0; k < EW_PER; k++) res[k] = make_ulonglong2(0, 0);
         for (int r = 0; r < R; r++) {
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word));
-            s0 += v.x;
-            s1 += v.y;
+            const uint64_t *src = in + (long)__ldg(in_index + o * R + r) * ctw + word0;
+#pragma unroll
+            for (int k = 0; k < EW_PER; k++)
+                if (k < per) {
+                    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(src + 512 * k));
+                    res[k].x += v.x;
+                    res[k].y += v.y;
+                }
         }
-        res.x = s0; res.y = s1;  // reduced below (Shoup product and reduce64 accept any 64-bit value)
     } else {
-        U128 s0{0, 0}, s1{0, 0};
-        for (int r = 0; r < R; r++) {
-            const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word));
-            add128_64(s0, v.x);
-            add128_64(s1, v.y);
+#pragma unroll
+        for (int k = 0; k < EW_PER; k++) {
+            if (k >= per) continue;
+            U128 s0{0, 0}, s1{0, 0};
+            for (int r = 0; r < R; r++) {
+                const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(in + (long)__ldg(in_index + o * R + r) * ctw + word0 + 512 * k));
+                add128_64(s0, v.x);
+                add128_64(s1, v.y);
+            }
+            res[k].x = barrett128(s0, mod);
+            res[k].y = barrett128(s1, mod);
         }
-        res.x = barrett128(s0, mod);
-        res.y = barrett128(s1, mod);
     }
-    if (scale) {
-        const long lw = (long)j * n + word % n;
-        const ulonglong2 sc = __ldg(reinterpret_cast<const ulonglong2 *>(scale + lw));
-        const ulonglong2 sh = __ldg(reinterpret_cast<const ulonglong2 *>(scale_sh + lw));
-        res.x = mulshoup_lazy(res.x, sc.x, sh.x, mod.q);
-        res.y = mulshoup_lazy(res.y, sc.y, sh.y, mod.q);
-        res.x = res.x >= mod.q ? res.x - mod.q : res.x;
-        res.y = res.y >= mod.q ? res.y - mod.q : res.y;
-    } else if (SMALL) {
-        res.x = reduce64(res.x, mod);
-        res.y = reduce64(res.y, mod);
+#pragma unroll
+    for (int k = 0; k < EW_PER; k++) {
+        if (k >= per) continue;
+        ulonglong2 v = res[k];
+        if (scale) {
+            const ulonglong2 sc = __ldg(reinterpret_cast<const ulonglong2 *>(scale + lw0 + 512 * k));
+            const ulonglong2 sh = __ldg(reinterpret_cast<const ulonglong2 *>(scale_sh + lw0 + 512 * k));
+            v.x = mulshoup_lazy(v.x, sc.x, sh.x, mod.q);   // reduces any 64-bit sum
+            v.y = mulshoup_lazy(v.y, sc.y, sh.y, mod.q);
+            v.x = v.x >= mod.q ? v.x - mod.q : v.x;
+            v.y = v.y >= mod.q ? v.y - mod.q : v.y;
+        } else if (SMALL) {
+            v.x = reduce64(v.x, mod);
+            v.y = reduce64(v.y, mod);
+        }
+        *reinterpret_cast<ulonglong2 *>(out + o * ctw + word0 + 512 * k) = v;
     }
-    *reinterpret_cast<ulonglong2 *>(out + o * ctw + word) = res;
 }
 
 // =====================================================================================
@@ -354,30 +377,40 @@ pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in,
 __global__ void __launch_bounds__(256)
 bn_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, int per_channel, int channels,
           const uint64_t *__restrict__ mean, const uint64_t *__restrict__ invstd, const uint64_t *__restrict__ invstd_sh,
-          uint64_t *__restrict__ out) {
+          uint64_t *__restrict__ out, int chunks, int per) {
     const int n = P->n, K = P->K;
     const long pw = (long)K * n, ctw = 2 * pw;
-    const int chunks = (int)(ctw / 512);
     const long ct = blockIdx.x / chunks;
-    const long word = ((long)(blockIdx.x % chunks) * 256 + threadIdx.x) * 2;  // two adjacent residues per thread
-    const int poly = (int)(word / pw);
-    const long lw = word - poly * pw;  // j*n + c
-    const int j = (int)(lw / n);
+    const long word0 = (long)(blockIdx.x % chunks) * (512L * per) + 2 * threadIdx.x;  // two adjacent residues per group
+    const int poly = (int)(word0 / pw);
+    const long lw0 = word0 - poly * pw;  // j*n + c
+    const int j = (int)(lw0 / n);
     const int z = (int)((ct / per_channel) % channels);
     const uint64_t q = P->tab[j].mod.q;
-    ulonglong2 x = __ldg(reinterpret_cast<const ulonglong2 *>(in + ct * ctw + word));
-    if (poly == 0) {
-        const ulonglong2 m = __ldg(reinterpret_cast<const ulonglong2 *>(mean + z * pw + lw));
-        x.x = submod(x.x, m.x, q);
-        x.y = submod(x.y, m.y, q);
-    }
-    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(invstd + z * pw + lw));
-    const ulonglong2 vs = __ldg(reinterpret_cast<const ulonglong2 *>(invstd_sh + z * pw + lw));
-    x.x = mulshoup_lazy(x.x, v.x, vs.x, q);
-    x.y = mulshoup_lazy(x.y, v.y, vs.y, q);
-    x.x = x.x >= q ? x.x - q : x.x;
-    x.y = x.y >= q ? x.y - q : x.y;
-    *reinterpret_cast<ulonglong2 *>(out + ct * ctw + word) = x;
+    const uint64_t *src = in + ct * ctw + word0, *mp = mean + z * pw + lw0, *vp = invstd + z * pw + lw0, *sp = invstd_sh + z * pw + lw0;
+    ulonglong2 x[EW_PER], m[EW_PER], v[EW_PER], vs[EW_PER];
+#pragma unroll
+    for (int k = 0; k < EW_PER; k++)
+        if (k < per) {
+            x[k] = __ldg(reinterpret_cast<const ulonglong2 *>(src + 512 * k));
+            v[k] = __ldg(reinterpret_cast<const ulonglong2 *>(vp + 512 * k));
+            vs[k] = __ldg(reinterpret_cast<const ulonglong2 *>(sp + 512 * k));
+            if (poly == 0) m[k] = __ldg(reinterpret_cast<const ulonglong2 *>(mp + 512 * k));
+        }
+#pragma unroll
+    for (int k = 0; k < EW_PER; k++)
+        if (k < per) {
+            ulonglong2 y = x[k];
+            if (poly == 0) {
+                y.x = submod(y.x, m[k].x, q);
+                y.y = submod(y.y, m[k].y, q);
+            }
+            y.x = mulshoup_lazy(y.x, v[k].x, vs[k].x, q);
+            y.y = mulshoup_lazy(y.y, v[k].y, vs[k].y, q);
+            y.x = y.x >= q ? y.x - q : y.x;
+            y.y = y.y >= q ? y.y - q : y.y;
+            *reinterpret_cast<ulonglong2 *>(out + ct * ctw + word0 + 512 * k) = y;
+        }
 }
 
 // =====================================================================================
@@ -777,13 +810,17 @@ cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const Relin
 // =====================================================================================
 // simple launch wrappers
 // =====================================================================================
+// groups of 512 residues a CTA of the element-wise kernels covers: the largest of 4, 2, 1 that keeps a CTA inside one limb
+static int ew_per(int n) { return n % (512 * 4) == 0 ? 4 : (n % (512 * 2) == 0 ? 2 : 1); }
+
 cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout,
                            int R, const uint64_t *scale_ntt, const uint64_t *scale_shoup, bool sum_fits_64, uint64_t *out,
                            cudaStream_t stream) {
     if (Nout <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((long)Nout * (2L * K * n / 512));
-    if (sum_fits_64) pool_kernel<true><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out);
-    else pool_kernel<false><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out);
+    const int per = ew_per(n), chunks = (int)(2L * K * n / (512 * per));
+    const unsigned grid = (unsigned)((long)Nout * chunks);
+    if (sum_fits_64) pool_kernel<true><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out, chunks, per);
+    else pool_kernel<false><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out, chunks, per);
     return cudaGetLastError();
 }
 
@@ -791,8 +828,9 @@ cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, l
                          int channels, const uint64_t *mean_ntt, const uint64_t *invstd_ntt, const uint64_t *invstd_shoup,
                          uint64_t *out, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)(count * (2L * K * n / 512));
-    bn_kernel<<<grid, 256, 0, stream>>>(P, in, per_channel, channels, mean_ntt, invstd_ntt, invstd_shoup, out);
+    const int per = ew_per(n), chunks = (int)(2L * K * n / (512 * per));
+    const unsigned grid = (unsigned)(count * chunks);
+    bn_kernel<<<grid, 256, 0, stream>>>(P, in, per_channel, channels, mean_ntt, invstd_ntt, invstd_shoup, out, chunks, per);
     return cudaGetLastError();
 }
 

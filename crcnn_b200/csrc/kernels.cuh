@@ -14,8 +14,11 @@ cudaError_t launch_ntt(const DeviceParams *P, int logn, uint64_t *data, long npo
 
 // Same for polynomials that sit `slot_count` in a row at offset group_off inside records of group_polys polynomials
 // (e.g. only the Bsk limbs of [count][2][K+S][n]).
+// src (inverse transform only): read the polynomials from src instead of data (out of place, same indexing).
+// addend (inverse only): output polynomial p = transform + polynomial (p / add_group) * add_stride + p % add_group of addend.
 cudaError_t launch_ntt_grouped(const DeviceParams *P, int logn, uint64_t *data, long npolys, int slot_base, int slot_count,
-                               bool inverse, int group_polys, int group_off, cudaStream_t stream);
+                               bool inverse, int group_polys, int group_off, cudaStream_t stream, const uint64_t *src = nullptr,
+                               const uint64_t *addend = nullptr, int add_group = 1, int add_stride = 1);
 
 // ---- plaintext packs: sparse coefficient form -> dense NTT form, one CTA per (plaintext, limb).
 // mode 0: lifted residues (multiplicative use: weights, scale factors)  [evaluator.cpp:1465-1486]

@@ -145,7 +145,8 @@ __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restric
 
 // DST_GLOBAL marks the last pass: the n^-1 scaling and the canonical store happen there.
 template <int LOGN, int B, bool DST_GLOBAL, bool CORR>
-__device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gdst, const NttTable &tb, int g) {
+__device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gdst, const NttTable &tb, int g,
+                                         const uint64_t *__restrict__ gadd = nullptr) {
     constexpr int N = 1 << LOGN;
     const uint64_t q = tb.mod.q;
     const uint64_t c = CORR ? q : 0 - q, c2 = CORR ? 2 * q : 4 * q;
@@ -161,7 +162,9 @@ __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gd
         for (int k = 0; k < (1 << B); k++) {
             if (DST_GLOBAL) {
                 uint64_t v = mulshoup_lazy(x[k], tb.ninv, tb.ninvp, q);  // exact product: [0,2q) for any 64-bit input
-                gdst[base + k * g] = v >= q ? v - q : v;
+                v = v >= q ? v - q : v;
+                if (gadd) v = addmod(v, __ldg(gadd + base + k * g), q);   // fused "+ c_p" of relinearize
+                gdst[base + k * g] = v;
             } else {
                 sm[ntt_pad(base + k * g)] = x[k];
             }
@@ -207,7 +210,8 @@ __device__ __forceinline__ void ntt_forward_in_smem(uint64_t *sm, const NttTable
 // (global, canonical).  Pass order mirrors the forward plan (narrow passes first so the last, HBM-writing pass
 // is strided).
 template <int LOGN, bool CORR>
-__device__ __forceinline__ void ntt_inverse_passes(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb) {
+__device__ __forceinline__ void ntt_inverse_passes(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb,
+                                                   const uint64_t *__restrict__ add) {
     using P = NttPlan<LOGN>;
     int g = 1;
 #pragma unroll
@@ -216,13 +220,14 @@ __device__ __forceinline__ void ntt_inverse_passes(uint64_t *sm, uint64_t *__res
         g <<= P::bits(p);
         __syncthreads();
     }
-    if (P::bits(0) == 4) inv_pass<LOGN, 4, true, CORR>(sm, dst, tb, g); else inv_pass<LOGN, 3, true, CORR>(sm, dst, tb, g);
+    if (P::bits(0) == 4) inv_pass<LOGN, 4, true, CORR>(sm, dst, tb, g, add); else inv_pass<LOGN, 3, true, CORR>(sm, dst, tb, g, add);
 }
 
 template <int LOGN>
-__device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb) {
-    if (ntt_needs_correction(tb.mod.q)) ntt_inverse_passes<LOGN, true>(sm, dst, tb);
-    else ntt_inverse_passes<LOGN, false>(sm, dst, tb);
+__device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb,
+                                                      const uint64_t *__restrict__ add = nullptr) {
+    if (ntt_needs_correction(tb.mod.q)) ntt_inverse_passes<LOGN, true>(sm, dst, tb, add);
+    else ntt_inverse_passes<LOGN, false>(sm, dst, tb, add);
 }
 
 // Coalesced copies between global (unpadded) and shared (padded).
