@@ -14,6 +14,7 @@
 #include "params.h"
 #include "tc_mac.cuh"
 #include "tcn_mac.cuh"
+#include "relin32.cuh"
 
 using namespace crcnn;
 
@@ -21,12 +22,12 @@ namespace {
 
 enum KernelClass {
     KC_NTT_FWD = 0, KC_NTT_INV, KC_MAC, KC_PLAIN_EXPAND, KC_POOL, KC_BN, KC_PLAIN_OP,
-    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_TCN_SPLIT, KC_TCN_MAC, KC_COUNT
+    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_TCN_SPLIT, KC_TCN_MAC, KC_RELIN32, KC_COUNT
 };
 const char *kClassNames[KC_COUNT] = {"ntt_forward", "ntt_inverse", "weighted_sum_mac", "plain_expand_ntt", "pool_sum",
                                      "batch_norm", "plain_op", "behz_lift", "square_tensor", "behz_floor_sk",
                                      "relinearize", "imad_probe", "tc_plane_split", "weighted_sum_tc_i8", "tcn_plane_split",
-                                     "weighted_sum_tcn_i8"};
+                                     "weighted_sum_tcn_i8", "relinearize_u32"};
 
 thread_local std::string g_create_error;
 
@@ -65,6 +66,8 @@ struct crcnn_evk {
     long key_off[MAXK];
     int digits[MAXK];
     int dbc;
+    bool has_r32 = false;  // keys also converted for the word-size auxiliary-prime path (relin32.cuh)
+    Relin32 r32;
 };
 
 struct crcnn_ctx {
@@ -81,6 +84,7 @@ struct crcnn_ctx {
     int tc_min_fanin = 256;
     int tc_min_outputs = 32;
     int tap_mode = 1;                // 1: avg-pool / batch-norm on coefficient-form inputs multiply in the coefficient domain (tapmul_kernel); env CRCNN_TAP
+    int relin_mode = 1;              // 1: relinearize through 30-bit auxiliary primes when exact for the parameters (relin32.cuh); 0: 64-bit transforms
     int tcn_mode = 1;                // 1: weighted sums whose staged weights fit the weight cache run as the NTT-domain limb-split GEMM (tcn_mac.cuh)
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
@@ -605,6 +609,13 @@ int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode) {
     return CRCNN_OK;
 }
 
+int crcnn_ctx_set_relin_mode(crcnn_ctx *ctx, int mode) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(mode == 0 || mode == 1, "relinearize mode must be 0 (64-bit transforms) or 1 (word-size auxiliary primes)");
+    ctx->relin_mode = mode;
+    return CRCNN_OK;
+}
+
 int crcnn_ctx_ntt_table(const crcnn_ctx *ctx_c, int slot, int which, uint64_t *out) {
     crcnn_ctx *ctx = const_cast<crcnn_ctx *>(ctx_c);
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
@@ -848,12 +859,24 @@ int crcnn_evk_upload(crcnn_ctx *ctx, const uint64_t *host, int dbc, const int *s
     const size_t n = ctx->n, rows = (size_t)polys * ctx->K;
     CU(cudaMemcpy2DAsync(k->d, n * 8, host, (n + 1) * 8, n * 8, rows, cudaMemcpyHostToDevice, ctx->stream));
     CU(launch_canonicalize(ctx->dP, k->d, (long)(rows * n), ctx->stream));
+    {
+        uint64_t q[MAXK];
+        for (int i = 0; i < ctx->K; i++) q[i] = ctx->hp.d.tab[i].mod.q;
+        if (relin32_applicable(ctx->n, ctx->K, q, k->digits, dbc, k->r32.c)) {
+            cudaError_t e = relin32_build(ctx->dP, ctx->logn, ctx->K, q, k->d, k->key_off, polys, k->r32, ctx->stream);
+            if (e != cudaSuccess) { relin32_free(k->r32); dev_free(ctx, k->d); delete k; return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+            k->has_r32 = true;
+        }
+    }
     *out = k;
     return CRCNN_OK;
 }
 int crcnn_evk_free(crcnn_ctx *ctx, crcnn_evk *k) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     if (!k) return CRCNN_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    relin32_free(k->r32);
     dev_free(ctx, k->d);
     delete k;
     return CRCNN_OK;
@@ -1113,12 +1136,33 @@ int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_t
     crcnn_tensor *o = nullptr;
     rc = new_tensor(ctx, in3->count, 2, 0, &o);
     if (rc) return rc;
+    const size_t pw = poly_words(ctx);
+    if (evk->has_r32 && ctx->relin_mode == 1) {
+        // word-size auxiliary-prime path: D*S3 forward + 2K*S3 inverse 32-bit transforms per ciphertext
+        const Relin32Consts &c = evk->r32.c;
+        const size_t per_ct = relin32_scratch_bytes(ctx->n, ctx->K, c);
+        const long step = std::max<long>(1, std::min<long>(std::min<long>(in3->count, 200000), (long)((2ull << 30) / per_ct)));
+        void *scratch = nullptr;
+        rc = dev_alloc(ctx, (size_t)step * per_ct, &scratch);
+        if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+        for (long c0 = 0; c0 < in3->count && !rc; c0 += step) {
+            const long cnt = std::min<long>(step, in3->count - c0);
+            // work: bytes = in (3 polys) + out (2 polys) per ciphertext; operations = 32-bit butterflies
+            ProfScope ps(ctx, KC_RELIN32, lp_bytes(ctx, (double)cnt * 5 * ctx->K),
+                         lp_bfly(ctx, (double)cnt * (c.D + 2 * ctx->K) * c.S3));
+            cudaError_t e = relin32_run(ctx->dP, ctx->logn, ctx->K, evk->r32, in3->d + c0 * 3 * pw, o->d + c0 * 2 * pw, cnt, scratch, ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
+        }
+        dev_free(ctx, scratch);
+        if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+        *out2 = o;
+        return CRCNN_OK;
+    }
     RelinArgs a{};
     a.evk = evk->d; a.dbc = evk->dbc;
     for (int i = 0; i < MAXK; i++) { a.key_off[i] = evk->key_off[i]; a.digits[i] = evk->digits[i]; }
     // scratch per ciphertext: scaled c2 (K polys) + digit NTTs (D*K polys) + accumulators (2K polys);
     // chunked so it stays near 2 GB
-    const size_t pw = poly_words(ctx);
     const size_t per_ct = (size_t)(1 + total_digits + 2) * pw * 8;
     const long step = std::max<long>(1, std::min<long>(in3->count, (long)((2ull << 30) / per_ct)));
     uint64_t *scratch = nullptr;

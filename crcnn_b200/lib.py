@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcrcnn_b200.so")
+# CRCNN_B200_LIB selects another build of the same library (kernel A/B runs of tools/ntt_ab.py)
+LIB_PATH = os.environ.get("CRCNN_B200_LIB") or os.path.join(_HERE, "libcrcnn_b200.so")
 
 _u64p = C.POINTER(C.c_uint64)
 _u32p = C.POINTER(C.c_uint32)
@@ -29,6 +30,7 @@ SYMBOLS = [
     ("crcnn_ctx_set_weight_cache_bytes", _I, [_vp, C.c_size_t]),
     ("crcnn_ctx_set_tensor_core_mode", _I, [_vp, C.c_int, C.c_int, C.c_size_t]),
     ("crcnn_ctx_set_limb_split_mode", _I, [_vp, C.c_int]),
+    ("crcnn_ctx_set_relin_mode", _I, [_vp, C.c_int]),
     ("crcnn_ctx_ntt_table", _I, [_vp, _I, _I, _u64p]),
     ("crcnn_ctx_bsk_count", _I, [_vp]),
     ("crcnn_tensor_upload", _I, [_vp, _vp, _L, _I, _vpp]),
@@ -171,6 +173,9 @@ class Engine:
 
     def set_limb_split_mode(self, mode):
         self._chk(self.lib.crcnn_ctx_set_limb_split_mode(self.h, int(mode)))
+
+    def set_relin_mode(self, mode):
+        self._chk(self.lib.crcnn_ctx_set_relin_mode(self.h, int(mode)))
 
     def ntt_table(self, slot, which):
         out = np.zeros(self.n, dtype=np.uint64)

@@ -79,6 +79,12 @@ int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size
  * kernel shapes (outputs / columns on the UMMA rows) instead of choosing by layer shape.  Env CRCNN_TCN sets the
  * initial mode (default 1).  The scratch budget is the one of crcnn_ctx_set_tensor_core_mode. */
 int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode);
+/* relinearize (Evaluator::relinearize, SEAL/seal/evaluator.cpp:886-1069): mode 1 (default) evaluates the digit (x) key
+ * product sums over three or four NTT-friendly primes below 2^30 and reconstructs each coefficient exactly before reducing it
+ * mod q_j (crcnn_b200/csrc/relin32.cuh) -- the same canonical residues from 32-bit transforms; it applies when
+ * 2 * D * n * (2^dbc - 1) * max q_j is below the product of those primes (every SEAL default with dbc <= 16), otherwise, or
+ * with mode 0, the 64-bit transforms of the reference's own procedure run. */
+int crcnn_ctx_set_relin_mode(crcnn_ctx *ctx, int mode);
 /* Derived constants, for cross-checking against SEAL: which = 0 root_powers, 1 scaled_root_powers,
  * 2 inv_root_powers_div_two, 3 scaled_inv_root_powers_div_two (SEAL/seal/util/smallntt.cpp:37-92);
  * slot in [0,K) = coefficient primes, [K,K+S) = Bsk primes.  out has n words. */

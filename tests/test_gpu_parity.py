@@ -121,6 +121,31 @@ def test_square_and_relinearize(env):
     assert np.array_equal(eng.download(tn), x), "square must not change the value of its input"
 
 
+def test_relinearize_both_paths(env):
+    """Word-size auxiliary-prime path (default) and the 64-bit path of the reference's own procedure give the oracle's
+    bytes, also for extreme operands (keys and c2 at q-1 / 0: largest and smallest integer coefficient sums)."""
+    n, primes, t, eng, orc, rng = env
+    K = len(primes)
+    evk, sizes, dbc = random_evk(rng, n, primes)
+    x3 = random_cts(rng, n, primes, 5, size=3)
+    top = np.zeros_like(x3[:1])
+    for j, q in enumerate(primes):
+        top[:, :, j, :n] = q - 1
+    x3 = np.concatenate([x3, top, np.zeros_like(top)])
+    evk_max = np.zeros_like(evk).reshape(-1, K, n + 1)
+    for j, q in enumerate(primes):
+        evk_max[:, j, :n] = q - 1
+    for keys in (evk, evk_max.ravel()):
+        want = orc.relinearize(x3, keys, sizes, dbc)
+        k = eng.evk_upload(keys, sizes, dbc)
+        try:
+            for mode in (1, 0):
+                eng.set_relin_mode(mode)
+                assert np.array_equal(eng.download(eng.relinearize(eng.upload(x3, size=3), k)), want), mode
+        finally:
+            eng.set_relin_mode(1)
+
+
 def _layer_params(orc, rng, count):
     vals = rng.uniform(-1, 1, size=count).astype(np.float32)
     return vals, orc.encode_many(vals)
