@@ -3,6 +3,7 @@
 #include "kernels.cuh"
 #include "modarith.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace crcnn {
@@ -272,13 +273,19 @@ r32_scale_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__rest
     const int n = P->n, K = P->K;
     const long pw = (long)K * n;
     const long ct = blockIdx.x;
-    const long lw = (long)blockIdx.y * 256 + threadIdx.x;
+    const long lw = ((long)blockIdx.y * 256 + threadIdx.x) * 2;  // two coefficients per thread
     const int i = (int)(lw / n), e = (int)(lw - (long)i * n);
-    const uint64_t v = mulmod(__ldg(in3 + (ct * 3 + 2) * pw + lw), P->inv_qhat[i], P->tab[i].mod);
+    const ulonglong2 c2 = __ldg(reinterpret_cast<const ulonglong2 *>(in3 + (ct * 3 + 2) * pw + lw));
+    const Mod mod = P->tab[i].mod;
+    const uint64_t f = P->inv_qhat[i];
+    const uint64_t v0 = mulmod(c2.x, f, mod), v1 = mulmod(c2.y, f, mod);
     const int dbc = cp->dbc, D = cp->D;
     const uint32_t mask = (1u << dbc) - 1;
-    for (int d = cp->dfirst[i]; d < D && cp->dprime[d] == i; d++)
-        planes[(ct * D + d) * n + e] = (uint16_t)((uint32_t)(v >> cp->dshift[d]) & mask);
+    for (int d = cp->dfirst[i]; d < D && cp->dprime[d] == i; d++) {
+        const int sh = cp->dshift[d];
+        const uint32_t lo = (uint32_t)(v0 >> sh) & mask, hi = (uint32_t)(v1 >> sh) & mask;
+        *reinterpret_cast<uint32_t *>(planes + (ct * D + d) * n + e) = lo | (hi << 16);
+    }
 }
 
 // one CTA = (ciphertext, digit, auxiliary prime): digit polynomial -> NTT mod p_s, canonical
@@ -366,8 +373,12 @@ r32_mac_kernel(const uint32_t *__restrict__ dig, const uint32_t *__restrict__ ke
     const uint64_t mu = cp->mu[s];
     const int D = cp->D, S3 = cp->S3;
     {
+        // rows of EW words (16-byte vectors, several in flight per thread)
         const uint32_t *kg = keys + (long)s * D * OC * n + blockIdx.x * EW;
-        for (int i = threadIdx.x; i < D * OC * EW; i += 256) ksm[i] = __ldg(kg + (long)(i / EW) * n + (i % EW));
+        constexpr int V = EW / 4;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < D * OC * V; i += 256)
+            sm32v[i] = __ldg(reinterpret_cast<const uint4 *>(kg + (long)(i / V) * n) + (i % V));
     }
     __syncthreads();
     const long dstride = (long)S3 * n;
@@ -410,6 +421,96 @@ r32_mac_kernel(const uint32_t *__restrict__ dig, const uint32_t *__restrict__ ke
 #pragma unroll
                 for (int o = 0; o < OC; o++) ap[(long)o * S3 * n] = red64_32(a[t][o], mu, p);
             }
+    }
+}
+
+// The same sum for the shapes SEAL's default parameters give (D = 4K digits, OC = 2K outputs): the kernel above is bound by
+// the latency of its digit loads (ncu: long_scoreboard 7.9 of 11 stall cycles per issue, 1.8 TB/s).  Here every thread keeps
+// the keys of its coefficient and its two outputs in registers (2*D words, loaded once per CTA) and the digit transforms
+// stream through a 6-stage cp.async ring in shared memory, two ciphertexts per stage, so dozens of KB are in flight per SM
+// whatever the compute phase is doing.  32*OC threads = 64 coefficients x OC/2 output pairs.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+template <int D, int OC>
+__global__ void __launch_bounds__(32 * OC)
+r32_mac_reg_kernel(const uint32_t *__restrict__ dig, const uint32_t *__restrict__ keys, const Relin32Consts *__restrict__ cp, int n,
+                   long count, int cpb, uint32_t *__restrict__ acc) {
+    constexpr int EW = 64, CPS = 2, NS = 6, SW = CPS * D * EW;
+    extern __shared__ uint4 sm32v[];
+    uint32_t *sm = reinterpret_cast<uint32_t *>(sm32v);  // [NS][CPS][D][EW]
+    const int el = threadIdx.x % EW, og = threadIdx.x / EW;
+    const int e0 = blockIdx.x * EW;
+    const int s = blockIdx.y, S3 = cp->S3;
+    const long ctb = (long)blockIdx.z * cpb;
+    const long cte = min(ctb + cpb, count);
+    const int nst = (int)((cte - ctb + CPS - 1) / CPS);
+    const uint32_t p = cp->p[s];
+    const uint64_t mu = cp->mu[s];
+    uint32_t k0[D], k1[D];
+    {
+        const uint32_t *kg = keys + ((long)s * D * OC + og * 2) * n + e0 + el;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            k0[d] = __ldg(kg + (long)d * OC * n);
+            k1[d] = __ldg(kg + (long)d * OC * n + n);
+        }
+    }
+    // this thread's 16-byte chunk of every ciphertext tile: digit cd, words cpart*4 .. +3 (16*D chunks = 32*OC threads)
+    const int cd = threadIdx.x / 16, cpart = threadIdx.x % 16;
+    auto issue = [&](int st) {
+        if (st < nst) {
+            uint32_t *dst = sm + (st % NS) * SW + cd * EW + cpart * 4;
+#pragma unroll
+            for (int u = 0; u < CPS; u++) {
+                const long ct = min(ctb + (long)st * CPS + u, count - 1);  // an odd tail repeats the last ciphertext
+                cp_async16(dst + u * D * EW, dig + ((ct * D + cd) * S3 + s) * n + e0 + cpart * 4);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int st = 0; st < NS - 1; st++) issue(st);
+    for (int st = 0; st < nst; st++) {
+        cp_async_wait<NS - 2>();
+        __syncthreads();
+        issue(st + NS - 1);
+        const uint32_t *tile = sm + (st % NS) * SW + el;
+        uint64_t a[CPS][2];
+#pragma unroll
+        for (int u = 0; u < CPS; u++) {
+            a[u][0] = 0;
+            a[u][1] = 0;
+        }
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+#pragma unroll
+            for (int u = 0; u < CPS; u++) {
+                const uint32_t x = tile[(u * D + d) * EW];
+                madwide(a[u][0], x, k0[d]);
+                madwide(a[u][1], x, k1[d]);
+            }
+            if (D > 16 && d == 15) {  // 16 products of canonical residues below 2^30 fit 64 bits
+#pragma unroll
+                for (int u = 0; u < CPS; u++) {
+                    a[u][0] = red64_32(a[u][0], mu, p);
+                    a[u][1] = red64_32(a[u][1], mu, p);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < CPS; u++) {
+            const long ct = ctb + (long)st * CPS + u;
+            if (ct < cte) {
+                uint32_t *ap = acc + ((ct * OC + og * 2) * S3 + s) * n + e0 + el;
+                ap[0] = red64_32(a[u][0], mu, p);
+                ap[(long)S3 * n] = red64_32(a[u][1], mu, p);
+            }
+        }
     }
 }
 
@@ -458,20 +559,25 @@ r32_crt_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__restri
             a[s] = 0;
         }
     }
-    U128 z{a[0], 0};
+    // W mod q_j = a_0 + sum_(s>0) a_s * (p_0...p_(s-1) mod q_j): Shoup products (each in [0,2q)), one lazy sum, three
+    // conditional subtractions; negative W (mixed-radix digits above those of (P-1)/2) subtracts P mod q_j
+    const uint64_t q = P->tab[j].mod.q;
+    uint64_t v = a[0];
     bool neg = false, decided = false;
 #pragma unroll
     for (int s = R32_MAXP - 1; s >= 0; s--) {
         if (s < S3) {
-            if (s > 0) mac128(z, (uint64_t)a[s], cp->cmodq[j][s]);
+            if (s > 0) v += mulshoup_lazy((uint64_t)a[s], cp->cmodq[j][s], cp->cmodq_sh[j][s], q);
             if (!decided && a[s] != cp->half[s]) { neg = a[s] > cp->half[s]; decided = true; }
         }
     }
-    const Mod mod = P->tab[j].mod;
-    uint64_t v = barrett128(z, mod);
-    if (neg) v = submod(v, cp->Pmodq[j], mod.q);
+    // v < 2^30 + 2(S3-1)q <= 7q
+    v = v >= 4 * q ? v - 4 * q : v;
+    v = v >= 2 * q ? v - 2 * q : v;
+    v = v >= q ? v - q : v;
+    if (neg) v = submod(v, cp->Pmodq[j], q);
     const long w = (long)j * n + e;
-    out[(ct * 2 + pi) * (long)K * n + w] = addmod(__ldg(in3 + (ct * 3 + pi) * (long)K * n + w), v, mod.q);
+    out[(ct * 2 + pi) * (long)K * n + w] = addmod(__ldg(in3 + (ct * 3 + pi) * (long)K * n + w), v, q);
 }
 
 template <int LOGN>
@@ -501,6 +607,20 @@ cudaError_t launch_mac(const uint32_t *dig, const Relin32 &r, int n, long count,
     return cudaGetLastError();
 }
 
+template <int D, int OC>
+cudaError_t launch_mac_reg(const uint32_t *dig, const Relin32 &r, int n, long count, int cpb, unsigned gz, uint32_t *acc, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)6 * 2 * D * 64 * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(r32_mac_reg_kernel<D, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(r32_mac_reg_kernel<D, OC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    r32_mac_reg_kernel<D, OC><<<dim3((unsigned)(n / 64), (unsigned)r.c.S3, gz), 32 * OC, smem, stream>>>(dig, r.keys, r.dc, n, count, cpb, acc);
+    return cudaGetLastError();
+}
+
 template <int LOGN>
 cudaError_t run_t(const DeviceParams *dP, int K, const Relin32 &r, const uint64_t *in3, uint64_t *out, long count, void *scratch,
                   cudaStream_t stream) {
@@ -512,13 +632,19 @@ cudaError_t run_t(const DeviceParams *dP, int K, const Relin32 &r, const uint64_
     uint32_t *dig = (uint32_t *)scratch;
     uint32_t *acc = dig + (size_t)count * c.D * c.S3 * N;
     uint16_t *planes = (uint16_t *)(acc + (size_t)count * 2 * K * c.S3 * N);
-    r32_scale_kernel<<<dim3((unsigned)count, (unsigned)((long)K * N / 256)), 256, 0, stream>>>(dP, r.dc, in3, planes);
+    r32_scale_kernel<<<dim3((unsigned)count, (unsigned)((long)K * N / 512)), 256, 0, stream>>>(dP, r.dc, in3, planes);
     r32_digits_kernel<LOGN><<<(unsigned)(count * c.D * c.S3), Pl::THREADS, smem, stream>>>(planes, r.dc, dig);
     {
-        const int cpb = 64;
+        const int cpb = 128;
         const unsigned gz = (unsigned)((count + cpb - 1) / cpb);
         const size_t ksmem = (size_t)c.D * 2 * K * 4;  // bytes per staged coefficient
         cudaError_t e = cudaSuccess;
+        const bool generic = std::getenv("CRCNN_R32_GENERIC_MAC") != nullptr;  // A/B switch for tools/ntt_ab.py
+        if (!generic && c.D == 4 * K && K == 1) e = launch_mac_reg<4, 2>(dig, r, N, count, cpb, gz, acc, stream);
+        else if (!generic && c.D == 4 * K && K == 2) e = launch_mac_reg<8, 4>(dig, r, N, count, cpb, gz, acc, stream);
+        else if (!generic && c.D == 4 * K && K == 4) e = launch_mac_reg<16, 8>(dig, r, N, count, cpb, gz, acc, stream);
+        else if (!generic && c.D == 4 * K && K == 8) e = launch_mac_reg<32, 16>(dig, r, N, count, cpb, gz, acc, stream);
+        else
         switch (2 * K) {
             case 2: e = launch_mac<4, 2, 64>(dig, r, N, count, cpb, gz, ksmem, acc, stream); break;
             case 4: e = launch_mac<4, 4, 64>(dig, r, N, count, cpb, gz, ksmem, acc, stream); break;
@@ -582,6 +708,7 @@ bool relin32_applicable(int n, int K, const uint64_t *q, const int *digits, int 
         unsigned __int128 prod = 1;
         for (int s = 0; s < c.S3; s++) {
             c.cmodq[j][s] = (uint64_t)prod;
+            c.cmodq_sh[j][s] = (uint64_t)((prod << 64) / q[j]);
             prod = prod * kAuxPrimes[s] % q[j];
         }
         c.Pmodq[j] = (uint64_t)prod;

@@ -39,6 +39,7 @@ struct Relin32Consts {  // passed to the kernels by value
     uint32_t ginvp[R32_MAXP][R32_MAXP];
     uint32_t half[R32_MAXP];                    // (p_s - 1) / 2: mixed-radix digits of (P - 1) / 2
     uint64_t cmodq[MAXK][R32_MAXP];             // prod_(k<s) p_k mod q_j
+    uint64_t cmodq_sh[MAXK][R32_MAXP];          // floor(cmodq * 2^64 / q_j)
     uint64_t Pmodq[MAXK];                       // P = prod p_s mod q_j
     unsigned char dprime[32], dshift[32];       // digit d = (scaled c2 of prime dprime[d] >> dshift[d]) & (2^dbc - 1)
     int dfirst[MAXK];                           // first digit of prime i
