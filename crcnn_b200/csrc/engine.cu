@@ -542,6 +542,24 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
         }
         e = up(fw, &hp.d.tab[s].w);
         if (e == cudaSuccess) e = up(bw, &hp.d.tab[s].iw);
+        // transposed pairs of the contiguous 4-stage pass: forward stage s of group G uses the 2^s pairs from ((n/16 + G) << s),
+        // inverse stage s the 2^(3-s) pairs from (n/2 >> s) + (G << (3-s))
+        const int NG = n >> 4;
+        std::vector<uint64_t> fl(2 * (size_t)16 * NG, 0), bl(2 * (size_t)16 * NG, 0);
+        for (int G = 0; G < NG; G++)
+            for (int st = 0; st < 4; st++) {
+                for (int lb = 0; lb < (1 << st); lb++) {
+                    const size_t at = 2 * ((size_t)((1 << st) - 1 + lb) * NG + G), from = 2 * ((((size_t)NG + G) << st) + lb);
+                    fl[at] = fw[from]; fl[at + 1] = fw[from + 1];
+                }
+                for (int lb = 0; lb < (1 << (3 - st)); lb++) {
+                    const size_t at = 2 * ((size_t)(16 - (16 >> st) + lb) * NG + G);
+                    const size_t from = 2 * ((size_t)((n >> 1) >> st) + ((size_t)G << (3 - st)) + lb);
+                    bl[at] = bw[from]; bl[at + 1] = bw[from + 1];
+                }
+            }
+        if (e == cudaSuccess) e = up(fl, &hp.d.tab[s].wl);
+        if (e == cudaSuccess) e = up(bl, &hp.d.tab[s].iwl);
         hp.d.tab[s].tf = nullptr;
         if (e == cudaSuccess && s < K) e = up(hp.tf[s], &hp.d.tab[s].tf);
     }

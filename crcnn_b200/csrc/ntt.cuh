@@ -17,8 +17,11 @@
 //
 // Schedule: log2(n) stages are grouped into passes of 3 or 4 stages done in registers
 // (8 or 16 residues per thread and group); between passes the polynomial lives in shared memory
-// with one pad word every 16 residues, which makes the strided passes (gaps >= 32 or 16) and the
-// final contiguous pass bank-conflict free.  The first forward pass reads HBM directly (coalesced),
+// with two pad words every 16 residues, which makes the strided passes (gaps >= 32 or 16) and the
+// contiguous pass bank-conflict free and keeps every group of the contiguous pass 16-byte aligned, so it moves
+// with 128-bit shared-memory accesses.  The contiguous pass gives every thread its own 15 twiddle pairs; read from
+// the generic table the lanes of a warp touch 32 cache lines per load (ncu: L1 data pipe 62 % busy, two thirds of
+// it these loads), so its pairs are also stored transposed (NttTable::wl / iwl: 15 rows, group index fastest).  The first forward pass reads HBM directly (coalesced),
 // the last inverse pass writes HBM directly; the contiguous ends are staged through shared memory.
 #pragma once
 #include "modarith.cuh"
@@ -26,13 +29,13 @@
 
 namespace crcnn {
 
-__device__ __forceinline__ int ntt_pad(int i) { return i + (i >> 4); }
+__device__ __forceinline__ int ntt_pad(int i) { return i + ((i >> 4) << 1); }
 
 template <int LOGN>
 struct NttPlan {
     static constexpr int N = 1 << LOGN;
     static constexpr int THREADS = N / 32;  // 2 groups of 16 (4 of 8) residues per thread and pass
-    static constexpr int SMEM_WORDS = N + N / 16;
+    static constexpr int SMEM_WORDS = N + N / 8;
     // CTAs per SM the shared-memory footprint allows (227 KB usable), capped so 85 registers per thread suffice
     static constexpr int FIT = (227 * 1024) / (SMEM_WORDS * 8);
     static constexpr int MIN_CTAS = FIT > 768 / THREADS ? 768 / THREADS : (FIT < 1 ? 1 : FIT);
@@ -143,6 +146,72 @@ __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restric
     }
 }
 
+// The contiguous 4-stage pass of the forward transform (g = 1): 16 consecutive residues per group, twiddles from the
+// transposed table wl[row][G], row = 2^s - 1 + lb.
+template <int LOGN, bool CORR>
+__device__ __forceinline__ void fwd_last_pass(uint64_t *sm, const NttTable &tb) {
+    constexpr int N = 1 << LOGN, NG = N >> 4;
+    const uint64_t q = CORR ? tb.mod.q : 0 - tb.mod.q, twoq = CORR ? 2 * tb.mod.q : 4 * tb.mod.q;
+    const ulonglong2 *wl = reinterpret_cast<const ulonglong2 *>(tb.wl);
+    for (int G = threadIdx.x; G < NG; G += blockDim.x) {
+        ulonglong2 *row = reinterpret_cast<ulonglong2 *>(sm + 18 * G);
+        uint64_t x[16];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const ulonglong2 v = row[m];
+            x[2 * m] = v.x;
+            x[2 * m + 1] = v.y;
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+#pragma unroll
+            for (int lb = 0; lb < (1 << s); lb++) {
+                const ulonglong2 W = __ldg(wl + ((1 << s) - 1 + lb) * NG + G);
+#pragma unroll
+                for (int a = 0; a < (1 << (3 - s)); a++) {
+                    const int ia = (lb << (4 - s)) + a;
+                    ct_butterfly<CORR>(x[ia], x[ia + (1 << (3 - s))], W.x, W.y, q, twoq);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) row[m] = make_ulonglong2(x[2 * m], x[2 * m + 1]);
+    }
+}
+
+// The contiguous 4-stage pass of the inverse transform (the first one): twiddles from iwl[row][G], row = 16 - (16 >> s) + lb.
+template <int LOGN, bool CORR>
+__device__ __forceinline__ void inv_first_pass(uint64_t *sm, const NttTable &tb) {
+    constexpr int N = 1 << LOGN, NG = N >> 4;
+    const uint64_t q = tb.mod.q;
+    const uint64_t c = CORR ? q : 0 - q, c2 = CORR ? 2 * q : 4 * q;
+    const ulonglong2 *iwl = reinterpret_cast<const ulonglong2 *>(tb.iwl);
+    for (int G = threadIdx.x; G < NG; G += blockDim.x) {
+        ulonglong2 *row = reinterpret_cast<ulonglong2 *>(sm + 18 * G);
+        uint64_t x[16];
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            const ulonglong2 v = row[m];
+            x[2 * m] = v.x;
+            x[2 * m + 1] = v.y;
+        }
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+#pragma unroll
+            for (int lb = 0; lb < (1 << (3 - s)); lb++) {
+                const ulonglong2 W = __ldg(iwl + (16 - (16 >> s) + lb) * NG + G);
+#pragma unroll
+                for (int a = 0; a < (1 << s); a++) {
+                    const int ia = (lb << (s + 1)) + a;
+                    gs_butterfly<CORR>(x[ia], x[ia + (1 << s)], W.x, W.y, c, c2);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 8; m++) row[m] = make_ulonglong2(x[2 * m], x[2 * m + 1]);
+    }
+}
+
 // DST_GLOBAL marks the last pass: the n^-1 scaling and the canonical store happen there.
 template <int LOGN, int B, bool DST_GLOBAL, bool CORR>
 __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gdst, const NttTable &tb, int g,
@@ -181,7 +250,9 @@ __device__ __forceinline__ void ntt_forward_passes(uint64_t *sm, const uint64_t 
 #pragma unroll
     for (int p = FIRST_PASS; p < P::PASSES; p++) {
         g >>= P::bits(p);
-        if (p == 0 && src != nullptr) {
+        if (p == P::PASSES - 1 && P::bits(p) == 4 && !(p == 0 && src != nullptr)) {
+            fwd_last_pass<LOGN, CORR>(sm, tb);
+        } else if (p == 0 && src != nullptr) {
             if (P::bits(p) == 4) fwd_pass<LOGN, 4, true, CORR>(sm, src, tb, m0, g); else fwd_pass<LOGN, 3, true, CORR>(sm, src, tb, m0, g);
         } else {
             if (P::bits(p) == 4) fwd_pass<LOGN, 4, false, CORR>(sm, nullptr, tb, m0, g); else fwd_pass<LOGN, 3, false, CORR>(sm, nullptr, tb, m0, g);
@@ -216,7 +287,8 @@ __device__ __forceinline__ void ntt_inverse_passes(uint64_t *sm, uint64_t *__res
     int g = 1;
 #pragma unroll
     for (int p = P::PASSES - 1; p >= 1; p--) {
-        if (P::bits(p) == 4) inv_pass<LOGN, 4, false, CORR>(sm, nullptr, tb, g); else inv_pass<LOGN, 3, false, CORR>(sm, nullptr, tb, g);
+        if (p == P::PASSES - 1 && P::bits(p) == 4) inv_first_pass<LOGN, CORR>(sm, tb);
+        else if (P::bits(p) == 4) inv_pass<LOGN, 4, false, CORR>(sm, nullptr, tb, g); else inv_pass<LOGN, 3, false, CORR>(sm, nullptr, tb, g);
         g <<= P::bits(p);
         __syncthreads();
     }

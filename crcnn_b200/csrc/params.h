@@ -30,6 +30,8 @@ struct NttTable {
     const uint64_t *iw;   // interleaved inverse pairs psi^-bitrev(i) (NOT pre-halved: the kernels scale by n^-1 once at the end)
     uint64_t ninv, ninvp; // n^-1 mod q and floor(n^-1 * 2^64 / q)
     const uint64_t *tf;   // top-block factors for the sparse-input forward transform (see ntt.cuh), 2^skip entries
+    const uint64_t *wl;   // pairs of the contiguous 4-stage forward pass, transposed: [15 rows][n/16 groups] (ntt.cuh: fwd_last_pass)
+    const uint64_t *iwl;  // same for the first (contiguous) inverse pass
 };
 
 // Forward-NTT stages that can be skipped for FractionalEncoder-shaped plaintexts (support in

@@ -533,51 +533,80 @@ r32_intt_kernel(const Relin32Consts *__restrict__ cp, uint32_t *__restrict__ acc
     store32_canonical<LOGN, 2>(sm32, poly, p);
 }
 
-// Garner mixed-radix digits of W mod P, sign by comparison with (P-1)/2, reduction mod q_j, "+ c_p"
-__global__ void __launch_bounds__(256)
-r32_crt_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__restrict__ cp, const uint32_t *__restrict__ acc,
-               const uint64_t *__restrict__ in3, uint64_t *__restrict__ out) {
-    const int n = P->n, K = P->K, S3 = cp->S3;
-    const int e = blockIdx.y * 256 + threadIdx.x;
-    const int o = (int)(blockIdx.x % (unsigned)(2 * K));
-    const long ct = blockIdx.x / (unsigned)(2 * K);
-    const int pi = o / K, j = o % K;
-    const uint32_t *r = acc + ((ct * 2 * K + o) * S3) * n + e;
-    uint32_t a[R32_MAXP];
+// Garner mixed-radix digits of W mod P, sign by comparison with (P-1)/2, reduction mod q_j
+struct CrtConsts {
+    uint32_t p[R32_MAXP], half[R32_MAXP], ginv[R32_MAXP][R32_MAXP], ginvp[R32_MAXP][R32_MAXP];
+    uint64_t c[R32_MAXP], csh[R32_MAXP], Pmodq, q;
+};
+template <int S3>
+__device__ __forceinline__ uint64_t crt_one(const uint32_t (&r)[R32_MAXP], const CrtConsts &k) {
+    uint32_t a[S3];
 #pragma unroll
-    for (int s = 0; s < R32_MAXP; s++) {
-        if (s < S3) {
-            const uint32_t ps = cp->p[s];
-            uint32_t t = __ldg(r + (long)s * n);
+    for (int s = 0; s < S3; s++) {
+        uint32_t t = r[s];
 #pragma unroll
-            for (int k = 0; k < s; k++) {
-                const uint32_t ak = csub(a[k], ps);  // a_k < p_k < 2 p_s
-                t = csub(shoup32(t + ps - ak, cp->ginv[s][k], cp->ginvp[s][k], ps), ps);
-            }
-            a[s] = t;
-        } else {
-            a[s] = 0;
+        for (int i = 0; i < s; i++) {
+            const uint32_t ai = csub(a[i], k.p[s]);  // a_i < p_i < 2 p_s
+            t = csub(shoup32(t + k.p[s] - ai, k.ginv[s][i], k.ginvp[s][i], k.p[s]), k.p[s]);
         }
+        a[s] = t;
     }
     // W mod q_j = a_0 + sum_(s>0) a_s * (p_0...p_(s-1) mod q_j): Shoup products (each in [0,2q)), one lazy sum, three
     // conditional subtractions; negative W (mixed-radix digits above those of (P-1)/2) subtracts P mod q_j
-    const uint64_t q = P->tab[j].mod.q;
     uint64_t v = a[0];
     bool neg = false, decided = false;
 #pragma unroll
-    for (int s = R32_MAXP - 1; s >= 0; s--) {
-        if (s < S3) {
-            if (s > 0) v += mulshoup_lazy((uint64_t)a[s], cp->cmodq[j][s], cp->cmodq_sh[j][s], q);
-            if (!decided && a[s] != cp->half[s]) { neg = a[s] > cp->half[s]; decided = true; }
-        }
+    for (int s = S3 - 1; s >= 0; s--) {
+        if (s > 0) v += mulshoup_lazy((uint64_t)a[s], k.c[s], k.csh[s], k.q);
+        if (!decided && a[s] != k.half[s]) { neg = a[s] > k.half[s]; decided = true; }
     }
     // v < 2^30 + 2(S3-1)q <= 7q
-    v = v >= 4 * q ? v - 4 * q : v;
-    v = v >= 2 * q ? v - 2 * q : v;
-    v = v >= q ? v - q : v;
-    if (neg) v = submod(v, cp->Pmodq[j], q);
+    v = v >= 4 * k.q ? v - 4 * k.q : v;
+    v = v >= 2 * k.q ? v - 2 * k.q : v;
+    v = v >= k.q ? v - k.q : v;
+    if (neg) v = submod(v, k.Pmodq, k.q);
+    return v;
+}
+
+// one CTA = (ciphertext, output o = p*K + j, 512 coefficients), two coefficients per thread: out = c_p + (W mod q_j)
+template <int S3>
+__global__ void __launch_bounds__(256)
+r32_crt_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__restrict__ cp, const uint32_t *__restrict__ acc,
+               const uint64_t *__restrict__ in3, uint64_t *__restrict__ out) {
+    const int n = P->n, K = P->K;
+    const int e = (blockIdx.y * 256 + threadIdx.x) * 2;
+    const int o = (int)(blockIdx.x % (unsigned)(2 * K));
+    const long ct = blockIdx.x / (unsigned)(2 * K);
+    const int pi = o / K, j = o % K;
+    CrtConsts k;
+#pragma unroll
+    for (int s = 0; s < S3; s++) {
+        k.p[s] = cp->p[s];
+        k.half[s] = cp->half[s];
+        k.c[s] = cp->cmodq[j][s];
+        k.csh[s] = cp->cmodq_sh[j][s];
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            k.ginv[s][i] = cp->ginv[s][i];
+            k.ginvp[s][i] = cp->ginvp[s][i];
+        }
+    }
+    k.Pmodq = cp->Pmodq[j];
+    k.q = P->tab[j].mod.q;
+    const uint32_t *r = acc + ((ct * 2 * K + o) * S3) * n + e;
+    uint32_t r0[R32_MAXP], r1[R32_MAXP];
+#pragma unroll
+    for (int s = 0; s < S3; s++) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2 *>(r + (long)s * n));
+        r0[s] = v.x;
+        r1[s] = v.y;
+    }
     const long w = (long)j * n + e;
-    out[(ct * 2 + pi) * (long)K * n + w] = addmod(__ldg(in3 + (ct * 3 + pi) * (long)K * n + w), v, q);
+    const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2 *>(in3 + (ct * 3 + pi) * (long)K * n + w));
+    ulonglong2 res;
+    res.x = addmod(c.x, crt_one<S3>(r0, k), k.q);
+    res.y = addmod(c.y, crt_one<S3>(r1, k), k.q);
+    *reinterpret_cast<ulonglong2 *>(out + (ct * 2 + pi) * (long)K * n + w) = res;
 }
 
 template <int LOGN>
@@ -655,7 +684,10 @@ cudaError_t run_t(const DeviceParams *dP, int K, const Relin32 &r, const uint64_
         if (e != cudaSuccess) return e;
     }
     r32_intt_kernel<LOGN><<<(unsigned)(count * 2 * K * c.S3), Pl::THREADS, smem, stream>>>(r.dc, acc);
-    r32_crt_kernel<<<dim3((unsigned)(count * 2 * K), (unsigned)(N / 256)), 256, 0, stream>>>(dP, r.dc, acc, in3, out);
+    const dim3 gc((unsigned)(count * 2 * K), (unsigned)(N / 512));
+    if (c.S3 == 2) r32_crt_kernel<2><<<gc, 256, 0, stream>>>(dP, r.dc, acc, in3, out);
+    else if (c.S3 == 3) r32_crt_kernel<3><<<gc, 256, 0, stream>>>(dP, r.dc, acc, in3, out);
+    else r32_crt_kernel<4><<<gc, 256, 0, stream>>>(dP, r.dc, acc, in3, out);
     return cudaGetLastError();
 }
 
