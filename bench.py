@@ -492,6 +492,11 @@ def main_b200(args, rank, world, local_rank):
         elif name in BFLY_CLASSES:
             ent["gbutterfly_s"] = ops / sec / 1e9
             ent["int_pipe_frac"] = BFLY_MACS * ops / sec / probe_rate
+        elif name == "relinearize_u32":
+            # relinearize through 30-bit auxiliary primes (relin32.cuh): ops = 32-bit Harvey butterflies, each 1 IMAD.HI + 2 IMAD
+            # = 0.75 of the probe's 4-instruction MAC; the transforms are bound by instruction issue and the L1 data pipe (ncu)
+            ent["gbutterfly32_s"] = ops / sec / 1e9
+            ent["int_pipe_frac"] = 0.75 * ops / sec / probe_rate
         classes[name] = ent
         kernel_ms[name] = {"launches_per_step": ent["launches_per_step"], "ms_per_step": ent["ms_per_step"]}
     dom = max(classes.items(), key=lambda kv: kv[1]["ms_per_step"])
@@ -523,7 +528,7 @@ def main_b200(args, rank, world, local_rank):
                                 if (MODEL, N_POLY) == ("PlainModel", 8192) else "%s encoded net, n=%d, K=%d, t=2^%d" % (MODEL, N_POLY, K, T_PLAIN.bit_length() - 1)),
                    "images_per_step_per_gpu": B, "parallelism": "image replicas x%d (no collective)" % world,
                    "l2": "inputs (%.1f GB per step) and weights exceed the 126 MB L2; no flush needed" % (h2d / 1e9),
-                   "weights": "conv1/conv2/fc4: NTT-form plaintexts resident (CUDA-core weighted sum); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
+                   "weights": "conv1/conv2/fc4: byte planes of the NTT-form plaintexts resident (limb-split tcgen05 kind::i8 weighted sum in the NTT domain); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
                 "upload_ms": [round(a_.elapsed_time(b_), 1) for a_, b_ in up_ev],

@@ -1124,8 +1124,11 @@ int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3) {
                 e = launch_ntt(ctx->dP, ctx->logn, ext, cur * 2 * KS, 0, KS, false, ctx->stream);
             }
         }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_SQ_TENSOR, lp_bytes(ctx, (double)cur * 5 * KS), (double)cur * 3 * KS * n); e = launch_square_tensor(ctx->dP, ctx->n, KS, ext, cur, prod, ctx->stream); }
-        if (e == cudaSuccess) { ProfScope ps(ctx, KC_NTT_INV, 2 * lp_bytes(ctx, (double)cur * 3 * KS), lp_bfly(ctx, (double)cur * 3 * KS)); e = launch_ntt(ctx->dP, ctx->logn, prod, cur * 3 * KS, 0, KS, true, ctx->stream); }
+        if (e == cudaSuccess) {
+            // tensor products formed while the inverse transform loads its polynomial (bytes: 2 inputs + 3 outputs per limb)
+            ProfScope ps(ctx, KC_NTT_INV, lp_bytes(ctx, (double)cur * 5 * KS), lp_bfly(ctx, (double)cur * 3 * KS));
+            e = launch_ntt_inv_tensor(ctx->dP, ctx->logn, ext, cur, KS, prod, ctx->stream);
+        }
         if (e == cudaSuccess) { ProfScope ps(ctx, KC_BEHZ_FLOOR, lp_bytes(ctx, (double)cur * 3 * (KS + ctx->K)),
                                                      (double)cur * 3 * n * (ctx->S * (ctx->K + 1) + ctx->S + ctx->K * ctx->S)); e = launch_behz_floor(ctx->hp.d, ctx->n, prod, cur, o->d + c0 * 3 * pw, ctx->stream); }
         if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));

@@ -36,6 +36,65 @@ ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, 
     ntt_inverse_from_smem<LOGN>(sm, poly, tb, addend ? addend + ((p / add_group) * add_stride + p % add_group) * (1L << LOGN) : nullptr);
 }
 
+// Tensor square fused into the inverse transform (evaluator.cpp:783-848): the CTA of output limb-polynomial (ct, k, j)
+// forms c0*c0 (k = 0), 2*c0*c1 (k = 1) or c1*c1 (k = 2) mod the j-th prime of q U Bsk while loading, then inverse-transforms it.
+// Saves the write and re-read of the 3(K+S) product polynomials of every ciphertext.
+template <int LOGN>
+__global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
+ntt_inv_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ ext, int KS, uint64_t *__restrict__ prod) {
+    extern __shared__ uint64_t sm[];
+    constexpr int N = 1 << LOGN;
+    const long b = blockIdx.x;  // (ct * 3 + k) * KS + j
+    const int j = (int)(b % KS);
+    const int k = (int)((b / KS) % 3);
+    const long ct = b / (3L * KS);
+    const NttTable tb = P->tab[j];
+    const uint64_t *c0 = ext + ((ct * 2) * KS + j) * N, *c1 = c0 + (long)KS * N;
+    if (k == 1) {
+#pragma unroll 8
+        for (int i = threadIdx.x; i < N; i += NttPlan<LOGN>::THREADS) {
+            const uint64_t ab = mulmod(__ldg(c0 + i), __ldg(c1 + i), tb.mod);
+            sm[ntt_pad(i)] = addmod(ab, ab, tb.mod.q);
+        }
+    } else {
+        const uint64_t *c = k == 0 ? c0 : c1;
+#pragma unroll 8
+        for (int i = threadIdx.x; i < N; i += NttPlan<LOGN>::THREADS) {
+            const uint64_t a = __ldg(c + i);
+            sm[ntt_pad(i)] = mulmod(a, a, tb.mod);
+        }
+    }
+    __syncthreads();
+    ntt_inverse_from_smem<LOGN>(sm, prod + b * N, tb);
+}
+
+template <int LOGN>
+static cudaError_t launch_ntt_inv_tensor_t(const DeviceParams *P, const uint64_t *ext, long count, int KS, uint64_t *prod, cudaStream_t stream) {
+    using Pl = NttPlan<LOGN>;
+    const size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
+    auto kf = ntt_inv_tensor_kernel<LOGN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    kf<<<(unsigned)(count * 3 * KS), Pl::THREADS, smem, stream>>>(P, ext, KS, prod);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ntt_inv_tensor(const DeviceParams *P, int logn, const uint64_t *ext, long count, int KS, uint64_t *prod, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    switch (logn) {
+        case 10: return launch_ntt_inv_tensor_t<10>(P, ext, count, KS, prod, stream);
+        case 11: return launch_ntt_inv_tensor_t<11>(P, ext, count, KS, prod, stream);
+        case 12: return launch_ntt_inv_tensor_t<12>(P, ext, count, KS, prod, stream);
+        case 13: return launch_ntt_inv_tensor_t<13>(P, ext, count, KS, prod, stream);
+        case 14: return launch_ntt_inv_tensor_t<14>(P, ext, count, KS, prod, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int LOGN>
 static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npolys, int slot_base, int slot_count,
                                 bool inverse, int group_polys, int group_off, const uint64_t *src, const uint64_t *addend,

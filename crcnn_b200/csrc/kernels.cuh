@@ -103,6 +103,10 @@ struct RelinArgs {
     // scratch (per call): dsc [count][K][n], dig [count][sum digits][K][n], acc [count][2][K][n]
     uint64_t *dsc, *dig, *acc;
 };
+// ---- tensor square (c0*c0, 2*c0*c1, c1*c1 in q U Bsk) fused into the inverse transform of each product polynomial:
+// ext = [count][2][KS][n] NTT form, prod = [count][3][KS][n] coefficient form
+cudaError_t launch_ntt_inv_tensor(const DeviceParams *P, int logn, const uint64_t *ext, long count, int KS, uint64_t *prod, cudaStream_t stream);
+
 // stages 1-3 (scale, digit NTTs, key MAC); then the caller inverse-NTTs `acc` and calls launch_relin_finish
 cudaError_t launch_relin(const DeviceParams *P, int logn, int K, const RelinArgs &a, cudaStream_t stream);
 cudaError_t launch_relin_finish(const DeviceParams *P, int n, int K, const RelinArgs &a, cudaStream_t stream);

@@ -305,12 +305,14 @@ __device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__
 // Coalesced copies between global (unpadded) and shared (padded).
 template <int LOGN>
 __device__ __forceinline__ void smem_load_poly(uint64_t *sm, const uint64_t *__restrict__ src) {
-    for (int i = threadIdx.x; i < (1 << LOGN); i += blockDim.x) sm[ntt_pad(i)] = src[i];
+#pragma unroll 8
+    for (int i = threadIdx.x; i < (1 << LOGN); i += NttPlan<LOGN>::THREADS) sm[ntt_pad(i)] = src[i];
 }
 // Lazy forward output (any value below 2^63) -> canonical residues in global memory.
 template <int LOGN>
 __device__ __forceinline__ void smem_store_poly_canonical(const uint64_t *sm, uint64_t *__restrict__ dst, const Mod &mod) {
-    for (int i = threadIdx.x; i < (1 << LOGN); i += blockDim.x) dst[i] = reduce64(sm[ntt_pad(i)], mod);
+#pragma unroll 8
+    for (int i = threadIdx.x; i < (1 << LOGN); i += NttPlan<LOGN>::THREADS) dst[i] = reduce64(sm[ntt_pad(i)], mod);
 }
 
 }  // namespace crcnn
