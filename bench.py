@@ -40,7 +40,7 @@ W = 8  # bytes per residue
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="images per step per GPU")
@@ -404,6 +404,7 @@ def main_b200(args, rank, world, local_rank):
         # tensors and the staging buffer are allocated once (crcnn_tensor_upload_into), nothing per step
         done = [None, None]                      # event: forward that consumed the buffer has finished
         up_ev = []                               # (start, end) of every upload on the copy stream
+        fwd_ev = []                              # (start, forward done, download done) of every step on the compute stream
         def upload(i):
             a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a_.record(copy_stream)
@@ -419,10 +420,15 @@ def main_b200(args, rank, world, local_rank):
                 if done[nxt] is not None:
                     copy_stream.wait_event(done[nxt])
                 upload(nxt)
+            f0, f1, f2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            f0.record(stream)
             y = net.forward(cur, batch=B)
-            done[s & 1] = torch.cuda.Event(); done[s & 1].record(stream)
+            f1.record(stream)
+            done[s & 1] = f1
             eng.download_ptr(y, host_out.data_ptr())
             y.free()
+            f2.record(stream)
+            fwd_ev.append((f0, f1, f2))
         ev2[1].record(stream)
         barrier()
         ms_e2e = ev2[0].elapsed_time(ev2[1])
@@ -532,6 +538,8 @@ def main_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
                 "upload_ms": [round(a_.elapsed_time(b_), 1) for a_, b_ in up_ev],
+                "forward_ms": [round(a_.elapsed_time(b_), 1) for a_, b_, _ in fwd_ev],
+                "download_ms": [round(b_.elapsed_time(c_), 1) for _, b_, c_ in fwd_ev],
                 "device_mem_free_gb": {"after_resident_loop": round(mem_free[0], 1), "after_e2e_loop": round(mem_free[1], 1)},
                 "note": "H2D + re-stride of step s+1 overlap the forward of step s on a copy stream; the first upload is not overlapped"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,

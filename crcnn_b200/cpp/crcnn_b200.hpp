@@ -236,6 +236,21 @@ struct PlainPack {
         }
         rt.check(crcnn_plain_upload_sparse(rt.ctx(), idx.data(), val.data(), off.data(), (long)pts.size(), &p));
     }
+    // Floats -> FractionalEncoder(t, x^n+1, 64, 32, base 3) plaintexts on the device, as CnnBuilder encodes them
+    // (CrCNN/src/cnnBuilder.cpp:25-105); no host Plaintext per weight (fc3 of PlainModel.h5 would be 41 GB of them).
+    void encode(const std::vector<float> &values) {
+        clear();
+        Runtime &rt = Runtime::get();
+        rt.check(crcnn_plain_encode(rt.ctx(), values.data(), (long)values.size(), &p));
+    }
+    // Host copy of plaintext `index` (coefficient form, n+1 words like the encoder's output)
+    Plaintext fetch(long index) const {
+        Runtime &rt = Runtime::get();
+        Plaintext pt;
+        pt.resize(rt.n() + 1);
+        rt.check(crcnn_plain_get(rt.ctx(), p, index, pt.data()));
+        return pt;
+    }
 };
 
 // ciphertext3D <-> device
@@ -331,6 +346,28 @@ public:
         loadPlaintextParameters(infile);
     }
 
+    // Trained floats in the reference's order [nf][zd][xf][yf] (cnnBuilder.cpp:36-47), encoded on the device; the host
+    // members `filters` / `biases` stay empty until materializeHostParameters() (getKernel, getBias and save call it).
+    ConvolutionalLayer(std::string name, int xd, int yd, int zd, int xs, int ys, int xf, int yf, int nf, int th_count,
+                       const std::vector<float> &weights, const std::vector<float> &bias_values)
+        : Layer(name), xd(xd), yd(yd), zd(zd), xs(xs), ys(ys), xf(xf), yf(yf), nf(nf), th_count(th_count),
+          xo((xd - xf) / xs + 1), yo((yd - yf) / ys + 1), zo(nf), filters_already_ntt(false) {
+        if ((long)weights.size() != (long)nf * zd * xf * yf || (int)bias_values.size() != nf) throw std::invalid_argument("kernel shape does not match the layer");
+        w_.encode(weights); b_.encode(bias_values);
+    }
+    void materializeHostParameters() {
+        if (!filters.empty() || !w_.p) return;
+        filters.assign(nf, plaintext3D(zd, plaintext2D(xf, std::vector<Plaintext>(yf))));
+        biases.resize(nf);
+        long w = 0;
+        for (int n = 0; n < nf; n++) {
+            for (int z = 0; z < zd; z++)
+                for (int i = 0; i < xf; i++)
+                    for (int j = 0; j < yf; j++) filters[n][z][i][j] = w_.fetch(w++);
+            biases[n] = b_.fetch(n);
+        }
+    }
+
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
         ensure_packs();
@@ -338,11 +375,12 @@ public:
         rt.check(crcnn_conv_forward(rt.ctx(), in.t, w_.p, b_.p, 1, xd, yd, zd, xs, ys, xf, yf, nf, &o));
         return DeviceTensor(o, zo, xo, yo);
     }
-    plaintext3D getKernel(int kernel_index) { return filters[kernel_index]; }
-    Plaintext getBias(int bias_index) { return biases[bias_index]; }
+    plaintext3D getKernel(int kernel_index) { materializeHostParameters(); return filters[kernel_index]; }
+    Plaintext getBias(int bias_index) { materializeHostParameters(); return biases[bias_index]; }
 
     // stream format: per filter zd*xf*yf weight records then the bias (convolutionalLayer.cpp:213-229)
     void savePlaintextParameters(std::ostream *outfile) override {
+        materializeHostParameters();
         for (int n = 0; n < nf; n++) {
             for (int z = 0; z < zd; z++)
                 for (int i = 0; i < xf; i++)
@@ -397,6 +435,24 @@ public:
         loadPlaintextParameters(infile);
     }
 
+    // Trained floats in the reference's order [out_dim][in_dim] (cnnBuilder.cpp:64-73), encoded on the device; `weights` /
+    // `biases` stay empty until materializeHostParameters().
+    FullyConnectedLayer(std::string name, int in_dim, int out_dim, int th_count, const std::vector<float> &weight_values,
+                        const std::vector<float> &bias_values)
+        : Layer(name), in_dim(in_dim), out_dim(out_dim), th_count(th_count), weights_already_ntt(false) {
+        if ((long)weight_values.size() != (long)in_dim * out_dim || (int)bias_values.size() != out_dim) throw std::invalid_argument("weight shape does not match the layer");
+        w_.encode(weight_values); b_.encode(bias_values);
+    }
+    void materializeHostParameters() {
+        if (!weights.empty() || !w_.p) return;
+        weights.assign(out_dim, std::vector<Plaintext>(in_dim));
+        biases.resize(out_dim);
+        for (int i = 0; i < out_dim; i++) {
+            for (int j = 0; j < in_dim; j++) weights[i][j] = w_.fetch((long)i * in_dim + j);
+            biases[i] = b_.fetch(i);
+        }
+    }
+
     // reshapeInput (fullyConnectedLayer.cpp:38-56): [z][x][y] -> [1][z*x*y][1], row-major.
     ciphertext3D reshapeInput(ciphertext3D input) {
         int x_size = (int)input[0].size(), y_size = (int)input[0][0].size(), z_size = (int)input.size();
@@ -418,11 +474,12 @@ public:
         rt.check(crcnn_fc_forward(rt.ctx(), in.t, w_.p, b_.p, 1, in_dim, out_dim, &o));
         return DeviceTensor(o, 1, out_dim, 1);
     }
-    Plaintext getWeight(int x_index, int y_index) { return weights[x_index][y_index]; }
-    Plaintext getBias(int x_index) { return biases[x_index]; }
+    Plaintext getWeight(int x_index, int y_index) { materializeHostParameters(); return weights[x_index][y_index]; }
+    Plaintext getBias(int x_index) { materializeHostParameters(); return biases[x_index]; }
 
     // per output row in_dim weights then the bias (fullyConnectedLayer.cpp:198-208)
     void savePlaintextParameters(std::ostream *outfile) override {
+        materializeHostParameters();
         for (int i = 0; i < out_dim; i++) {
             for (int j = 0; j < in_dim; j++) { weights[i][j].save(*outfile); outfile->flush(); }
             biases[i].save(*outfile);
@@ -506,6 +563,17 @@ public:
     BatchNormLayer(std::string name, int num_channels, std::istream *infile) : Layer(name), num_channels(num_channels) {
         loadPlaintextParameters(infile);
     }
+    // running mean and 1/sqrt(running_var + 1e-5) as floats (cnnBuilder.cpp:96-103), encoded on the device
+    BatchNormLayer(std::string name, int num_channels, const std::vector<float> &mean_values, const std::vector<float> &invstd_values)
+        : Layer(name), num_channels(num_channels) {
+        if ((int)mean_values.size() != num_channels || (int)invstd_values.size() != num_channels) throw std::invalid_argument("statistics do not match the channel count");
+        m_.encode(mean_values); v_.encode(invstd_values);
+    }
+    void materializeHostParameters() {
+        if (!mean.empty() || !m_.p) return;
+        mean.resize(num_channels); var.resize(num_channels);
+        for (int i = 0; i < num_channels; i++) { mean[i] = m_.fetch(i); var[i] = v_.fetch(i); }
+    }
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
         if (!m_.p) {
@@ -518,10 +586,11 @@ public:
         rt.check(crcnn_bn_forward(rt.ctx(), in.t, 1, in.zd, in.xd, in.yd, m_.p, v_.p, &o));
         return DeviceTensor(o, in.zd, in.xd, in.yd);
     }
-    Plaintext getMean(int index) { return mean[index]; }
-    Plaintext getVar(int index) { return var[index]; }
+    Plaintext getMean(int index) { materializeHostParameters(); return mean[index]; }
+    Plaintext getVar(int index) { materializeHostParameters(); return var[index]; }
     // alternating mean / var records (batchNormLayer.cpp:42-48)
     void savePlaintextParameters(std::ostream *outfile) override {
+        materializeHostParameters();
         for (int i = 0; i < num_channels; i++) { mean[i].save(*outfile); var[i].save(*outfile); outfile->flush(); }
     }
     void loadPlaintextParameters(std::istream *infile) override {

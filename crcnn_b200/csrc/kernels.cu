@@ -41,7 +41,8 @@ ntt_inv_kernel(uint64_t *__restrict__ data, const DeviceParams *__restrict__ P, 
 // Saves the write and re-read of the 3(K+S) product polynomials of every ciphertext.
 template <int LOGN>
 __global__ void __launch_bounds__(NttPlan<LOGN>::THREADS, NttPlan<LOGN>::MIN_CTAS)
-ntt_inv_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ ext, int KS, uint64_t *__restrict__ prod) {
+ntt_inv_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ ext, const uint64_t *__restrict__ qntt, int KS,
+                      uint64_t *__restrict__ prod) {
     extern __shared__ uint64_t sm[];
     constexpr int N = 1 << LOGN;
     const long b = blockIdx.x;  // (ct * 3 + k) * KS + j
@@ -50,6 +51,10 @@ ntt_inv_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__rest
     const long ct = b / (3L * KS);
     const NttTable tb = P->tab[j];
     const uint64_t *c0 = ext + ((ct * 2) * KS + j) * N, *c1 = c0 + (long)KS * N;
+    if (qntt && j < P->K) {  // q limbs straight from the NTT-form input tensor [ct][2][K][n]
+        c0 = qntt + ((ct * 2) * P->K + j) * N;
+        c1 = c0 + (long)P->K * N;
+    }
     if (k == 1) {
 #pragma unroll 8
         for (int i = threadIdx.x; i < N; i += NttPlan<LOGN>::THREADS) {
@@ -69,7 +74,8 @@ ntt_inv_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__rest
 }
 
 template <int LOGN>
-static cudaError_t launch_ntt_inv_tensor_t(const DeviceParams *P, const uint64_t *ext, long count, int KS, uint64_t *prod, cudaStream_t stream) {
+static cudaError_t launch_ntt_inv_tensor_t(const DeviceParams *P, const uint64_t *ext, const uint64_t *qntt, long count, int KS, uint64_t *prod,
+                                           cudaStream_t stream) {
     using Pl = NttPlan<LOGN>;
     const size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto kf = ntt_inv_tensor_kernel<LOGN>;
@@ -79,18 +85,19 @@ static cudaError_t launch_ntt_inv_tensor_t(const DeviceParams *P, const uint64_t
         cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
-    kf<<<(unsigned)(count * 3 * KS), Pl::THREADS, smem, stream>>>(P, ext, KS, prod);
+    kf<<<(unsigned)(count * 3 * KS), Pl::THREADS, smem, stream>>>(P, ext, qntt, KS, prod);
     return cudaGetLastError();
 }
 
-cudaError_t launch_ntt_inv_tensor(const DeviceParams *P, int logn, const uint64_t *ext, long count, int KS, uint64_t *prod, cudaStream_t stream) {
+cudaError_t launch_ntt_inv_tensor(const DeviceParams *P, int logn, const uint64_t *ext, const uint64_t *qntt, long count, int KS, uint64_t *prod,
+                                  cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
     switch (logn) {
-        case 10: return launch_ntt_inv_tensor_t<10>(P, ext, count, KS, prod, stream);
-        case 11: return launch_ntt_inv_tensor_t<11>(P, ext, count, KS, prod, stream);
-        case 12: return launch_ntt_inv_tensor_t<12>(P, ext, count, KS, prod, stream);
-        case 13: return launch_ntt_inv_tensor_t<13>(P, ext, count, KS, prod, stream);
-        case 14: return launch_ntt_inv_tensor_t<14>(P, ext, count, KS, prod, stream);
+        case 10: return launch_ntt_inv_tensor_t<10>(P, ext, qntt, count, KS, prod, stream);
+        case 11: return launch_ntt_inv_tensor_t<11>(P, ext, qntt, count, KS, prod, stream);
+        case 12: return launch_ntt_inv_tensor_t<12>(P, ext, qntt, count, KS, prod, stream);
+        case 13: return launch_ntt_inv_tensor_t<13>(P, ext, qntt, count, KS, prod, stream);
+        case 14: return launch_ntt_inv_tensor_t<14>(P, ext, qntt, count, KS, prod, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -642,8 +649,9 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
     for (int i = 0; i < KB; i++) {
         if (i < K) {
             uint64_t x = __ldg(src + (long)i * n);
-            // the q limbs of ext are transformed next: take them already transformed when the caller has them
-            dst[(long)i * n] = in_ntt ? __ldg(in_ntt + poly * K * n + c + (long)i * n) : x;
+            // the q limbs of ext are transformed next; when the caller already holds them transformed (in_ntt) the tensor
+            // stage reads them from there and nothing is written here
+            if (!in_ntt) dst[(long)i * n] = x;
             y[i] = mulmod(x, P.mt_inv_qhat[i], P.tab[i].mod);
             zmt += (uint32_t)y[i] * (uint32_t)P.qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
         }

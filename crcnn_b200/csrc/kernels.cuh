@@ -80,7 +80,7 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
 // lift:   in [count][2][K][n] (coefficient form) -> ext [count][2][K+S][n] (q limbs copied, Bsk limbs computed)
 // (lift and floor take the HOST copy of the parameter block: it travels as a by-value kernel argument, so every
 // base-conversion constant is a constant-bank operand)
-// in_ntt (optional): the same ciphertexts in NTT form; the q limbs of ext are then copied from it and only the Bsk
+// in_ntt (optional): the same ciphertexts in NTT form; the q limbs of ext are then left unwritten (launch_ntt_inv_tensor reads them from in_ntt) and only the Bsk
 // limbs still need the forward transform
 cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, const uint64_t *in_ntt, long count, uint64_t *ext,
                              cudaStream_t stream);
@@ -104,8 +104,10 @@ struct RelinArgs {
     uint64_t *dsc, *dig, *acc;
 };
 // ---- tensor square (c0*c0, 2*c0*c1, c1*c1 in q U Bsk) fused into the inverse transform of each product polynomial:
-// ext = [count][2][KS][n] NTT form, prod = [count][3][KS][n] coefficient form
-cudaError_t launch_ntt_inv_tensor(const DeviceParams *P, int logn, const uint64_t *ext, long count, int KS, uint64_t *prod, cudaStream_t stream);
+// ext = [count][2][KS][n] NTT form (qntt != null: its q limbs are taken from qntt = [count][2][K][n] instead),
+// prod = [count][3][KS][n] coefficient form
+cudaError_t launch_ntt_inv_tensor(const DeviceParams *P, int logn, const uint64_t *ext, const uint64_t *qntt, long count, int KS, uint64_t *prod,
+                                  cudaStream_t stream);
 
 // stages 1-3 (scale, digit NTTs, key MAC); then the caller inverse-NTTs `acc` and calls launch_relin_finish
 cudaError_t launch_relin(const DeviceParams *P, int logn, int K, const RelinArgs &a, cudaStream_t stream);

@@ -112,7 +112,7 @@ class Network:
             elif kind == "bn":
                 # CnnBuilder::buildBatchNormLayer, cnnBuilder.cpp:89-105 (float32 arithmetic as in the reference)
                 var = w[name + ".running_var"].astype(np.float32)
-                invstd = (np.float32(1) / np.sqrt(var + np.float32(0.00001))).astype(np.float32)
+                invstd = (1.0 / np.sqrt(var.astype(np.float64) + 0.00001)).astype(np.float32)  # double arithmetic, float result: cnnBuilder.cpp:101
                 self.packs[name] = (eng.plain_encode(w[name + ".running_mean"]), eng.plain_encode(invstd))
             elif kind == "avgpool":
                 xf, yf = layer[7], layer[8]
@@ -193,7 +193,7 @@ class ShardedNetwork(Network):
             elif layer[0] == "bn":
                 k0, kc = shard_range(channels, self.world, self.rank)
                 var = w[layer[1] + ".running_var"].astype(np.float32)
-                invstd = (np.float32(1) / np.sqrt(var + np.float32(0.00001))).astype(np.float32)
+                invstd = (1.0 / np.sqrt(var.astype(np.float64) + 0.00001)).astype(np.float32)  # double arithmetic, float result: cnnBuilder.cpp:101
                 self.local_bn[layer[1]] = (eng.plain_encode(w[layer[1] + ".running_mean"][k0:k0 + kc]),
                                            eng.plain_encode(invstd[k0:k0 + kc]))
 

@@ -1,0 +1,65 @@
+// Drives crcnn_b200::CnnBuilder the way the reference's main() drives its CnnBuilder (CrCNN/src/mainparams.cpp:64-116):
+//   builder_test <case.bin> <weights.h5> <topology> <out.bin>
+// case.bin: n, K, t, primes, dbc, key sizes, evaluation keys, input shape (z,x,y), input ciphertexts (Ciphertext::save records).
+// out.bin:  conv1 kernel [0][0][0][0] and bias [0] as Plaintext::save records, then the network's output ciphertexts.
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include "../../crcnn_b200/cpp/cnn_builder.hpp"
+
+using namespace std;
+using namespace crcnn_b200;
+
+template <class T> static T rd(istream &in) { T v; in.read(reinterpret_cast<char *>(&v), sizeof(T)); return v; }
+
+int main(int argc, char **argv) {
+    if (argc != 5) { cerr << "usage: builder_test <case.bin> <weights.h5> <topology> <out.bin>\n"; return 2; }
+    ifstream in(argv[1], ios::binary);
+    int n = rd<int32_t>(in), K = rd<int32_t>(in);
+    uint64_t t = rd<uint64_t>(in);
+    vector<uint64_t> q(K);
+    for (auto &x : q) x = rd<uint64_t>(in);
+    try {
+        Runtime &rt = Runtime::get();
+        rt.init(n, q, t);
+        int dbc = rd<int32_t>(in);
+        vector<int> sizes(K);
+        size_t words = 0;
+        for (auto &s : sizes) { s = rd<int32_t>(in); words += (size_t)s * K * (n + 1); }
+        vector<uint64_t> evk(words);
+        in.read(reinterpret_cast<char *>(evk.data()), words * 8);
+        rt.setEvaluationKeys(evk.data(), sizes.data(), dbc);
+        int zd = rd<int32_t>(in), xd = rd<int32_t>(in), yd = rd<int32_t>(in);
+        ciphertext3D x(zd, ciphertext2D(xd, vector<Ciphertext>(yd)));
+        for (auto &pl : x) for (auto &row : pl) for (auto &ct : row) ct.load(in);
+
+        CnnBuilder builder(argv[2]);
+        vector<float> b4 = builder.getPretrained("classifier.fc4.bias");
+        cout << "fc4_bias_count " << b4.size() << "\n";
+        Network net = builder.buildNetwork(argv[3], "");
+        cout << "layers " << net.getNumLayers() << "\n";
+
+        ofstream out(argv[4], ios::binary);
+        auto *conv1 = static_cast<ConvolutionalLayer *>(net.getLayer(0).get());
+        conv1->getKernel(0)[0][0][0].save(out);
+        conv1->getBias(0).save(out);
+        ciphertext3D y = net.forward(x);
+        for (auto &pl : y) for (auto &row : pl) for (auto &ct : row) ct.save(out);
+
+        // the encoded-network stream of one layer written by savePlaintextParameters is what the istream constructor reads back
+        stringstream ss(ios::in | ios::out | ios::binary);
+        conv1->savePlaintextParameters(&ss);
+        ConvolutionalLayer again(conv1->name, conv1->xd, conv1->yd, conv1->zd, conv1->xs, conv1->ys, conv1->xf, conv1->yf, conv1->nf, 1, &ss);
+        ciphertext3D c1 = conv1->forward(x), c2 = again.forward(x);
+        bool same = true;
+        for (size_t a = 0; a < c1.size(); a++) for (size_t b = 0; b < c1[a].size(); b++) for (size_t c = 0; c < c1[a][b].size(); c++)
+            same = same && memcmp(c1[a][b][c].data(), c2[a][b][c].data(), rt.ct_words() * 8) == 0;
+        bool threw = false;
+        try { builder.getPretrained("no.such.tensor"); } catch (const exception &) { threw = true; }
+        cout << "saveload_same " << same << "\nmissing_tensor_throws " << threw << "\nOK\n";
+    } catch (const exception &e) {
+        cout << "EXCEPTION " << e.what() << "\n";
+        return 1;
+    }
+    return 0;
+}
