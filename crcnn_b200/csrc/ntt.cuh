@@ -56,14 +56,25 @@ struct NttPlan {
 // by at most 4q per stage, < 61q < 2^63 after 14 stages, and are reduced once at the final store.  Larger moduli
 // (the 61-bit Bsk primes of `square`) keep the exact product and Harvey's correction.
 __device__ __forceinline__ bool ntt_needs_correction(uint64_t q) { return (q >> 57) != 0; }
+__device__ __forceinline__ int ntt_fwd_mode(uint64_t q) { return (q >> 57) == 0 ? 0 : ((q >> 61) == 0 ? 2 : 1); }
+// inverse: the lazy butterfly keeps u, v in [0,4q) and forms T = u + 4q - v < 8q, so it serves every q < 2^61
+__device__ __forceinline__ bool ntt_inv_exact(uint64_t q) { return (q >> 61) != 0; }
 
-// c = nq (2^64 - q) and c2 = 4q on the lazy path; c = q and c2 = 2q on the exact path
-template <bool CORR>
+// Forward butterfly modes (picked per modulus by ntt_fwd_mode):
+//   0  q < 2^57: approximate Shoup product, no correction of X at all (values grow by < 4q per stage)   c = nq, c2 = 4q
+//   1  exact Harvey butterfly, [0,4q) -> [0,4q) (any q < 2^62)                                          c = q,  c2 = 2q
+//   2  q < 2^61 (the Bsk primes): approximate product (result < 4q) with X corrected by 4q: [0,8q) -> [0,8q), 8q < 2^64
+//                                                                                                       c = nq, c2 = 4q
+template <int MODE>
 __device__ __forceinline__ void ct_butterfly(uint64_t &x, uint64_t &y, uint64_t W, uint64_t Wp, uint64_t c, uint64_t c2) {
-    if (CORR) {
-        // Harvey butterfly: x,y in [0,4q) -> [0,4q)
+    if (MODE == 1) {
         uint64_t X = x >= c2 ? x - c2 : x;
         uint64_t Q = mulshoup_lazy(y, W, Wp, c);
+        x = X + Q;
+        y = X + c2 - Q;
+    } else if (MODE == 2) {
+        uint64_t X = x >= c2 ? x - c2 : x;
+        uint64_t Q = mulshoup_lazy4(y, W, Wp, c);
         x = X + Q;
         y = X + c2 - Q;
     } else {
@@ -94,7 +105,7 @@ __device__ __forceinline__ void gs_butterfly(uint64_t &u, uint64_t &v, uint64_t 
 
 // B forward stages on 2^B residues spaced g apart; m0 = number of blocks at the first stage,
 // blk = this group's block index at that stage.
-template <int B, bool CORR>
+template <int B, int CORR>
 __device__ __forceinline__ void fwd_group(uint64_t (&x)[1 << B], const ulonglong2 *__restrict__ w,
                                           uint64_t q, uint64_t twoq, int m0, int blk) {
 #pragma unroll
@@ -130,10 +141,10 @@ __device__ __forceinline__ void inv_group(uint64_t (&x)[1 << B], const ulonglong
 }
 
 // One forward pass over the whole polynomial.  SRC_GLOBAL: read `gsrc` (unpadded) instead of smem.
-template <int LOGN, int B, bool SRC_GLOBAL, bool CORR>
+template <int LOGN, int B, bool SRC_GLOBAL, int CORR>
 __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restrict__ gsrc, const NttTable &tb, int m0, int g) {
     constexpr int N = 1 << LOGN;
-    const uint64_t q = CORR ? tb.mod.q : 0 - tb.mod.q, twoq = CORR ? 2 * tb.mod.q : 4 * tb.mod.q;
+    const uint64_t q = CORR == 1 ? tb.mod.q : 0 - tb.mod.q, twoq = CORR == 1 ? 2 * tb.mod.q : 4 * tb.mod.q;
     for (int G = threadIdx.x; G < (N >> B); G += blockDim.x) {
         int blk = G / g, o = G - blk * g;
         int base = blk * (g << B) + o;
@@ -148,10 +159,10 @@ __device__ __forceinline__ void fwd_pass(uint64_t *sm, const uint64_t *__restric
 
 // The contiguous 4-stage pass of the forward transform (g = 1): 16 consecutive residues per group, twiddles from the
 // transposed table wl[row][G], row = 2^s - 1 + lb.
-template <int LOGN, bool CORR>
+template <int LOGN, int CORR>
 __device__ __forceinline__ void fwd_last_pass(uint64_t *sm, const NttTable &tb) {
     constexpr int N = 1 << LOGN, NG = N >> 4;
-    const uint64_t q = CORR ? tb.mod.q : 0 - tb.mod.q, twoq = CORR ? 2 * tb.mod.q : 4 * tb.mod.q;
+    const uint64_t q = CORR == 1 ? tb.mod.q : 0 - tb.mod.q, twoq = CORR == 1 ? 2 * tb.mod.q : 4 * tb.mod.q;
     const ulonglong2 *wl = reinterpret_cast<const ulonglong2 *>(tb.wl);
     for (int G = threadIdx.x; G < NG; G += blockDim.x) {
         ulonglong2 *row = reinterpret_cast<ulonglong2 *>(sm + 18 * G);
@@ -241,7 +252,7 @@ __device__ __forceinline__ void inv_pass(uint64_t *sm, uint64_t *__restrict__ gd
     }
 }
 
-template <int LOGN, int FIRST_PASS, bool CORR>
+template <int LOGN, int FIRST_PASS, int CORR>
 __device__ __forceinline__ void ntt_forward_passes(uint64_t *sm, const uint64_t *__restrict__ src, const NttTable &tb) {
     using P = NttPlan<LOGN>;
     int m0 = 1, g = P::N;
@@ -265,16 +276,20 @@ __device__ __forceinline__ void ntt_forward_passes(uint64_t *sm, const uint64_t 
 // Forward transform of one polynomial: src (global, n words, canonical or < 4q) -> sm (padded, lazy).
 template <int LOGN>
 __device__ __forceinline__ void ntt_forward_to_smem(uint64_t *sm, const uint64_t *__restrict__ src, const NttTable &tb) {
-    if (ntt_needs_correction(tb.mod.q)) ntt_forward_passes<LOGN, 0, true>(sm, src, tb);
-    else ntt_forward_passes<LOGN, 0, false>(sm, src, tb);
+    const int mode = ntt_fwd_mode(tb.mod.q);
+    if (mode == 0) ntt_forward_passes<LOGN, 0, 0>(sm, src, tb);
+    else if (mode == 2) ntt_forward_passes<LOGN, 0, 2>(sm, src, tb);
+    else ntt_forward_passes<LOGN, 0, 1>(sm, src, tb);
 }
 
 // Forward transform when the polynomial is already in padded shared memory (values < 4q).
 // FIRST_PASS > 0 resumes the schedule after the passes a sparse-input expansion has replaced.
 template <int LOGN, int FIRST_PASS = 0>
 __device__ __forceinline__ void ntt_forward_in_smem(uint64_t *sm, const NttTable &tb) {
-    if (ntt_needs_correction(tb.mod.q)) ntt_forward_passes<LOGN, FIRST_PASS, true>(sm, nullptr, tb);
-    else ntt_forward_passes<LOGN, FIRST_PASS, false>(sm, nullptr, tb);
+    const int mode = ntt_fwd_mode(tb.mod.q);
+    if (mode == 0) ntt_forward_passes<LOGN, FIRST_PASS, 0>(sm, nullptr, tb);
+    else if (mode == 2) ntt_forward_passes<LOGN, FIRST_PASS, 2>(sm, nullptr, tb);
+    else ntt_forward_passes<LOGN, FIRST_PASS, 1>(sm, nullptr, tb);
 }
 
 // Inverse transform of the polynomial in padded shared memory (values < 2q, < 4q on the lazy path) -> dst
@@ -298,7 +313,7 @@ __device__ __forceinline__ void ntt_inverse_passes(uint64_t *sm, uint64_t *__res
 template <int LOGN>
 __device__ __forceinline__ void ntt_inverse_from_smem(uint64_t *sm, uint64_t *__restrict__ dst, const NttTable &tb,
                                                       const uint64_t *__restrict__ add = nullptr) {
-    if (ntt_needs_correction(tb.mod.q)) ntt_inverse_passes<LOGN, true>(sm, dst, tb, add);
+    if (ntt_inv_exact(tb.mod.q)) ntt_inverse_passes<LOGN, true>(sm, dst, tb, add);
     else ntt_inverse_passes<LOGN, false>(sm, dst, tb, add);
 }
 
