@@ -213,7 +213,13 @@ constexpr int TCN2_THREADS = 32 * (2 + TCN2_EPI_WARPS);
 template <int BK> struct Tcn2Cfg {
     static constexpr int W_BLOCK = TCN_PLANES * TCN2_MT * BK;   // weight planes of one K block: [7][32][BK]
     static constexpr int X_STAGE = TCN2_CB * BK;                // one input plane of one K block: [128][BK]
-    static constexpr int STAGES = BK == 128 ? 6 : 8;
+#ifndef TCN2_STAGES_SMALL
+#define TCN2_STAGES_SMALL 8
+#define TCN2_STAGES_BIG 6
+#endif
+    // ring depth: measured on B200, 40 / 9 stages instead of 8 / 6 made conv1 slower (42.6 -> 62.8 ms) and left conv2 unchanged,
+    // although 39 % of the samples of the 8-stage kernel wait on the accumulator-full barrier (profiles/r01f_ncu_source_top.txt)
+    static constexpr int STAGES = BK == 128 ? TCN2_STAGES_BIG : TCN2_STAGES_SMALL;
     static constexpr size_t SMEM = 1024 + (size_t)TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE + 8 * (2 * STAGES + 4) + 16;
 };
 
