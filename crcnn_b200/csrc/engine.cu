@@ -861,6 +861,7 @@ long crcnn_plain_count(const crcnn_plain *p) { return p ? p->count : -1; }
 int crcnn_evk_upload(crcnn_ctx *ctx, const uint64_t *host, int dbc, const int *sizes, crcnn_evk **out) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(host && sizes && out && dbc >= 1 && dbc <= 60, "bad evaluation key arguments");
+    CU(cudaSetDevice(ctx->device));
     auto *k = new crcnn_evk();
     k->dbc = dbc;
     long polys = 0;
@@ -1298,7 +1299,7 @@ int crcnn_prof_reset(crcnn_ctx *ctx) {
     for (int i = 0; i < KC_COUNT; i++) { ctx->launches[i] = 0; ctx->ms[i] = 0; ctx->work_bytes[i] = 0; ctx->work_ops[i] = 0; }
     return CRCNN_OK;
 }
-int crcnn_prof_count(crcnn_ctx *ctx) { return ctx ? KC_COUNT : CRCNN_ERR_INVALID_ARGUMENT; }
+int crcnn_prof_count(crcnn_ctx *ctx) { return ctx ? (int)KC_COUNT : (int)CRCNN_ERR_INVALID_ARGUMENT; }
 int crcnn_prof_get(crcnn_ctx *ctx, int cls, char *name, long *launches, double *ms) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(cls >= 0 && cls < KC_COUNT, "bad kernel class");

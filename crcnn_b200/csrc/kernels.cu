@@ -371,10 +371,9 @@ cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t str
 // grid.x = 1 KB... (word chunk of 512 residues) fastest, then the output ciphertext: the CTAs resident together work on a
 // handful of neighbouring outputs, so overlapping windows (2x2 stride 1 reads every input 4 times) are served by L2.
 // SMALL: R * max(q) < 2^64, the window sum fits 64 bits.  scale_sh = Shoup companions of `scale` (floor(s * 2^64 / q)).
-// One CTA = EW_CHUNK consecutive residues of one output ciphertext (inside one limb: EW_CHUNK divides n), a thread owns
+// One CTA = 512 * EW_PER consecutive residues of one output ciphertext (inside one limb: it divides n), a thread owns
 // EW_PER groups of two residues, 512 words apart, with all its loads issued before the arithmetic.
 constexpr int EW_PER = 4;
-constexpr int EW_CHUNK = 512 * EW_PER;
 
 template <bool SMALL>
 __global__ void __launch_bounds__(256)
@@ -670,23 +669,6 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
     }
 }
 
-// NTT-domain tensor square in both bases (evaluator.cpp:783-834)
-__global__ void __launch_bounds__(256)
-square_tensor_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ ext, uint64_t *__restrict__ prod) {
-    const int n = P->n, KS = P->K + P->S;
-    const long pw = (long)KS * n;
-    const long ct = blockIdx.x;
-    const long lw = (long)blockIdx.y * 256 + threadIdx.x;
-    if (lw >= pw) return;
-    const Mod mod = P->tab[lw / n].mod;
-    const uint64_t a = __ldg(ext + ct * 2 * pw + lw), b = __ldg(ext + ct * 2 * pw + pw + lw);
-    uint64_t *o = prod + ct * 3 * pw + lw;
-    o[0] = mulmod(a, a, mod);
-    uint64_t ab = mulmod(a, b, mod);
-    o[pw] = addmod(ab, ab, mod.q);
-    o[2 * pw] = mulmod(b, b, mod);
-}
-
 // multiply by t, fast_floor (q U Bsk -> Bsk), fastbconv_sk (Bsk -> q)
 // (evaluator.cpp:852-883, baseconverter.cpp:624-661, :448-579), one thread per coefficient.  Constant
 // factors are folded (fl_c, fl_T, fl_N, fl_P in params.h) so that every residue the reference computes
@@ -923,14 +905,6 @@ cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, 
     if (count <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)(count * 2 * (n / 128));
     CRCNN_BEHZ_DISPATCH(behz_lift_kernel, grid, in, in_ntt, ext);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uint64_t *ext, long count,
-                                    uint64_t *prod, cudaStream_t stream) {
-    if (count <= 0) return cudaSuccess;
-    dim3 grid((unsigned)count, (unsigned)(((long)KS * n + 255) / 256));
-    square_tensor_kernel<<<grid, 256, 0, stream>>>(P, ext, prod);
     return cudaGetLastError();
 }
 

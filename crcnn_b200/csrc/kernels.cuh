@@ -84,8 +84,6 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
 // limbs still need the forward transform
 cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, const uint64_t *in_ntt, long count, uint64_t *ext,
                              cudaStream_t stream);
-// tensor: ext (NTT form) -> prod [count][3][K+S][n] (NTT form): c0^2, 2 c0 c1, c1^2
-cudaError_t launch_square_tensor(const DeviceParams *P, int n, int KS, const uint64_t *ext, long count, uint64_t *prod, cudaStream_t stream);
 // floor:  prod (coefficient form) -> out [count][3][K][n]: multiply by t, fast_floor, fastbconv_sk
 cudaError_t launch_behz_floor(const DeviceParams &hp, int n, const uint64_t *prod, long count, uint64_t *out, cudaStream_t stream);
 

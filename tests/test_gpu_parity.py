@@ -146,6 +146,16 @@ def test_relinearize_both_paths(env):
             eng.set_relin_mode(1)
 
 
+def test_relinearize_other_digit_width(env):
+    """Keys with 20-bit digits do not fit the 16-bit digit planes of the auxiliary-prime path: the engine must fall back to the
+    64-bit procedure on its own and still give the oracle's bytes."""
+    n, primes, t, eng, orc, rng = env
+    evk, sizes, dbc = random_evk(rng, n, primes, dbc=20)
+    x3 = random_cts(rng, n, primes, 3, size=3)
+    k = eng.evk_upload(evk, sizes, dbc)
+    assert np.array_equal(eng.download(eng.relinearize(eng.upload(x3, size=3), k)), orc.relinearize(x3, evk, sizes, dbc))
+
+
 def _layer_params(orc, rng, count):
     vals = rng.uniform(-1, 1, size=count).astype(np.float32)
     return vals, orc.encode_many(vals)
