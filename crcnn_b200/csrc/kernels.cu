@@ -1,5 +1,6 @@
 // Device kernels of the encrypted-forward hot path (sm_100a).  See kernels.cuh for the contracts.
 #include "kernels.cuh"
+#include "devcfg.cuh"
 #include "ntt.cuh"
 #include <cstdlib>
 
@@ -79,11 +80,10 @@ static cudaError_t launch_ntt_inv_tensor_t(const DeviceParams *P, const uint64_t
     using Pl = NttPlan<LOGN>;
     const size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto kf = ntt_inv_tensor_kernel<LOGN>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     kf<<<(unsigned)(count * 3 * KS), Pl::THREADS, smem, stream>>>(P, ext, qntt, KS, prod);
     return cudaGetLastError();
@@ -110,14 +110,13 @@ static cudaError_t launch_ntt_t(const DeviceParams *P, uint64_t *data, long npol
     size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto kf = ntt_fwd_kernel<LOGN>;
     auto ki = ntt_inv_kernel<LOGN>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         // without this the driver sizes the carve-out for ONE resident CTA (seen in ncu: occupancy limit 1)
         cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(ki, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     if (npolys <= 0) return cudaSuccess;
     if ((src || addend) && !inverse) return cudaErrorInvalidValue;
@@ -211,11 +210,10 @@ static cudaError_t launch_plain_expand_t(const DeviceParams *P, int K, const uin
     using Pl = NttPlan<LOGN>;
     size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto k = plain_expand_kernel<LOGN>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     if (count <= 0) return cudaSuccess;
     k<<<(unsigned)(count * K), Pl::THREADS, smem, stream>>>(P, K, offsets, idx, val, first, mode, to_ntt ? 1 : 0, out);
@@ -808,11 +806,10 @@ static cudaError_t launch_digits_t(const DeviceParams *P, int K, const uint64_t 
     using Pl = NttPlan<LOGN>;
     size_t smem = Pl::SMEM_WORDS * sizeof(uint64_t);
     auto k = ntt_fwd_digits_kernel<LOGN>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     k<<<(unsigned)(count * map.D * K), Pl::THREADS, smem, stream>>>(P, dsc, map, mask, dig);
     return cudaGetLastError();

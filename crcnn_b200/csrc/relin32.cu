@@ -1,6 +1,7 @@
 // Relinearisation through word-size auxiliary primes: see relin32.cuh for the algorithm and why it is bit-exact.
 #include "relin32.cuh"
 #include "kernels.cuh"
+#include "devcfg.cuh"
 #include "modarith.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -611,27 +612,23 @@ r32_crt_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__restri
 
 template <int LOGN>
 void configure32() {
-    static bool done = false;
-    if (done) return;
+    static DeviceOnce once;
+    if (!once.first()) return;
     const int smem = Plan32<LOGN>::SMEM_WORDS * 4;
     cudaFuncSetAttribute(r32_digits_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(r32_key_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(r32_intt_kernel<LOGN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(r32_digits_kernel<LOGN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(r32_intt_kernel<LOGN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    done = true;
 }
 
 template <int T, int OC, int EW>
 cudaError_t launch_mac(const uint32_t *dig, const Relin32 &r, int n, long count, int cpb, unsigned gz, size_t bytes_per_coeff, uint32_t *acc,
                        cudaStream_t stream) {
     const size_t smem = bytes_per_coeff * EW;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(r32_mac_kernel<T, OC, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    // the staged size depends on the digit count of the context: set it on every launch (a cheap driver call, once per chunk)
+    cudaError_t e = cudaFuncSetAttribute(r32_mac_kernel<T, OC, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     r32_mac_kernel<T, OC, EW><<<dim3((unsigned)(n / EW), (unsigned)r.c.S3, gz), 256, smem, stream>>>(dig, r.keys, r.dc, n, count, cpb, acc);
     return cudaGetLastError();
 }
@@ -639,12 +636,11 @@ cudaError_t launch_mac(const uint32_t *dig, const Relin32 &r, int n, long count,
 template <int D, int OC>
 cudaError_t launch_mac_reg(const uint32_t *dig, const Relin32 &r, int n, long count, int cpb, unsigned gz, uint32_t *acc, cudaStream_t stream) {
     constexpr size_t smem = (size_t)6 * 2 * D * 64 * 4;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(r32_mac_reg_kernel<D, OC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(r32_mac_reg_kernel<D, OC>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
     }
     r32_mac_reg_kernel<D, OC><<<dim3((unsigned)(n / 64), (unsigned)r.c.S3, gz), 32 * OC, smem, stream>>>(dig, r.keys, r.dc, n, count, cpb, acc);
     return cudaGetLastError();

@@ -2,6 +2,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdio>
+#include "devcfg.cuh"
 #include "modarith.cuh"
 #include "tc_mac.cuh"
 #include "tc_ptx.cuh"
@@ -255,11 +256,10 @@ cudaError_t launch_tc_mac_t(const DeviceParams *P, const TcMacArgs &a, int sm_co
     }
     auto k = tc_mac_kernel<PLANES>;
     const size_t smem = tc_smem_bytes<PLANES>();
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const long items = (long)a.npos * 2 * a.K * (a.Mpad / TC_BM);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include "devcfg.cuh"
 #include "modarith.cuh"
 #include "tc_ptx.cuh"
 #include "tcn_mac.cuh"
@@ -482,11 +483,10 @@ cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_
     }
     auto k = tcn_mac_kernel<BK>;
     const size_t smem = TcnCfg<BK>::SMEM;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const long items = (long)a.nslots * ((a.M + TCN_BM - 1) / TCN_BM);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
@@ -520,11 +520,10 @@ cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm
     }
     auto k = tcn2_mac_kernel<BK>;
     const size_t smem = Tcn2Cfg<BK>::SMEM;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const long items = (long)a.nslots * ((a.M + TCN2_MT - 1) / TCN2_MT);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
