@@ -25,6 +25,9 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE JSON line: whatever NCCL has to say (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
