@@ -26,7 +26,7 @@ namespace crcnn {
 
 constexpr int R32_MAXP = 4;
 
-struct Relin32Consts {  // passed to the kernels by value
+struct Relin32Consts {  // one device copy per key set (Relin32::dc); the kernels index its arrays dynamically
     int S3;             // auxiliary primes in use
     int D;              // total digits = sum_i digits_i
     int dbc;
