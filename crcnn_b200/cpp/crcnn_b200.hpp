@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <istream>
 #include <memory>
@@ -299,6 +300,30 @@ inline ciphertext3D download(const DeviceTensor &d) {
             }
     return out;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Encrypted-image files (CrCNN/src/globals.cpp:160-205): zd*xd*yd Ciphertext::save records back to back, [z][x][y] order.
+// loadEncryptedImage / deepCopyImage keep the reference's signatures; saveEncryptedImage is the writing half of
+// encryptAndSaveImage (the encryption itself stays with the key holder, SEAL on the host).
+// ------------------------------------------------------------------------------------------------
+inline ciphertext3D loadEncryptedImage(int zd, int xd, int yd, std::string file_name) {
+    std::ifstream imagefile(file_name, std::ifstream::binary);
+    if (!imagefile) throw std::invalid_argument("cannot open encrypted image " + file_name);
+    ciphertext3D encrypted_image(zd, ciphertext2D(xd, std::vector<Ciphertext>(yd)));
+    for (int z = 0; z < zd; z++)
+        for (int i = 0; i < xd; i++)
+            for (int j = 0; j < yd; j++) encrypted_image[z][i][j].load(imagefile);
+    if (!imagefile) throw std::invalid_argument("encrypted image " + file_name + " is shorter than the requested shape");
+    return encrypted_image;
+}
+inline void saveEncryptedImage(const ciphertext3D &encrypted_image, std::string file_name) {
+    std::ofstream outfile(file_name, std::ofstream::binary);
+    if (!outfile) throw std::invalid_argument("cannot write " + file_name);
+    for (auto &plane : encrypted_image)
+        for (auto &row : plane)
+            for (auto &ct : row) ct.save(outfile);
+}
+inline ciphertext3D deepCopyImage(ciphertext3D image) { return image; }  // value semantics: the vectors copy every Ciphertext
 
 // ------------------------------------------------------------------------------------------------
 // Layer (CrCNN/src/layer.h:10-31)

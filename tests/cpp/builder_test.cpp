@@ -54,6 +54,15 @@ int main(int argc, char **argv) {
         bool same = true;
         for (size_t a = 0; a < c1.size(); a++) for (size_t b = 0; b < c1[a].size(); b++) for (size_t c = 0; c < c1[a][b].size(); c++)
             same = same && memcmp(c1[a][b][c].data(), c2[a][b][c].data(), rt.ct_words() * 8) == 0;
+        // encrypted-image file round trip (globals.cpp:160-205 format)
+        const string img_file = string(argv[4]) + ".img";
+        saveEncryptedImage(x, img_file);
+        ciphertext3D back = loadEncryptedImage(zd, xd, yd, img_file);
+        bool img_same = true;
+        for (int z = 0; z < zd; z++) for (int i = 0; i < xd; i++) for (int j = 0; j < yd; j++)
+            img_same = img_same && memcmp(back[z][i][j].data(), x[z][i][j].data(), rt.ct_words() * 8) == 0;
+        remove(img_file.c_str());
+        cout << "image_file_same " << img_same << "\n";
         bool threw = false;
         try { builder.getPretrained("no.such.tensor"); } catch (const exception &) { threw = true; }
         cout << "saveload_same " << same << "\nmissing_tensor_throws " << threw << "\nOK\n";
