@@ -156,6 +156,29 @@ def test_relinearize_other_digit_width(env):
     assert np.array_equal(eng.download(eng.relinearize(eng.upload(x3, size=3), k)), orc.relinearize(x3, evk, sizes, dbc))
 
 
+def test_degree_1024_square_relinearize_transforms():
+    """n = 1024 is the smallest degree the kernels are instantiated for (one 5-stage strided pass + the contiguous pass in the
+    32-bit transforms, generic key-product kernel): not a CrCNN configuration, but SEAL accepts it."""
+    from crcnn_b200.lib import Engine
+    n, primes, t = 1024, [0x3fffffff000001], 1 << 10
+    eng, orc = Engine(n, primes, t), Oracle(n, primes, t)
+    rng = np.random.default_rng(1024)
+    x = random_cts(rng, n, primes, 5)
+    tx = eng.upload(x)
+    eng.to_ntt(tx)
+    assert np.array_equal(eng.download(tx, ntt_form=True), orc.ct_transform(x))
+    want3 = orc.square(x)
+    t3 = eng.square(tx)
+    assert np.array_equal(eng.download(t3), want3)
+    evk, sizes, dbc = random_evk(rng, n, primes)
+    want2 = orc.relinearize(want3, evk, sizes, dbc)
+    k = eng.evk_upload(evk, sizes, dbc)
+    for mode in (1, 0):
+        eng.set_relin_mode(mode)
+        assert np.array_equal(eng.download(eng.relinearize(t3, k)), want2), mode
+    eng.close()
+
+
 def _layer_params(orc, rng, count):
     vals = rng.uniform(-1, 1, size=count).astype(np.float32)
     return vals, orc.encode_many(vals)
