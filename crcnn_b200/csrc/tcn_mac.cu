@@ -211,6 +211,23 @@ constexpr int TCN2_KBMAX = 2;
 constexpr int TCN2_EPI_WARPS = 12;                      // three per TMEM lane quadrant
 constexpr int TCN2_THREADS = 32 * (2 + TCN2_EPI_WARPS);
 
+// -DCRCNN_TCN2_TRACE: CTA 0 records clock64() at the hand-over points of its three roles (tools/tcn2_trace.py reads them
+// back).  Every record costs a global-memory round trip (~340 cycles): compare intervals that contain the same number of records.
+#ifdef CRCNN_TCN2_TRACE
+constexpr int TCN2_TRACE_N = 8192;
+__device__ unsigned long long g_tcn2_trace[3][TCN2_TRACE_N];
+__device__ int g_tcn2_trace_n[3];
+#define TCN2_TR(role, tag)                                                                                    \
+    do {                                                                                                      \
+        if (blockIdx.x == 0) {                                                                                \
+            const int i_ = g_tcn2_trace_n[role];                                                              \
+            if (i_ < TCN2_TRACE_N) { g_tcn2_trace[role][i_] = ((unsigned long long)(tag) << 56) | (clock64() & 0xffffffffffffffull); g_tcn2_trace_n[role] = i_ + 1; } \
+        }                                                                                                     \
+    } while (0)
+#else
+#define TCN2_TR(role, tag) do { } while (0)
+#endif
+
 template <int BK> struct Tcn2Cfg {
     static constexpr int W_BLOCK = TCN_PLANES * TCN2_MT * BK;   // weight planes of one K block: [7][32][BK]
     static constexpr int X_STAGE = TCN2_CB * BK;                // one input plane of one K block: [128][BK]
@@ -289,6 +306,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     for (int kb = 0; kb < KB; kb++)
                         for (int bi = 0; bi < TCN_PLANES; bi++) {
                             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                            TCN2_TR(0, bi);                         // stage free: load of plane bi issued now
                             mbar_expect_tx(bar_full + 8 * stage, X_STAGE);
                             tma_load_4d(sX + stage * X_STAGE, &tmX, bar_full + 8 * stage, kb * BK, ch * TCN2_CB, plane_of(bi), sl);
                             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -306,7 +324,9 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 wphase ^= 1;
                 tc_fence_after();
                 for (int ch = 0; ch < chunks; ch++) {
+                    TCN2_TR(1, 100);                                // waiting for the accumulator
                     mbar_wait(bar_tempty, acc_phase ^ 1);
+                    TCN2_TR(1, 101);                                // accumulator free
                     tc_fence_after();
                     for (int kb = 0; kb < KB; kb++) {
                         const uint32_t wS = sW + kb * W_BLOCK;
@@ -314,6 +334,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         for (int bi = 0; bi < TCN_PLANES; bi++) {
                             const int pb = plane_of(bi);
                             mbar_wait(bar_full + 8 * stage, phase);
+                            TCN2_TR(1, kb * 8 + bi);                    // plane tile arrived
                             tc_fence_after();
                             const uint32_t xS = sX + stage * X_STAGE;
                             for (int ks = 0; ks < nks; ks++) {
@@ -334,6 +355,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                         }
                     }
                     umma_commit(bar_tfull);
+                    TCN2_TR(1, 102);                                // all MMAs of the chunk issued
                     acc_phase ^= 1;
                 }
                 umma_commit(bar_wempty);   // every MMA that reads this item's weights has been issued before this commit
@@ -363,7 +385,9 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const long colbase = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + p % a.Pimg;
                 uint64_t *out_col = a.out + (colbase * 2 + poly) * pw + slot_off + (long)(a.m0 + mt * TCN2_MT) * m_stride;
                 const bool add_bias = bias_p != nullptr && poly == 0;
+                if (warp == 2 && lane == 0) TCN2_TR(2, 200);    // waiting for the accumulator
                 mbar_wait(bar_tfull, acc_phase);
+                if (warp == 2 && lane == 0) TCN2_TR(2, 201);    // accumulator complete
                 tc_fence_after();
 #pragma unroll 1
                 for (int g = sub; g < groups; g += TCN2_EPI_WARPS / 4) {
@@ -389,6 +413,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty);
+                if (warp == 2 && lane == 0) TCN2_TR(2, 202);    // this warp's share of the chunk recombined and stored
                 acc_phase ^= 1;
             }
         }
@@ -557,3 +582,18 @@ cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_co
 }
 
 }  // namespace crcnn
+
+#ifdef CRCNN_TCN2_TRACE
+// debug builds only: reset / read back the trace of CTA 0 (role 0 producer, 1 MMA issuer, 2 first epilogue warp)
+extern "C" int crcnn_debug_tcn2_trace_reset() {
+    int z[3] = {0, 0, 0};
+    return (int)cudaMemcpyToSymbol(crcnn::g_tcn2_trace_n, z, sizeof(z));
+}
+extern "C" int crcnn_debug_tcn2_trace_read(int role, unsigned long long *out, int cap) {
+    int n[3];
+    if (cudaMemcpyFromSymbol(n, crcnn::g_tcn2_trace_n, sizeof(n)) != cudaSuccess) return -1;
+    const int cnt = n[role] < cap ? n[role] : cap;
+    if (cudaMemcpyFromSymbol(out, crcnn::g_tcn2_trace, (size_t)cnt * 8, (size_t)role * crcnn::TCN2_TRACE_N * 8) != cudaSuccess) return -1;
+    return cnt;
+}
+#endif
