@@ -86,6 +86,7 @@ struct crcnn_ctx {
     int tap_mode = 1;                // 1: avg-pool / batch-norm on coefficient-form inputs multiply in the coefficient domain (tapmul_kernel); env CRCNN_TAP
     int relin_mode = 1;              // 1: relinearize through 30-bit auxiliary primes when exact for the parameters (relin32.cuh); 0: 64-bit transforms
     int tcn_mode = 1;                // 1: weighted sums whose staged weights fit the weight cache run as the NTT-domain limb-split GEMM (tcn_mac.cuh)
+    int tcn_fold = 0;                // 1: the limb-split GEMM reduces its class sums through the 2^k - delta shape of the primes when they have it (modarith.cuh: tcn_fold_reduce), 0: 128-bit recombination + Barrett; same bytes, measured equally fast on B200 (the epilogue is not instruction bound); env CRCNN_TCN_FOLD
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
@@ -396,6 +397,8 @@ int run_weighted_sum_tcn(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn
     a.R = R; a.Kpad = Kpad; a.planes = 7; a.ncols = ncols;
     a.Pimg = Pimg; a.Mtotal = M; a.m0 = 0; a.n = ctx->n; a.K = ctx->K;
     a.variant = ctx->tcn_mode >= 2 ? ctx->tcn_mode - 1 : 0;
+    a.use_fold = ctx->tcn_fold;
+    for (int j = 0; j < ctx->K; j++) a.fold[j] = tcn_fold_make(ctx->hp.d.tab[j].mod.q);
     for (long s0 = 0; s0 < total && !rc; s0 += chunk) {
         const int ns = (int)std::min<long>(chunk, total - s0);
         s.slot0 = a.slot0 = (int)s0; s.nslots = a.nslots = ns;
@@ -516,6 +519,7 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
     if (const char *e = getenv("CRCNN_TC")) c->tc_mode = atoi(e);
     if (const char *e = getenv("CRCNN_TCN")) c->tcn_mode = atoi(e);
     if (const char *e = getenv("CRCNN_TAP")) c->tap_mode = atoi(e);
+    if (const char *e = getenv("CRCNN_TCN_FOLD")) c->tcn_fold = atoi(e);
     // stream-ordered allocator: keep freed blocks cached
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -624,6 +628,13 @@ int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(mode >= 0 && mode <= 3, "limb-split mode must be 0 (off), 1 (on), 2 (row-major kernel) or 3 (column-major kernel)");
     ctx->tcn_mode = mode;
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_set_limb_split_reduction(crcnn_ctx *ctx, int mode) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(mode == 0 || mode == 1, "limb-split reduction must be 0 (128-bit recombination + Barrett) or 1 (folded through 2^k - delta)");
+    ctx->tcn_fold = mode;
     return CRCNN_OK;
 }
 

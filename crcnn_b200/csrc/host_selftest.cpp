@@ -46,6 +46,29 @@ int main(int argc, char **argv) {
                 if (lazy >= 2 * m.q || lazy % m.q != want) { printf("SHOUP MISMATCH\n"); return 1; }
             }
         }
+        // folded reduction of the limb-split GEMM's class sums (modarith.cuh: tcn_fold_reduce) against unsigned __int128
+        for (int j = 0; j < d.K; j++) {
+            const Mod &m = d.tab[j].mod;
+            const TcnFold f = tcn_fold_make(m.q);
+            printf("fold %d ok %u T %u delta %u\n", j, f.ok, f.T, f.delta);
+            if (!f.ok) continue;
+            for (int it = 0; it < 200000; it++) {
+                uint32_t s[13];
+                const int mode = it % 8;
+                for (int w = 0; w < 13; w++) {
+                    x = x * 6364136223846793005ULL + 1442695040888963407ULL;
+                    const uint32_t r = (uint32_t)(x >> 33);                 // < 2^31
+                    s[w] = mode == 0 ? 0x7fffffffu : mode == 1 ? 0u : mode == 2 ? ((x >> 20) & 1 ? 0x7fffffffu : 0u)
+                         : mode == 3 ? 7u * 4096u * 255u * 255u - (r & 3) : mode == 4 ? (r >> (x & 31)) : r;
+                }
+                y = y * 2862933555777941757ULL + 3037000493ULL;
+                const uint64_t bias = mode == 0 ? m.q - 1 : (it & 1) ? y % m.q : 0;
+                unsigned __int128 z = 0;
+                for (int w = 12; w >= 0; w--) z = (z << 8) + s[w];
+                const uint64_t want = (uint64_t)((z + bias) % m.q);
+                if (tcn_fold_reduce(s, bias, f, m.q) != want) { printf("FOLD MISMATCH\n"); return 1; }
+            }
+        }
         // fractional encoder
         for (int i = 4; i >= 0; i--) {
             double vals[] = {0.0867, -3.25, 0.0, 1.0, 2.8215};

@@ -180,4 +180,90 @@ CRCNN_HD uint64_t mulshoup_lazy4(uint64_t y, uint64_t w, uint64_t wp, uint64_t n
 #endif
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Reduction of the 13 weight-class sums of the limb-split GEMM (tcn_mac.cuh) for primes of SEAL's shape
+// q = 2^k - delta (SEAL/seal/util/globals.cpp:50-74: the 54/55-bit primes have delta < 2^25), without forming the
+// 128-bit integer and without a generic Barrett step:  z = sum_w S_w 2^(8w) (+ bias)  ->  z mod q in [0, q).
+//   La, Lb, Ha, Hb = the classes 0-3, 4-6, 7-10, 11-12 as four sums of weight 2^0, 2^32, 2^56, 2^88 (the
+//   multiply-adds by 2^8, 2^16, 2^24 take their factor from a run-time operand, so each is ONE IMAD.WIDE instead
+//   of shifts and carry chains);  2^56 = T (mod q) with T = 2^(56-k) delta < 2^28 folds the upper two into the
+//   lower two:   z = [La + Ha0 T] + 2^32 [Lb + Ha1 T + Hb0 T] + 2^64 [Hb1 T]   (< 2^100);
+//   the bits above k fold through delta twice (67 bits, then < 2q; the bias joins in between), one conditional
+//   subtraction.  Every step is an identity mod q and the result is canonical, so it equals
+//   barrett128(tcn_combine(S)) (+ bias mod q) bit for bit; host_selftest.cpp checks it against unsigned __int128.
+struct TcnFold {
+    uint32_t T;           // 2^56 mod q
+    uint32_t delta;       // 2^k - q
+    uint32_t sh, mask;    // k - 32, 2^(k-32) - 1
+    uint32_t c8, c16, c24;
+    uint32_t ok;          // 0: this prime does not have the shape (the kernels then take the generic path)
+};
+
+// Worst-case magnitudes of every intermediate for S_w <= 2^31 - 1 and bias <= q - 1, checked numerically.
+inline TcnFold tcn_fold_make(uint64_t q) {
+    typedef unsigned __int128 u128;
+    TcnFold f{};
+    int k = 0;
+    for (uint64_t v = q; v; v >>= 1) k++;
+    if (k < 48 || k > 56) return f;
+    const uint64_t delta = (1ull << k) - q;
+    if (delta == 0 || delta >> 28) return f;
+    const u128 T = (u128)delta << (56 - k);
+    if (T >> 32 || T >= q) return f;
+    const u128 one = 1, smax = 0x7fffffffu, w32 = 0xffffffffu;
+    const u128 La = smax * (1 + (one << 8) + (one << 16) + (one << 24)), Lb = smax * (1 + (one << 8) + (one << 16));
+    const u128 Ha = La, Hb = smax * (1 + (one << 8));
+    const u128 a = w32 * T + La, b = (Ha >> 32) * T + Lb + w32 * T, e = (Hb >> 32) * T;
+    if (a >> 64 || b >> 64 || e >> 60) return f;
+    const u128 y = a + (b << 32) + (e << 64);                   // < 2^101
+    const u128 h1 = (y >> k) >> 32;
+    const u128 v = w32 * delta + ((one << k) - 1) + (q - 1), w = h1 * delta;
+    if (h1 >> 32 || v >> 64 || w >> 62) return f;
+    const u128 V = v + (w << 32);
+    const u128 g = V >> k;
+    if (V >> 96 || g >> 32) return f;
+    if (g * delta + ((one << k) - 1) >= 2 * (u128)q) return f;
+    f.T = (uint32_t)T; f.delta = (uint32_t)delta; f.sh = (uint32_t)(k - 32); f.mask = (1u << (k - 32)) - 1;
+    f.c8 = 1u << 8; f.c16 = 1u << 16; f.c24 = 1u << 24; f.ok = 1;
+    return f;
+}
+
+CRCNN_HD uint32_t tcn_shr64(uint32_t lo, uint32_t hi, uint32_t sh) {   // low word of (hi:lo) >> sh, 0 < sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (lo >> sh) | (hi << (32 - sh));
+#endif
+}
+
+// s[w] = class sum S_w (< 2^31), bias < q (0 when there is none)
+CRCNN_HD uint64_t tcn_fold_reduce(const uint32_t (&s)[13], uint64_t bias, const TcnFold &f, uint64_t q) {
+    const uint64_t La = (uint64_t)s[3] * f.c24 + ((uint64_t)s[2] * f.c16 + ((uint64_t)s[1] * f.c8 + s[0]));
+    const uint64_t Lb = (uint64_t)s[6] * f.c16 + ((uint64_t)s[5] * f.c8 + s[4]);
+    const uint64_t Ha = (uint64_t)s[10] * f.c24 + ((uint64_t)s[9] * f.c16 + ((uint64_t)s[8] * f.c8 + s[7]));
+    const uint64_t Hb = (uint64_t)s[12] * f.c8 + s[11];
+    const uint64_t a = (uint64_t)(uint32_t)Ha * f.T + La;
+    const uint64_t b = (uint64_t)(uint32_t)Hb * f.T + ((Ha >> 32) * f.T + Lb);
+    const uint64_t e = (Hb >> 32) * f.T;
+    // y = a + 2^32 b + 2^64 e  as words y0..y3
+    const uint32_t y0 = (uint32_t)a;
+    const uint64_t m1 = (a >> 32) + (uint32_t)b;
+    const uint32_t y1 = (uint32_t)m1;
+    const uint64_t m2 = (b >> 32) + (uint64_t)(uint32_t)e + (m1 >> 32);
+    const uint32_t y2 = (uint32_t)m2;
+    const uint32_t y3 = (uint32_t)(e >> 32) + (uint32_t)(m2 >> 32);
+    // first fold of the bits above k, bias added: V = v + 2^32 w
+    const uint32_t h0 = tcn_shr64(y1, y2, f.sh), h1 = tcn_shr64(y2, y3, f.sh);
+    const uint64_t l = ((uint64_t)(y1 & f.mask) << 32) | y0;
+    const uint64_t v = (uint64_t)h0 * f.delta + l + bias;
+    const uint64_t w = (uint64_t)h1 * f.delta;
+    const uint64_t m3 = (v >> 32) + (uint32_t)w;
+    const uint32_t V1 = (uint32_t)m3, V2 = (uint32_t)(w >> 32) + (uint32_t)(m3 >> 32);
+    // second fold
+    const uint32_t g = tcn_shr64(V1, V2, f.sh);
+    const uint64_t lo = ((uint64_t)(V1 & f.mask) << 32) | (uint32_t)v;
+    const uint64_t r = (uint64_t)g * f.delta + lo;
+    return r >= q ? r - q : r;
+}
+
 }  // namespace crcnn

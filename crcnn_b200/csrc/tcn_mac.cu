@@ -39,6 +39,14 @@ __device__ __forceinline__ U128 tcn_combine(const uint32_t (&S)[TCN_CLASSES][4],
     return z;
 }
 
+// output i of a group of four through the folded reduction (modarith.cuh: tcn_fold_reduce); bias = 0 when there is none
+__device__ __forceinline__ uint64_t tcn_fold_out(const uint32_t (&S)[TCN_CLASSES][4], int i, uint64_t bias, const TcnFold &f, uint64_t q) {
+    uint32_t s[TCN_CLASSES];
+#pragma unroll
+    for (int w = 0; w < TCN_CLASSES; w++) s[w] = S[w][i];
+    return tcn_fold_reduce(s, bias, f, q);
+}
+
 template <int BK> struct TcnCfg {
     static constexpr int A_STAGE = TCN_PLANES * TCN_BM * BK;   // weight planes of one K block
     static constexpr int B_STAGE = TCN_PLANES * TCN_NB * BK;   // input planes of one K block
@@ -47,7 +55,7 @@ template <int BK> struct TcnCfg {
 };
 
 // ------------------------------------------------------------------------------------ the GEMM kernel
-template <int BK>
+template <int BK, bool FOLD>
 __global__ void __launch_bounds__(TCN_THREADS, 1)
 tcn_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                const DeviceParams *__restrict__ P, TcnMacArgs a) {
@@ -160,6 +168,7 @@ tcn_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
             const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
             const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;
             const Mod mod = P->tab[j].mod;
+            const TcnFold fold = a.fold[FOLD ? j : 0];
             const int m = mt * TCN_BM + qd * 16 + lane;     // output row of this thread (lanes >= 16 hold nothing)
             const bool valid = lane < 16 && m < a.M;
             const uint64_t bias = (a.bias && valid) ? __ldg(a.bias + (long)m * pw + (long)j * n + c) : 0;
@@ -179,9 +188,14 @@ tcn_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
                     for (int i = 0; i < 4; i++) {
                         const int col = col0 + i;
                         if (!valid || col >= a.ncols) continue;
-                        uint64_t r = barrett128(tcn_combine(S, i), mod);
                         const int p = col >> 1, poly = col & 1;
-                        if (poly == 0 && a.bias) r = addmod(r, bias, mod.q);
+                        uint64_t r;
+                        if constexpr (FOLD) {
+                            r = tcn_fold_out(S, i, poly == 0 ? bias : 0, fold, mod.q);   // bias is 0 without a bias pack
+                        } else {
+                            r = barrett128(tcn_combine(S, i), mod);
+                            if (poly == 0 && a.bias) r = addmod(r, bias, mod.q);
+                        }
                         const long oct = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + row_off + p % a.Pimg;
                         a.out[((oct * 2 + poly) * a.K + j) * (long)n + c] = r;
                     }
@@ -241,7 +255,11 @@ template <int BK> struct Tcn2Cfg {
     static constexpr size_t SMEM = 1024 + (size_t)TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE + 8 * (2 * STAGES + 4) + 16;
 };
 
-template <int BK>
+// BIAS: 0 = the bias residue of an output is loaded where it is added; 1 = lane m fetches the bias of output m once per item and
+// the loop broadcasts it by shuffle; 2 = as 1 with the output stores dropped (timing experiments only, results are not written).
+// Measured on B200 (PlainModel.h5, batch 8): BIAS 1 takes conv2 (BK 128) from 35.3 to 33.4 ms and conv1 (BK 32) from 42.5 to 70 ms,
+// so the launcher uses 1 for BK 128 and 0 for BK 32 (DESIGN.md section 6 on why conv1 dislikes a quicker epilogue).
+template <int BK, bool FOLD, int BIAS>
 __global__ void __launch_bounds__(TCN2_THREADS, 1)
 tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                 const DeviceParams *__restrict__ P, TcnMacArgs a) {
@@ -374,9 +392,14 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
             const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;
             const Mod mod = P->tab[j].mod;
+            const TcnFold fold = a.fold[FOLD ? j : 0];
             const long slot_off = (long)j * n + c;
             const int m_valid = min(TCN2_MT, a.M - mt * TCN2_MT);
             const int groups = (m_valid + 3) >> 2;
+            // the bias residue of output m of this item does not depend on the column: lane m fetches it once per item and the
+            // loop below broadcasts it by shuffle (a load per output inside the loop put an L2 round trip into every output's chain)
+            uint64_t bias_lane = 0;
+            if (BIAS != 0 && a.bias && lane < m_valid) bias_lane = __ldg(a.bias + (long)(mt * TCN2_MT + lane) * pw + slot_off);
             const uint64_t *bias_p = a.bias ? a.bias + (long)(mt * TCN2_MT) * pw + slot_off : nullptr;
             for (int ch = 0; ch < chunks; ch++) {
                 const int col = ch * TCN2_CB + qd * 32 + lane;
@@ -384,7 +407,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const int p = col >> 1, poly = col & 1;
                 const long colbase = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + p % a.Pimg;
                 uint64_t *out_col = a.out + (colbase * 2 + poly) * pw + slot_off + (long)(a.m0 + mt * TCN2_MT) * m_stride;
-                const bool add_bias = bias_p != nullptr && poly == 0;
+                const bool add_bias = poly == 0 && (BIAS != 0 || bias_p != nullptr);
                 if (warp == 2 && lane == 0) TCN2_TR(2, 200);    // waiting for the accumulator
                 mbar_wait(bar_tfull, acc_phase);
                 if (warp == 2 && lane == 0) TCN2_TR(2, 201);    // accumulator complete
@@ -402,9 +425,18 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         if (mloc + i < m_valid) {                // warp uniform
-                            uint64_t r = barrett128(tcn_combine(S, i), mod);
-                            if (add_bias) r = addmod(r, __ldg(bp), mod.q);
-                            if (valid) *op = r;
+                            uint64_t bias_m = 0;
+                            if constexpr (BIAS != 0) bias_m = __shfl_sync(0xffffffffu, bias_lane, mloc + i);
+                            else if (add_bias) bias_m = __ldg(bp);
+                            uint64_t r;
+                            if constexpr (FOLD) {
+                                r = tcn_fold_out(S, i, add_bias ? bias_m : 0, fold, mod.q);
+                            } else {
+                                r = barrett128(tcn_combine(S, i), mod);
+                                if (add_bias) r = addmod(r, bias_m, mod.q);
+                            }
+                            if constexpr (BIAS == 2) { if (valid && r == ~0ull) *op = r; }   // never true: r < q
+                            else if (valid) *op = r;
                         }
                         op += m_stride;
                         bp += pw;
@@ -481,7 +513,7 @@ tcn_split_kernel(TcnSplitArgs a) {
 }
 
 // ------------------------------------------------------------------------------------ host side
-template <int BK>
+template <int BK, bool FOLD>
 cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -506,7 +538,7 @@ cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    auto k = tcn_mac_kernel<BK>;
+    auto k = tcn_mac_kernel<BK, FOLD>;
     const size_t smem = TcnCfg<BK>::SMEM;
     static DeviceOnce once;
     if (once.first()) {
@@ -519,7 +551,7 @@ cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_
     return cudaGetLastError();
 }
 
-template <int BK>
+template <int BK, bool FOLD, int BIAS>
 cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -543,7 +575,7 @@ cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    auto k = tcn2_mac_kernel<BK>;
+    auto k = tcn2_mac_kernel<BK, FOLD, BIAS>;
     const size_t smem = Tcn2Cfg<BK>::SMEM;
     static DeviceOnce once;
     if (once.first()) {
@@ -577,8 +609,25 @@ cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_co
     const int bk = tcn_bk(a.R);
     const bool fits2 = ((a.R + 31) / 32 * 32 + bk - 1) / bk <= TCN2_KBMAX;
     const bool use2 = fits2 && (forced == 2 || (forced != 1 && a.ncols >= 4 * a.M));
-    if (use2) return bk == 128 ? launch_tcn2_mac_t<128>(P, a, sm_count, stream) : launch_tcn2_mac_t<32>(P, a, sm_count, stream);
-    return bk == 128 ? launch_tcn_mac_t<128>(P, a, sm_count, stream) : launch_tcn_mac_t<32>(P, a, sm_count, stream);
+    // folded reduction of the class sums (modarith.cuh: tcn_fold_reduce) when every prime of the context has SEAL's shape
+    bool fold = a.use_fold != 0;
+    for (int j = 0; j < a.K && fold; j++) fold = a.fold[j].ok != 0;
+    // CRCNN_TCN2_BIAS=0|1 overrides where the column-major kernel takes its bias from (A/B runs; same bytes either way)
+    static const int bias_env = [] { const char *e = getenv("CRCNN_TCN2_BIAS"); return e ? atoi(e) : -1; }();
+    if (use2) {
+        const int bias_var = bias_env >= 0 ? bias_env : (bk == 128 ? 1 : 0);
+#ifdef CRCNN_TCN2_TIMING   // timing builds only (make EXTRA=-DCRCNN_TCN2_TIMING OUT=../../ab/libS.so OBJDIR=../../build/objS): 2 drops the stores, results are NOT written
+        if (bias_var == 2) return bk == 128 ? launch_tcn2_mac_t<128, false, 2>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 2>(P, a, sm_count, stream);
+#endif
+        if (fold) {
+            if (bias_var) return bk == 128 ? launch_tcn2_mac_t<128, true, 1>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, true, 1>(P, a, sm_count, stream);
+            return bk == 128 ? launch_tcn2_mac_t<128, true, 0>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, true, 0>(P, a, sm_count, stream);
+        }
+        if (bias_var) return bk == 128 ? launch_tcn2_mac_t<128, false, 1>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 1>(P, a, sm_count, stream);
+        return bk == 128 ? launch_tcn2_mac_t<128, false, 0>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 0>(P, a, sm_count, stream);
+    }
+    if (fold) return bk == 128 ? launch_tcn_mac_t<128, true>(P, a, sm_count, stream) : launch_tcn_mac_t<32, true>(P, a, sm_count, stream);
+    return bk == 128 ? launch_tcn_mac_t<128, false>(P, a, sm_count, stream) : launch_tcn_mac_t<32, false>(P, a, sm_count, stream);
 }
 
 }  // namespace crcnn

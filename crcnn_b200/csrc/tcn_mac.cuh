@@ -69,6 +69,8 @@ struct TcnMacArgs {
     int slot0, nslots;
     int Pimg, Mtotal, m0;
     int n, K;
+    int use_fold;          // 1: reduce the class sums with tcn_fold_reduce when fold[j].ok for every prime (0: 128-bit recombination + Barrett)
+    TcnFold fold[MAXK];    // per coefficient prime (modarith.cuh: tcn_fold_make)
     int variant;           // 0: pick by shape; 1: outputs on the UMMA rows (64 x 32 tiles); 2: columns on the UMMA rows (128 x 32 tiles, fan-in <= 256)
 };
 

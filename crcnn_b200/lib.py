@@ -30,6 +30,7 @@ SYMBOLS = [
     ("crcnn_ctx_set_weight_cache_bytes", _I, [_vp, C.c_size_t]),
     ("crcnn_ctx_set_tensor_core_mode", _I, [_vp, C.c_int, C.c_int, C.c_size_t]),
     ("crcnn_ctx_set_limb_split_mode", _I, [_vp, C.c_int]),
+    ("crcnn_ctx_set_limb_split_reduction", _I, [_vp, C.c_int]),
     ("crcnn_ctx_set_relin_mode", _I, [_vp, C.c_int]),
     ("crcnn_ctx_ntt_table", _I, [_vp, _I, _I, _u64p]),
     ("crcnn_ctx_bsk_count", _I, [_vp]),
@@ -173,6 +174,9 @@ class Engine:
 
     def set_limb_split_mode(self, mode):
         self._chk(self.lib.crcnn_ctx_set_limb_split_mode(self.h, int(mode)))
+
+    def set_limb_split_reduction(self, mode):
+        self._chk(self.lib.crcnn_ctx_set_limb_split_reduction(self.h, int(mode)))
 
     def set_relin_mode(self, mode):
         self._chk(self.lib.crcnn_ctx_set_relin_mode(self.h, int(mode)))

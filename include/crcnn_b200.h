@@ -79,6 +79,13 @@ int crcnn_ctx_set_tensor_core_mode(crcnn_ctx *ctx, int mode, int min_fanin, size
  * kernel shapes (outputs / columns on the UMMA rows) instead of choosing by layer shape.  Env CRCNN_TCN sets the
  * initial mode (default 1).  The scratch budget is the one of crcnn_ctx_set_tensor_core_mode. */
 int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode);
+/* How the limb-split GEMM turns its 13 class sums into a residue: mode 1 (default) uses the shape of SEAL's coefficient primes,
+ * q = 2^k - delta with delta < 2^25 (SEAL/seal/util/globals.cpp:50-74): the classes are gathered into four sums, 2^56 and the bits
+ * above k are folded through 2^56 mod q and delta, one conditional subtraction (crcnn_b200/csrc/modarith.cuh: tcn_fold_reduce); it
+ * applies when every prime of the context has that shape, otherwise, or with mode 0, the classes are recombined into a 128-bit
+ * integer and reduced by the generic Barrett step (barrett_reduce_128, SEAL/seal/util/uintarithsmallmod.h:137-176).  Both produce
+ * the canonical residue, i.e. the same bytes.  Env CRCNN_TCN_FOLD sets the initial mode. */
+int crcnn_ctx_set_limb_split_reduction(crcnn_ctx *ctx, int mode);
 /* relinearize (Evaluator::relinearize, SEAL/seal/evaluator.cpp:886-1069): mode 1 (default) evaluates the digit (x) key
  * product sums over three or four NTT-friendly primes below 2^30 and reconstructs each coefficient exactly before reducing it
  * mod q_j (crcnn_b200/csrc/relin32.cuh) -- the same canonical residues from 32-bit transforms; it applies when

@@ -152,3 +152,37 @@ def test_extreme_residues_limb_split(env):
     g1 = eng.download(eng.fc(tx, w, b_, 1, in_dim, out_dim), ntt_form=True)
     g2 = _cuda_core(eng, lambda: eng.download(eng.fc(tx, eng.plain_encode(wv), b_, 1, in_dim, out_dim), ntt_form=True))
     assert np.array_equal(g1, g2), _explain(g1, g2)
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+def test_both_reductions_of_the_class_sums(env, variant):
+    """The folded reduction through q = 2^k - delta (default) and the 128-bit recombination + Barrett give the oracle's bytes,
+    in both kernel shapes; random and all-(q-1) NTT-form slots (the largest class sums), with and without a bias in play
+    (polynomial 1 never takes one)."""
+    n, primes, t, eng, orc, rng = env
+    in_dim, out_dim = 40, 5
+    K = len(primes)
+    x = random_cts(rng, n, primes, in_dim)
+    wv, wp = _vals(orc, rng, in_dim * out_dim, -30.0, 30.0)
+    bv, bp = _vals(orc, rng, out_dim)
+    want = orc.fc(x, in_dim, out_dim, wp, bp)
+    xm = np.zeros((in_dim, 2, K, n + 1), dtype=np.uint64)
+    for j, q in enumerate(primes):
+        xm[:, :, j, :n] = q - 1
+    w, b_ = eng.plain_encode(wv), eng.plain_encode(bv)
+    outs = {}
+    eng.set_limb_split_mode(variant)
+    try:
+        for mode in (1, 0):
+            eng.set_limb_split_reduction(mode)
+            before = _launches(eng)
+            got = eng.download(eng.fc(eng.upload(x), w, b_, 1, in_dim, out_dim)).reshape(want.shape)
+            assert _launches(eng) == before + 1
+            assert np.array_equal(got, want), "reduction %d: %s" % (mode, _explain(got, want))
+            outs[mode] = eng.download(eng.fc(eng.upload(xm, ntt_form=True), w, b_, 1, in_dim, out_dim), ntt_form=True)
+    finally:
+        eng.set_limb_split_reduction(1)
+        eng.set_limb_split_mode(1)
+    assert np.array_equal(outs[0], outs[1]), _explain(outs[1], outs[0])
+    g2 = _cuda_core(eng, lambda: eng.download(eng.fc(eng.upload(xm, ntt_form=True), eng.plain_encode(wv), b_, 1, in_dim, out_dim), ntt_form=True))
+    assert np.array_equal(outs[1], g2), _explain(outs[1], g2)
