@@ -47,6 +47,12 @@ def test_derived_constants_match_oracle(selftest, n, t):
             assert int(f[9]) == o.minimal_root(base, idx)
             for col, which in ((11, 0), (13, 1), (15, 2), (17, 3)):
                 assert int(f[col]) == fnv(o.ntt_table(base, idx, which)), (s, which)
+        if f[0] == "fold":
+            # every SEAL default prime has the 2^k - delta shape the folded reduction of the limb-split GEMM needs; the selftest has
+            # compared tcn_fold_reduce with unsigned __int128 on 200000 class-sum vectors per prime before printing OK
+            j, q = int(f[1]), int(primes[int(f[1])])
+            k = q.bit_length()
+            assert int(f[3]) == 1 and int(f[7]) == (1 << k) - q and int(f[5]) == ((1 << k) - q) << (56 - k), ln
         if f[0] == "enc":
             want, _ = o.encode(float(f[1]))
             got = np.zeros(n + 1, dtype=np.uint64)
