@@ -252,14 +252,18 @@ template <int BK> struct Tcn2Cfg {
     // ring depth: measured on B200, 40 / 9 stages instead of 8 / 6 made conv1 slower (42.6 -> 62.8 ms) and left conv2 unchanged,
     // although 39 % of the samples of the 8-stage kernel wait on the accumulator-full barrier (profiles/r01f_ncu_source_top.txt)
     static constexpr int STAGES = BK == 128 ? TCN2_STAGES_BIG : TCN2_STAGES_SMALL;
-    static constexpr size_t SMEM = 1024 + (size_t)TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE + 8 * (2 * STAGES + 4) + 16;
+    static constexpr size_t smem(int ns) { return 1024 + (size_t)ns * TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE + 8 * (2 * STAGES + 4) + 16; }
 };
 
 // BIAS: 0 = the bias residue of an output is loaded where it is added; 1 = lane m fetches the bias of output m once per item and
 // the loop broadcasts it by shuffle; 2 = as 1 with the output stores dropped (timing experiments only, results are not written).
 // Measured on B200 (PlainModel.h5, batch 8): BIAS 1 takes conv2 (BK 128) from 35.3 to 33.4 ms and conv1 (BK 32) from 42.5 to 70 ms,
 // so the launcher uses 1 for BK 128 and 0 for BK 32 (DESIGN.md section 6 on why conv1 dislikes a quicker epilogue).
-template <int BK, bool FOLD, int BIAS>
+// NS: consecutive slots per work item.  1 = one slot per item (what every measured number of round 1 is).  4 (EXPERIMENTAL, not yet run
+// on hardware; CRCNN_TCN2_NS=4, BK 32 only) = the four slots of one 32-byte output sector belong to ONE item, loop order chunk-outer /
+// slot-inner with the four slots' weight planes resident, so a sector's four 8-byte writes come from the same thread a few microseconds apart
+// instead of from four CTAs that have to stay in step ("Correction").
+template <int BK, bool FOLD, int BIAS, int NS>
 __global__ void __launch_bounds__(TCN2_THREADS, 1)
 tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                 const DeviceParams *__restrict__ P, TcnMacArgs a) {
@@ -273,8 +277,8 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sW = base, sX = base + TCN2_KBMAX * W_BLOCK;
-    const uint32_t off_bar = TCN2_KBMAX * W_BLOCK + STAGES * X_STAGE;
+    const uint32_t sW = base, sX = base + NS * TCN2_KBMAX * W_BLOCK;
+    const uint32_t off_bar = NS * TCN2_KBMAX * W_BLOCK + STAGES * X_STAGE;
     const uint32_t bar_full = base + off_bar, bar_empty = bar_full + 8 * STAGES;
     const uint32_t bar_wfull = bar_empty + 8 * STAGES, bar_wempty = bar_wfull + 8;
     const uint32_t bar_tfull = bar_wempty + 8, bar_tempty = bar_tfull + 8;
@@ -284,7 +288,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = a.n;
     const int m_tiles = (a.M + TCN2_MT - 1) / TCN2_MT;
-    const long items = (long)a.nslots * m_tiles;
+    const long items = (long)(a.nslots / NS) * m_tiles;   // item = (group of NS consecutive slots, output tile)
     const int chunks = (a.ncols + TCN2_CB - 1) / TCN2_CB;
     const int ksteps = (a.R + 31) / 32;
     const int KB = (ksteps * 32 + BK - 1) / BK;   // <= TCN2_KBMAX (checked by the launcher)
@@ -314,21 +318,23 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0, wphase = 0;
             for (long item = blockIdx.x; item < items; item += gridDim.x) {
-                const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
+                const int sl = (int)(item / m_tiles) * NS, mt = (int)(item % m_tiles);
                 mbar_wait(bar_wempty, wphase ^ 1);
-                mbar_expect_tx(bar_wfull, KB * W_BLOCK);
-                for (int kb = 0; kb < KB; kb++)
-                    tma_load_4d(sW + kb * W_BLOCK, &tmW, bar_wfull, kb * BK, mt * TCN2_MT, 0, a.slot0 + sl);
+                mbar_expect_tx(bar_wfull, NS * KB * W_BLOCK);
+                for (int s = 0; s < NS; s++)
+                    for (int kb = 0; kb < KB; kb++)
+                        tma_load_4d(sW + (s * TCN2_KBMAX + kb) * W_BLOCK, &tmW, bar_wfull, kb * BK, mt * TCN2_MT, 0, a.slot0 + sl + s);
                 wphase ^= 1;
                 for (int ch = 0; ch < chunks; ch++)
-                    for (int kb = 0; kb < KB; kb++)
-                        for (int bi = 0; bi < TCN_PLANES; bi++) {
-                            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                            TCN2_TR(0, bi);                         // stage free: load of plane bi issued now
-                            mbar_expect_tx(bar_full + 8 * stage, X_STAGE);
-                            tma_load_4d(sX + stage * X_STAGE, &tmX, bar_full + 8 * stage, kb * BK, ch * TCN2_CB, plane_of(bi), sl);
-                            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                        }
+                    for (int s = 0; s < NS; s++)
+                        for (int kb = 0; kb < KB; kb++)
+                            for (int bi = 0; bi < TCN_PLANES; bi++) {
+                                mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                                TCN2_TR(0, bi);                         // stage free: load of plane bi issued now
+                                mbar_expect_tx(bar_full + 8 * stage, X_STAGE);
+                                tma_load_4d(sX + stage * X_STAGE, &tmX, bar_full + 8 * stage, kb * BK, ch * TCN2_CB, plane_of(bi), sl + s);
+                                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                            }
             }
         }
         __syncwarp();
@@ -341,13 +347,14 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 mbar_wait(bar_wfull, wphase);
                 wphase ^= 1;
                 tc_fence_after();
-                for (int ch = 0; ch < chunks; ch++) {
+                for (int chs = 0; chs < chunks * NS; chs++) {       // (chunk, slot of the item), slot fastest
+                    const int s = NS == 1 ? 0 : chs % NS;
                     TCN2_TR(1, 100);                                // waiting for the accumulator
                     mbar_wait(bar_tempty, acc_phase ^ 1);
                     TCN2_TR(1, 101);                                // accumulator free
                     tc_fence_after();
                     for (int kb = 0; kb < KB; kb++) {
-                        const uint32_t wS = sW + kb * W_BLOCK;
+                        const uint32_t wS = sW + (s * TCN2_KBMAX + kb) * W_BLOCK;
                         const int nks = BK == 128 ? min(4, ksteps - kb * 4) : 1;
                         for (int bi = 0; bi < TCN_PLANES; bi++) {
                             const int pb = plane_of(bi);
@@ -389,8 +396,8 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const long m_stride = 2L * a.Pimg * pw;      // words between consecutive outputs of one column
         uint32_t acc_phase = 0;
         for (long item = blockIdx.x; item < items; item += gridDim.x) {
-            const int sl = (int)(item / m_tiles), mt = (int)(item % m_tiles);
-            const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;
+            const int sl = (int)(item / m_tiles) * NS, mt = (int)(item % m_tiles);
+            const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;   // first slot of the item; its NS slots share the limb j (n and slot0 are multiples of NS)
             const Mod mod = P->tab[j].mod;
             const TcnFold fold = a.fold[FOLD ? j : 0];
             const long slot_off = (long)j * n + c;
@@ -398,8 +405,10 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
             const int groups = (m_valid + 3) >> 2;
             // the bias residue of output m of this item does not depend on the column: lane m fetches it once per item and the
             // loop below broadcasts it by shuffle (a load per output inside the loop put an L2 round trip into every output's chain)
-            uint64_t bias_lane = 0;
-            if (BIAS != 0 && a.bias && lane < m_valid) bias_lane = __ldg(a.bias + (long)(mt * TCN2_MT + lane) * pw + slot_off);
+            uint64_t bias_lane[NS];
+#pragma unroll
+            for (int s = 0; s < NS; s++)
+                bias_lane[s] = (BIAS != 0 && a.bias && lane < m_valid) ? __ldg(a.bias + (long)(mt * TCN2_MT + lane) * pw + slot_off + s) : 0;
             const uint64_t *bias_p = a.bias ? a.bias + (long)(mt * TCN2_MT) * pw + slot_off : nullptr;
             for (int ch = 0; ch < chunks; ch++) {
                 const int col = ch * TCN2_CB + qd * 32 + lane;
@@ -408,6 +417,8 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 const long colbase = (long)(p / a.Pimg) * ((long)a.Mtotal * a.Pimg) + p % a.Pimg;
                 uint64_t *out_col = a.out + (colbase * 2 + poly) * pw + slot_off + (long)(a.m0 + mt * TCN2_MT) * m_stride;
                 const bool add_bias = poly == 0 && (BIAS != 0 || bias_p != nullptr);
+#pragma unroll
+              for (int s = 0; s < NS; s++) {                    // slot sl + s of the item: residue position c + s
                 if (warp == 2 && lane == 0) TCN2_TR(2, 200);    // waiting for the accumulator
                 mbar_wait(bar_tfull, acc_phase);
                 if (warp == 2 && lane == 0) TCN2_TR(2, 201);    // accumulator complete
@@ -420,13 +431,13 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                     for (int w = 0; w < TCN_CLASSES; w++)
                         tmem_ld4(tmem_base + ((uint32_t)(qd * 32) << 16) + w * TCN2_MT + mloc, S[w]);
                     tmem_ld_wait();
-                    uint64_t *op = out_col + (long)mloc * m_stride;
-                    const uint64_t *bp = bias_p + (long)mloc * pw;
+                    uint64_t *op = out_col + (long)mloc * m_stride + s;
+                    const uint64_t *bp = bias_p + (long)mloc * pw + s;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         if (mloc + i < m_valid) {                // warp uniform
                             uint64_t bias_m = 0;
-                            if constexpr (BIAS != 0) bias_m = __shfl_sync(0xffffffffu, bias_lane, mloc + i);
+                            if constexpr (BIAS != 0) bias_m = __shfl_sync(0xffffffffu, bias_lane[s], mloc + i);
                             else if (add_bias) bias_m = __ldg(bp);
                             uint64_t r;
                             if constexpr (FOLD) {
@@ -447,6 +458,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                 if (lane == 0) mbar_arrive(bar_tempty);
                 if (warp == 2 && lane == 0) TCN2_TR(2, 202);    // this warp's share of the chunk recombined and stored
                 acc_phase ^= 1;
+              }
             }
         }
     }
@@ -551,7 +563,7 @@ cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_
     return cudaGetLastError();
 }
 
-template <int BK, bool FOLD, int BIAS>
+template <int BK, bool FOLD, int BIAS, int NS = 1>
 cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -575,14 +587,14 @@ cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    auto k = tcn2_mac_kernel<BK, FOLD, BIAS>;
-    const size_t smem = Tcn2Cfg<BK>::SMEM;
+    auto k = tcn2_mac_kernel<BK, FOLD, BIAS, NS>;
+    const size_t smem = Tcn2Cfg<BK>::smem(NS);
     static DeviceOnce once;
     if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long items = (long)a.nslots * ((a.M + TCN2_MT - 1) / TCN2_MT);
+    const long items = (long)(a.nslots / NS) * ((a.M + TCN2_MT - 1) / TCN2_MT);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
     k<<<grid, TCN2_THREADS, smem, stream>>>(tmW, tmX, P, a);
     return cudaGetLastError();
@@ -614,6 +626,11 @@ cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_co
     for (int j = 0; j < a.K && fold; j++) fold = a.fold[j].ok != 0;
     // CRCNN_TCN2_BIAS=0|1 overrides where the column-major kernel takes its bias from (A/B runs; same bytes either way)
     static const int bias_env = [] { const char *e = getenv("CRCNN_TCN2_BIAS"); return e ? atoi(e) : -1; }();
+    // EXPERIMENTAL, not yet run on hardware (see the kernel's NS comment): CRCNN_TCN2_NS=4 gives the 32-byte-row kernel items of four
+    // consecutive slots, with the per-item bias (the variant that needs well-behaved stores)
+    static const int ns_env = [] { const char *e = getenv("CRCNN_TCN2_NS"); return e ? atoi(e) : 1; }();
+    if (use2 && ns_env == 4 && bk == 32 && a.nslots % 4 == 0 && a.slot0 % 4 == 0 && a.n % 4 == 0)
+        return fold ? launch_tcn2_mac_t<32, true, 1, 4>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 1, 4>(P, a, sm_count, stream);
     if (use2) {
         const int bias_var = bias_env >= 0 ? bias_env : (bk == 128 ? 1 : 0);
 #ifdef CRCNN_TCN2_TIMING   // timing builds only (make EXTRA=-DCRCNN_TCN2_TIMING OUT=../../ab/libS.so OBJDIR=../../build/objS): 2 drops the stores, results are NOT written

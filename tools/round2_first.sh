@@ -1,0 +1,21 @@
+#!/bin/bash
+# FIRST GPU call of round 2 (under gpurun, one GPU): validate and time the experimental four-slots-per-item variant of the column-major
+# limb-split kernel (tcn2_mac_kernel<32, *, 1, 4>, never run on hardware in round 1; DESIGN.md section 6 "Correction", section 9 item 1a).
+# Everything runs under `timeout`: a pipeline bug in a tcgen05 kernel hangs rather than fails.
+#   gpurun --timeout 600 -- 'bash tools/round2_first.sh r02a'
+tag=${1:-r02a}
+mkdir -p gpurun_out
+CRCNN_TCN2_NS=4 timeout 240 python -m pytest tests/test_gpu_tcn.py tests/test_gpu_golden.py tests/test_gpu_builder.py -q > gpurun_out/${tag}_ns4_tests.log 2>&1
+echo "ns4 tests rc=$?"; tail -5 gpurun_out/${tag}_ns4_tests.log
+timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns1.json 2> gpurun_out/${tag}_bench_ns1.err; echo "ns1 rc=$?"
+CRCNN_TCN2_NS=4 timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns4.json 2> gpurun_out/${tag}_bench_ns4.err; echo "ns4 rc=$?"
+CRCNN_TCN2_NS=4 CRCNN_TCN_FOLD=1 timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns4_fold.json 2> gpurun_out/${tag}_bench_ns4_fold.err; echo "ns4 fold rc=$?"
+python - <<P
+import json
+for f in ("ns1", "ns4", "ns4_fold"):
+    try:
+        d = json.load(open("gpurun_out/${tag}_bench_%s.json" % f))
+        print(f, round(d["value"], 2), round(d["ms_per_step"], 1), {k: round(v, 1) for k, v in d["per_layer_ms"].items() if "conv" in k or "fc4" in k})
+    except Exception as e:
+        print(f, "ERR", e)
+P
