@@ -259,8 +259,8 @@ template <int BK> struct Tcn2Cfg {
 // the loop broadcasts it by shuffle; 2 = as 1 with the output stores dropped (timing experiments only, results are not written).
 // Measured on B200 (PlainModel.h5, batch 8): BIAS 1 takes conv2 (BK 128) from 35.3 to 33.4 ms and conv1 (BK 32) from 42.5 to 70 ms,
 // so the launcher uses 1 for BK 128 and 0 for BK 32 (DESIGN.md section 6 on why conv1 dislikes a quicker epilogue).
-// NS: consecutive slots per work item.  1 = one slot per item (what every measured number of round 1 is).  4 (EXPERIMENTAL, not yet run
-// on hardware; CRCNN_TCN2_NS=4, BK 32 only) = the four slots of one 32-byte output sector belong to ONE item, loop order chunk-outer /
+// NS: consecutive slots per work item.  1 = one slot per item (what every measured number of round 1 is).  4 (EXPERIMENTAL: six parity tests
+// at n = 2048 and one timing run on B200 so far, conv1 36 ms against 24 ms for the shipped kernel; CRCNN_TCN2_NS=4, BK 32 only) = the four slots of one 32-byte output sector belong to ONE item, loop order chunk-outer /
 // slot-inner with the four slots' weight planes resident, so a sector's four 8-byte writes come from the same thread a few microseconds apart
 // instead of from four CTAs that have to stay in step ("Correction").
 template <int BK, bool FOLD, int BIAS, int NS>
@@ -626,7 +626,7 @@ cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_co
     for (int j = 0; j < a.K && fold; j++) fold = a.fold[j].ok != 0;
     // CRCNN_TCN2_BIAS=0|1 overrides where the column-major kernel takes its bias from (A/B runs; same bytes either way)
     static const int bias_env = [] { const char *e = getenv("CRCNN_TCN2_BIAS"); return e ? atoi(e) : -1; }();
-    // EXPERIMENTAL, not yet run on hardware (see the kernel's NS comment): CRCNN_TCN2_NS=4 gives the 32-byte-row kernel items of four
+    // EXPERIMENTAL (see the kernel's NS comment): CRCNN_TCN2_NS=4 gives the 32-byte-row kernel items of four
     // consecutive slots, with the per-item bias (the variant that needs well-behaved stores)
     static const int ns_env = [] { const char *e = getenv("CRCNN_TCN2_NS"); return e ? atoi(e) : 1; }();
     if (use2 && ns_env == 4 && bk == 32 && a.nslots % 4 == 0 && a.slot0 % 4 == 0 && a.n % 4 == 0)

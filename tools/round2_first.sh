@@ -1,6 +1,6 @@
 #!/bin/bash
 # FIRST GPU call of round 2 (under gpurun, one GPU): validate and time the experimental four-slots-per-item variant of the column-major
-# limb-split kernel (tcn2_mac_kernel<32, *, 1, 4>, never run on hardware in round 1; DESIGN.md section 6 "Correction", section 9 item 1a).
+# limb-split kernel (tcn2_mac_kernel<32, *, 1, 4>; round 1 only ran six of its parity tests and one timing; DESIGN.md section 6 "Correction", section 9 item 1a).
 # Everything runs under `timeout`: a pipeline bug in a tcgen05 kernel hangs rather than fails.
 #   gpurun --timeout 600 -- 'bash tools/round2_first.sh r02a'
 tag=${1:-r02a}
