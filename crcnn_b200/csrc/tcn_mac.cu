@@ -252,8 +252,18 @@ template <int BK> struct Tcn2Cfg {
     // ring depth: measured on B200, 40 / 9 stages instead of 8 / 6 made conv1 slower (42.6 -> 62.8 ms) and left conv2 unchanged,
     // although 39 % of the samples of the 8-stage kernel wait on the accumulator-full barrier (profiles/r01f_ncu_source_top.txt)
     static constexpr int STAGES = BK == 128 ? TCN2_STAGES_BIG : TCN2_STAGES_SMALL;
-    static constexpr size_t smem(int ns) { return 1024 + (size_t)ns * TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE + 8 * (2 * STAGES + 4) + 16; }
+    static constexpr size_t BARS = (8 * (2 * STAGES + 4) + 16 + 127) / 128 * 128;   // barriers + TMEM slot, padded so that the output staging is 128-byte aligned
+    // staged: results of the first ns - 1 slots of an item wait in shared memory, [slot][output][column] words, for the whole-sector store
+    static constexpr size_t smem(int ns, bool staged) {
+        const size_t ops = 1024 + (size_t)ns * TCN2_KBMAX * W_BLOCK + (size_t)STAGES * X_STAGE;
+        return staged ? ops + BARS + (size_t)(ns - 1) * TCN2_MT * TCN2_CB * 8 : ops + 8 * (2 * STAGES + 4) + 16;
+    }
 };
+
+// one 256-bit store: a whole 32-byte sector from one thread (STG.E.256, sm_100)
+__device__ __forceinline__ void tcn_store_sector(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 
 // BIAS: 0 = the bias residue of an output is loaded where it is added; 1 = lane m fetches the bias of output m once per item and
 // the loop broadcasts it by shuffle; 2 = as 1 with the output stores dropped (timing experiments only, results are not written).
@@ -263,7 +273,9 @@ template <int BK> struct Tcn2Cfg {
 // at n = 2048 and one timing run on B200 so far, conv1 36 ms against 24 ms for the shipped kernel; CRCNN_TCN2_NS=4, BK 32 only) = the four slots of one 32-byte output sector belong to ONE item, loop order chunk-outer /
 // slot-inner with the four slots' weight planes resident, so a sector's four 8-byte writes come from the same thread a few microseconds apart
 // instead of from four CTAs that have to stay in step ("Correction").
-template <int BK, bool FOLD, int BIAS, int NS>
+// STAGED (NS = 4 only; NOT YET RUN ON HARDWARE, CRCNN_TCN2_STAGE=1): the results of slots 0-2 wait in shared memory (each thread reads back
+// only what it wrote, no synchronisation) and slot 3 writes all four as ONE 32-byte sector per (column, output): a quarter of the sector writes.
+template <int BK, bool FOLD, int BIAS, int NS, bool STAGED = false>
 __global__ void __launch_bounds__(TCN2_THREADS, 1)
 tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX,
                 const DeviceParams *__restrict__ P, TcnMacArgs a) {
@@ -284,6 +296,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const uint32_t bar_tfull = bar_wempty + 8, bar_tempty = bar_tfull + 8;
     const uint32_t tmem_slot = bar_tempty + 8;
     volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(base_ptr + off_bar + 8 * (2 * STAGES + 4));
+    uint64_t *out_stage = reinterpret_cast<uint64_t *>(base_ptr + off_bar + Cfg::BARS);   // [NS - 1][TCN2_MT][TCN2_CB], STAGED only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = a.n;
@@ -447,7 +460,11 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
                                 if (add_bias) r = addmod(r, bias_m, mod.q);
                             }
                             if constexpr (BIAS == 2) { if (valid && r == ~0ull) *op = r; }   // never true: r < q
-                            else if (valid) *op = r;
+                            else if constexpr (STAGED && NS == 4) {
+                                uint64_t *st = out_stage + (mloc + i) * TCN2_CB + qd * 32 + lane;
+                                if (s < NS - 1) st[s * (TCN2_MT * TCN2_CB)] = r;
+                                else if (valid) tcn_store_sector(op - (NS - 1), st[0], st[TCN2_MT * TCN2_CB], st[2 * TCN2_MT * TCN2_CB], r);
+                            } else if (valid) *op = r;
                         }
                         op += m_stride;
                         bp += pw;
@@ -563,7 +580,7 @@ cudaError_t launch_tcn_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_
     return cudaGetLastError();
 }
 
-template <int BK, bool FOLD, int BIAS, int NS = 1>
+template <int BK, bool FOLD, int BIAS, int NS = 1, bool STAGED = false>
 cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm_count, cudaStream_t stream) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -587,8 +604,8 @@ cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    auto k = tcn2_mac_kernel<BK, FOLD, BIAS, NS>;
-    const size_t smem = Tcn2Cfg<BK>::smem(NS);
+    auto k = tcn2_mac_kernel<BK, FOLD, BIAS, NS, STAGED>;
+    const size_t smem = Tcn2Cfg<BK>::smem(NS, STAGED);
     static DeviceOnce once;
     if (once.first()) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -629,8 +646,12 @@ cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_co
     // EXPERIMENTAL (see the kernel's NS comment): CRCNN_TCN2_NS=4 gives the 32-byte-row kernel items of four
     // consecutive slots, with the per-item bias (the variant that needs well-behaved stores)
     static const int ns_env = [] { const char *e = getenv("CRCNN_TCN2_NS"); return e ? atoi(e) : 1; }();
-    if (use2 && ns_env == 4 && bk == 32 && a.nslots % 4 == 0 && a.slot0 % 4 == 0 && a.n % 4 == 0)
+    static const int stage_env = [] { const char *e = getenv("CRCNN_TCN2_STAGE"); return e ? atoi(e) : 0; }();
+    if (use2 && ns_env == 4 && bk == 32 && a.nslots % 4 == 0 && a.slot0 % 4 == 0 && a.n % 4 == 0) {
+        if (stage_env && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0)   // whole-sector stores: NOT YET RUN ON HARDWARE
+            return fold ? launch_tcn2_mac_t<32, true, 1, 4, true>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 1, 4, true>(P, a, sm_count, stream);
         return fold ? launch_tcn2_mac_t<32, true, 1, 4>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 1, 4>(P, a, sm_count, stream);
+    }
     if (use2) {
         const int bias_var = bias_env >= 0 ? bias_env : (bk == 128 ? 1 : 0);
 #ifdef CRCNN_TCN2_TIMING   // timing builds only (make EXTRA=-DCRCNN_TCN2_TIMING OUT=../../ab/libS.so OBJDIR=../../build/objS): 2 drops the stores, results are NOT written

@@ -7,12 +7,18 @@ tag=${1:-r02a}
 mkdir -p gpurun_out
 CRCNN_TCN2_NS=4 timeout 240 python -m pytest tests/test_gpu_tcn.py tests/test_gpu_golden.py tests/test_gpu_builder.py -q > gpurun_out/${tag}_ns4_tests.log 2>&1
 echo "ns4 tests rc=$?"; tail -5 gpurun_out/${tag}_ns4_tests.log
+# whole-sector stores from shared-memory staging (STG.256): never run on hardware in round 1
+CRCNN_TCN2_NS=4 CRCNN_TCN2_STAGE=1 timeout 240 python -m pytest tests/test_gpu_tcn.py tests/test_gpu_golden.py tests/test_gpu_builder.py -q > gpurun_out/${tag}_ns4s_tests.log 2>&1
+echo "ns4 staged tests rc=$?"; tail -5 gpurun_out/${tag}_ns4s_tests.log
+for v in "" "CRCNN_TCN2_NS=4" "CRCNN_TCN2_NS=4 CRCNN_TCN2_STAGE=1" "CRCNN_TCN2_NS=4 CRCNN_TCN2_STAGE=1 CRCNN_TCN_FOLD=1"; do
+  echo "== conv1 only: $v"; env $v timeout 40 python tools/quick_layers.py --first 0 --last 1 2>&1 | tail -1
+done
 timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns1.json 2> gpurun_out/${tag}_bench_ns1.err; echo "ns1 rc=$?"
 CRCNN_TCN2_NS=4 timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns4.json 2> gpurun_out/${tag}_bench_ns4.err; echo "ns4 rc=$?"
-CRCNN_TCN2_NS=4 CRCNN_TCN_FOLD=1 timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns4_fold.json 2> gpurun_out/${tag}_bench_ns4_fold.err; echo "ns4 fold rc=$?"
+CRCNN_TCN2_NS=4 CRCNN_TCN2_STAGE=1 timeout 120 python bench.py --no-cpu-baseline > gpurun_out/${tag}_bench_ns4_fold.json 2> gpurun_out/${tag}_bench_ns4_fold.err; echo "ns4 staged rc=$?"
 python - <<P
 import json
-for f in ("ns1", "ns4", "ns4_fold"):
+for f in ("ns1", "ns4", "ns4_fold"):   # ns4_fold.json holds the STAGED run
     try:
         d = json.load(open("gpurun_out/${tag}_bench_%s.json" % f))
         print(f, round(d["value"], 2), round(d["ms_per_step"], 1), {k: round(v, 1) for k, v in d["per_layer_ms"].items() if "conv" in k or "fc4" in k})
