@@ -69,6 +69,23 @@ int main(int argc, char **argv) {
                 if (tcn_fold_reduce(s, bias, f, m.q) != want) { printf("FOLD MISMATCH\n"); return 1; }
             }
         }
+        // three-fold reduction of arbitrary 128-bit values (modarith.cuh: reduce128_fold) for every modulus, against barrett128 and __int128
+        for (int sidx = 0; sidx < d.K + d.S; sidx++) {
+            const Mod &m = d.tab[sidx].mod;
+            const Fold128 f = fold128_make(m.q);
+            printf("fold128 %d ok %u delta %u\n", sidx, f.ok, f.delta);
+            if (!f.ok) continue;
+            for (int it = 0; it < 200000; it++) {
+                x = x * 6364136223846793005ULL + 1442695040888963407ULL;
+                y = y * 2862933555777941757ULL + 3037000493ULL;
+                U128 z;
+                const int mode = it % 8;
+                z.lo = mode == 0 ? ~0ull : mode == 1 ? 0 : mode == 2 ? m.q - 1 : mode == 3 ? m.q : x;
+                z.hi = mode == 0 ? ~0ull : mode == 1 ? 0 : mode == 2 ? 0 : mode == 3 ? (y >> (y & 63)) : mode == 4 ? (y >> 40) : y;
+                const uint64_t want = (uint64_t)(((((unsigned __int128)z.hi) << 64) | z.lo) % m.q);
+                if (reduce128_fold(z, f) != want || barrett128(z, m) != want) { printf("FOLD128 MISMATCH\n"); return 1; }
+            }
+        }
         // fractional encoder
         for (int i = 4; i >= 0; i--) {
             double vals[] = {0.0867, -3.25, 0.0, 1.0, 2.8215};

@@ -266,4 +266,57 @@ CRCNN_HD uint64_t tcn_fold_reduce(const uint32_t (&s)[13], uint64_t bias, const 
     return r >= q ? r - q : r;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// The same idea for ANY 128-bit value (the lazy sums of the BEHZ and relinearize kernels): z mod q for q = 2^k - delta, 54 <= k <= 61,
+// delta < 2^27 -- every coefficient prime and every Bsk prime of SEAL 2.3.1 (SEAL/seal/util/globals.cpp:50-74, 321-340).  Three folds of
+// the bits above k through delta (6 IMAD.WIDE in all, against 18 multiply-pipe instructions of barrett128) and one conditional
+// subtraction; canonical result, so it equals barrett128(z, mod) bit for bit.  NOT wired into any kernel yet;
+// host_selftest.cpp checks it against unsigned __int128 for every modulus of the context.
+struct Fold128 {
+    uint64_t q;
+    uint32_t delta, sh, mask, ok;   // 2^k - q, k - 32, 2^(k-32) - 1
+};
+
+inline Fold128 fold128_make(uint64_t q) {
+    typedef unsigned __int128 u128;
+    Fold128 f{};
+    f.q = q;
+    int k = 0;
+    for (uint64_t v = q; v; v >>= 1) k++;
+    if (k < 54 || k > 61) return f;
+    const uint64_t delta = (1ull << k) - q;
+    if (delta == 0 || delta >> 27) return f;
+    // worst cases: z = 2^128 - 1;  y = l + h delta  < 2^k + 2^(128-k) delta;  V = l' + h' delta;  r = l'' + g delta < 2q
+    const u128 one = 1, zmax = ~(u128)0;
+    const u128 y = ((one << k) - 1) + (zmax >> k) * delta;
+    const u128 V = ((one << k) - 1) + (y >> k) * delta;
+    const u128 g = V >> k;
+    if (y >> 112 || (y >> k) >> 64 || V >> 96 || g >> 32) return f;
+    if (g * delta + ((one << k) - 1) >= 2 * (u128)q) return f;
+    f.delta = (uint32_t)delta; f.sh = (uint32_t)(k - 32); f.mask = (1u << (k - 32)) - 1; f.ok = 1;
+    return f;
+}
+
+CRCNN_HD uint64_t reduce128_fold(U128 z, const Fold128 &f) {
+    const uint32_t z0 = (uint32_t)z.lo, z1 = (uint32_t)(z.lo >> 32), z2 = (uint32_t)z.hi, z3 = (uint32_t)(z.hi >> 32);
+    // fold 1: h = z >> k (three words), l = z mod 2^k;  y = l + h delta as words y0..y3
+    const uint32_t h0 = tcn_shr64(z1, z2, f.sh), h1 = tcn_shr64(z2, z3, f.sh), h2 = z3 >> f.sh;
+    const uint64_t l = ((uint64_t)(z1 & f.mask) << 32) | z0;
+    const uint64_t t0 = (uint64_t)h0 * f.delta + l;
+    const uint64_t u = (uint64_t)h1 * f.delta + (t0 >> 32);                 // weight 2^32
+    const uint64_t u2 = (uint64_t)h2 * f.delta + (u >> 32);                 // weight 2^64
+    const uint32_t y0 = (uint32_t)t0, y1 = (uint32_t)u, y2 = (uint32_t)u2, y3 = (uint32_t)(u2 >> 32);
+    // fold 2: h' = y >> k (two words);  V = l' + h' delta as words V0..V2
+    const uint32_t g0 = tcn_shr64(y1, y2, f.sh), g1 = tcn_shr64(y2, y3, f.sh);
+    const uint64_t l2 = ((uint64_t)(y1 & f.mask) << 32) | y0;
+    const uint64_t v = (uint64_t)g0 * f.delta + l2;
+    const uint64_t w = (uint64_t)g1 * f.delta + (v >> 32);                  // weight 2^32
+    const uint32_t V0 = (uint32_t)v, V1 = (uint32_t)w, V2 = (uint32_t)(w >> 32);
+    // fold 3
+    const uint32_t g = tcn_shr64(V1, V2, f.sh);
+    const uint64_t l3 = ((uint64_t)(V1 & f.mask) << 32) | V0;
+    const uint64_t r = (uint64_t)g * f.delta + l3;
+    return r >= f.q ? r - f.q : r;
+}
+
 }  // namespace crcnn

@@ -53,6 +53,9 @@ def test_derived_constants_match_oracle(selftest, n, t):
             j, q = int(f[1]), int(primes[int(f[1])])
             k = q.bit_length()
             assert int(f[3]) == 1 and int(f[7]) == (1 << k) - q and int(f[5]) == ((1 << k) - q) << (56 - k), ln
+        if f[0] == "fold128":
+            # reduce128_fold applies to every modulus of the context (coefficient and Bsk primes); checked against __int128 by the selftest
+            assert int(f[3]) == 1, ln
         if f[0] == "enc":
             want, _ = o.encode(float(f[1]))
             got = np.zeros(n + 1, dtype=np.uint64)
