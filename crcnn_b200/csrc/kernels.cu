@@ -619,6 +619,21 @@ plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data,
     else if (poly == 0) *x = (op == 1) ? addmod(*x, __ldg(pl + lw), mod.q) : submod(*x, __ldg(pl + lw), mod.q);
 }
 
+// Reductions of the BEHZ kernels.  Default: the generic 128-bit Barrett step.  -DCRCNN_FOLD128 (EXPERIMENTAL, not yet run on hardware;
+// DESIGN.md section 9 item 5): the three-fold reduction through the 2^k - delta shape every SEAL modulus has (modarith.cuh:
+// reduce128_fold, host-checked); its constants are derived from q on the spot (5 instructions).
+#ifdef CRCNN_FOLD128
+__device__ __forceinline__ uint64_t behz_reduce(U128 z, const Mod &m) {
+    Fold128 f;
+    const int k = 64 - __clzll((long long)m.q);
+    f.q = m.q; f.delta = (uint32_t)((1ull << k) - m.q); f.sh = (uint32_t)(k - 32); f.mask = (1u << (k - 32)) - 1; f.ok = 1;
+    return reduce128_fold(z, f);
+}
+#else
+__device__ __forceinline__ uint64_t behz_reduce(U128 z, const Mod &m) { return barrett128(z, m); }
+#endif
+__device__ __forceinline__ uint64_t behz_mulmod(uint64_t a, uint64_t b, const Mod &m) { return behz_reduce(mul128(a, b), m); }
+
 // =====================================================================================
 // BEHZ square pieces
 // =====================================================================================
@@ -649,7 +664,7 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
             // the q limbs of ext are transformed next; when the caller already holds them transformed (in_ntt) the tensor
             // stage reads them from there and nothing is written here
             if (!in_ntt) dst[(long)i * n] = x;
-            y[i] = mulmod(x, P.mt_inv_qhat[i], P.tab[i].mod);
+            y[i] = behz_mulmod(x, P.mt_inv_qhat[i], P.tab[i].mod);
             zmt += (uint32_t)y[i] * (uint32_t)P.qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
         }
     }
@@ -662,7 +677,7 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
             for (int i = 0; i < KB; i++)
                 if (i < K) mac7(acc, y[i], P.lift_a[k][i]);
             mac7(acc, (uint64_t)r, P.lift_b[k]);
-            dst[(long)(K + k) * n] = barrett128(acc7_value(acc), P.tab[K + k].mod);
+            dst[(long)(K + k) * n] = behz_reduce(acc7_value(acc), P.tab[K + k].mod);
         }
     }
 }
@@ -689,7 +704,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
     uint64_t u[KB], g[SB];
 #pragma unroll
     for (int i = 0; i < KB; i++)
-        if (i < K) u[i] = mulmod(__ldg(src + (long)i * n), P.fl_c[i], P.tab[i].mod);
+        if (i < K) u[i] = behz_mulmod(__ldg(src + (long)i * n), P.fl_c[i], P.tab[i].mod);
     uint64_t f_sk = 0;
 #pragma unroll
     for (int k = 0; k < SB; k++)
@@ -699,7 +714,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
 #pragma unroll
             for (int i = 0; i < KB; i++)
                 if (i < K) mac7(acc, u[i], P.fl_N[k][i]);
-            uint64_t v = barrett128(acc7_value(acc), P.tab[K + k].mod);
+            uint64_t v = behz_reduce(acc7_value(acc), P.tab[K + k].mod);
             if (k < L) g[k] = v; else f_sk = v;
         }
     const Mod msk = P.tab[K + L].mod;
@@ -708,7 +723,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
     for (int i = 0; i < SB; i++)
         if (i < L) mac7(acc, g[i], P.fl_P[i]);
     mac7(acc, msk.q - f_sk, P.inv_M_mod_msk);
-    const uint64_t alpha = barrett128(acc7_value(acc), msk);
+    const uint64_t alpha = behz_reduce(acc7_value(acc), msk);
     const bool centered_neg = alpha > (msk.q >> 1);  // baseconverter.cpp:547-577
     const uint64_t alpha_mag = centered_neg ? msk.q - alpha : alpha;
 #pragma unroll
@@ -719,7 +734,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
             for (int i = 0; i < SB; i++)
                 if (i < L) mac7(e, g[i], P.Mhat_mod_q[j][i]);
             mac7(e, alpha_mag, centered_neg ? P.M_mod_q[j] : P.neg_M_mod_q[j]);
-            dst[(long)j * n] = barrett128(acc7_value(e), P.tab[j].mod);
+            dst[(long)j * n] = behz_reduce(acc7_value(e), P.tab[j].mod);
         }
 }
 

@@ -28,7 +28,11 @@ def main():
     n, primes, t = bench.N_POLY, bench.PRIMES, bench.T_PLAIN
     eng = Engine(n, primes, t, device=0)
     rng = np.random.default_rng(5)
-    net = nets.Network(eng, bench.MODEL, evk=None)
+    evk = None
+    if any(l[0] == "square" for l in nets.TOPOLOGIES[bench.MODEL]["layers"][args.first:args.last]):
+        evk_words, sizes, dbc = bench.synth_evk(rng, primes, n)
+        evk = eng.evk_upload(evk_words, sizes, dbc)
+    net = nets.Network(eng, bench.MODEL, evk=evk)
     nin = nets.layer_io_counts(net.layers[args.first])[0]
     one = bench.synth_residues(rng, (nin, 2), primes, n)
     x0 = eng.upload(np.concatenate([one] * args.batch))
