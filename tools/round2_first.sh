@@ -28,7 +28,7 @@ P
 
 # BEHZ kernels with the three-fold special-prime reduction (-DCRCNN_FOLD128; built here: nvcc is on the box): parity, then the square layer alone
 make -s -C crcnn_b200/csrc EXTRA=-DCRCNN_FOLD128 OUT=../../ab/libF.so OBJDIR=../../build/objF > gpurun_out/${tag}_fold128_build.log 2>&1; echo "fold128 build rc=$?"
-CRCNN_B200_LIB=$PWD/ab/libF.so timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -q -k "square or golden or behz or chain" > gpurun_out/${tag}_fold128_tests.log 2>&1
+CRCNN_B200_LIB=$PWD/ab/libF.so timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -q -k "square or golden or chain or seal" > gpurun_out/${tag}_fold128_tests.log 2>&1
 echo "fold128 tests rc=$?"; tail -4 gpurun_out/${tag}_fold128_tests.log
 echo "== square layer, default"; timeout 60 python tools/quick_layers.py --first 4 --last 5 2>&1 | tail -1
 echo "== square layer, fold128"; CRCNN_B200_LIB=$PWD/ab/libF.so timeout 60 python tools/quick_layers.py --first 4 --last 5 2>&1 | tail -1
