@@ -619,20 +619,25 @@ plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data,
     else if (poly == 0) *x = (op == 1) ? addmod(*x, __ldg(pl + lw), mod.q) : submod(*x, __ldg(pl + lw), mod.q);
 }
 
-// Reductions of the BEHZ kernels.  Default: the generic 128-bit Barrett step.  -DCRCNN_FOLD128 (EXPERIMENTAL, not yet run on hardware;
-// DESIGN.md section 9 item 5): the three-fold reduction through the 2^k - delta shape every SEAL modulus has (modarith.cuh:
-// reduce128_fold, host-checked); its constants are derived from q on the spot (5 instructions).
-#ifdef CRCNN_FOLD128
+// Reductions of the BEHZ kernels.  FOLD: the three-fold reduction through the 2^k - delta shape every SEAL modulus on this path has
+// (coefficient primes, the 61-bit Bsk primes and m_sk; modarith.cuh: reduce128_fold, host-checked against unsigned __int128 in
+// host_selftest.cpp); its constants are derived from q on the spot (5 instructions).  The launcher takes it only when
+// fold128_make(q).ok holds for EVERY modulus of the context (caller-supplied primes of another shape get the generic 128-bit
+// Barrett step); env CRCNN_BEHZ_FOLD=0 forces Barrett.  Measured on B200 (profiles/r02a_first.txt): behz_lift 9.0 -> 7.8 ms,
+// behz_floor 21.2 -> 18.0 ms per step of the bench network; both give the canonical residue, i.e. the same bytes.
+template <bool FOLD>
 __device__ __forceinline__ uint64_t behz_reduce(U128 z, const Mod &m) {
-    Fold128 f;
-    const int k = 64 - __clzll((long long)m.q);
-    f.q = m.q; f.delta = (uint32_t)((1ull << k) - m.q); f.sh = (uint32_t)(k - 32); f.mask = (1u << (k - 32)) - 1; f.ok = 1;
-    return reduce128_fold(z, f);
+    if constexpr (FOLD) {
+        Fold128 f;
+        const int k = 64 - __clzll((long long)m.q);
+        f.q = m.q; f.delta = (uint32_t)((1ull << k) - m.q); f.sh = (uint32_t)(k - 32); f.mask = (1u << (k - 32)) - 1; f.ok = 1;
+        return reduce128_fold(z, f);
+    } else {
+        return barrett128(z, m);
+    }
 }
-#else
-__device__ __forceinline__ uint64_t behz_reduce(U128 z, const Mod &m) { return barrett128(z, m); }
-#endif
-__device__ __forceinline__ uint64_t behz_mulmod(uint64_t a, uint64_t b, const Mod &m) { return behz_reduce(mul128(a, b), m); }
+template <bool FOLD>
+__device__ __forceinline__ uint64_t behz_mulmod(uint64_t a, uint64_t b, const Mod &m) { return behz_reduce<FOLD>(mul128(a, b), m); }
 
 // =====================================================================================
 // BEHZ square pieces
@@ -644,7 +649,7 @@ __device__ __forceinline__ uint64_t behz_mulmod(uint64_t a, uint64_t b, const Mo
 // folded (lift_a, lift_b) so each residue is one lazy 128-bit sum and one Barrett reduction.
 // KT/ST > 0: K and S are compile-time (loops unroll exactly, every constant is an immediate constant-bank operand
 // because the parameter block is passed by value); KT == 0: any K <= MAXK, S <= MAXS at run time.
-template <int KT, int ST>
+template <int KT, int ST, bool FOLD>
 __global__ void __launch_bounds__(128)
 behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restrict__ in, const uint64_t *__restrict__ in_ntt,
                  uint64_t *__restrict__ ext) {
@@ -664,7 +669,7 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
             // the q limbs of ext are transformed next; when the caller already holds them transformed (in_ntt) the tensor
             // stage reads them from there and nothing is written here
             if (!in_ntt) dst[(long)i * n] = x;
-            y[i] = behz_mulmod(x, P.mt_inv_qhat[i], P.tab[i].mod);
+            y[i] = behz_mulmod<FOLD>(x, P.mt_inv_qhat[i], P.tab[i].mod);
             zmt += (uint32_t)y[i] * (uint32_t)P.qhat_mod_mt[i];  // arithmetic mod m_tilde = 2^32
         }
     }
@@ -677,7 +682,7 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
             for (int i = 0; i < KB; i++)
                 if (i < K) mac7(acc, y[i], P.lift_a[k][i]);
             mac7(acc, (uint64_t)r, P.lift_b[k]);
-            dst[(long)(K + k) * n] = behz_reduce(acc7_value(acc), P.tab[K + k].mod);
+            dst[(long)(K + k) * n] = behz_reduce<FOLD>(acc7_value(acc), P.tab[K + k].mod);
         }
     }
 }
@@ -691,7 +696,7 @@ behz_lift_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restr
 //   g_k   = f_k (M/m_k)^-1                            mod m_k, k < L
 //   alpha = (sum_k g_k (M/m_k) - f_sk) M^-1           mod m_sk, centred
 //   out_j = sum_k g_k (M/m_k) - alpha M               mod q_j      (fastbconv_sk)
-template <int KT, int ST>
+template <int KT, int ST, bool FOLD>
 __global__ void __launch_bounds__(128)
 behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__restrict__ prod, uint64_t *__restrict__ out) {
     const int n = P.n, K = KT ? KT : P.K, S = KT ? ST : P.S, L = S - 1;
@@ -704,7 +709,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
     uint64_t u[KB], g[SB];
 #pragma unroll
     for (int i = 0; i < KB; i++)
-        if (i < K) u[i] = behz_mulmod(__ldg(src + (long)i * n), P.fl_c[i], P.tab[i].mod);
+        if (i < K) u[i] = behz_mulmod<FOLD>(__ldg(src + (long)i * n), P.fl_c[i], P.tab[i].mod);
     uint64_t f_sk = 0;
 #pragma unroll
     for (int k = 0; k < SB; k++)
@@ -714,7 +719,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
 #pragma unroll
             for (int i = 0; i < KB; i++)
                 if (i < K) mac7(acc, u[i], P.fl_N[k][i]);
-            uint64_t v = behz_reduce(acc7_value(acc), P.tab[K + k].mod);
+            uint64_t v = behz_reduce<FOLD>(acc7_value(acc), P.tab[K + k].mod);
             if (k < L) g[k] = v; else f_sk = v;
         }
     const Mod msk = P.tab[K + L].mod;
@@ -723,7 +728,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
     for (int i = 0; i < SB; i++)
         if (i < L) mac7(acc, g[i], P.fl_P[i]);
     mac7(acc, msk.q - f_sk, P.inv_M_mod_msk);
-    const uint64_t alpha = behz_reduce(acc7_value(acc), msk);
+    const uint64_t alpha = behz_reduce<FOLD>(acc7_value(acc), msk);
     const bool centered_neg = alpha > (msk.q >> 1);  // baseconverter.cpp:547-577
     const uint64_t alpha_mag = centered_neg ? msk.q - alpha : alpha;
 #pragma unroll
@@ -734,7 +739,7 @@ behz_floor_kernel(const __grid_constant__ DeviceParams P, const uint64_t *__rest
             for (int i = 0; i < SB; i++)
                 if (i < L) mac7(e, g[i], P.Mhat_mod_q[j][i]);
             mac7(e, alpha_mag, centered_neg ? P.M_mod_q[j] : P.neg_M_mod_q[j]);
-            dst[(long)j * n] = behz_reduce(acc7_value(e), P.tab[j].mod);
+            dst[(long)j * n] = behz_reduce<FOLD>(acc7_value(e), P.tab[j].mod);
         }
 }
 
@@ -904,13 +909,29 @@ cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data,
 }
 
 // K and S pairs of SEAL's default parameter sets get exact-size kernels (n = 4096: 2/3, 8192: 4/5, 16384: 8/9)
-#define CRCNN_BEHZ_DISPATCH(KERNEL, GRID, ...)                                                        \
-    do {                                                                                             \
-        if (hp.K == 2 && hp.S == 3) KERNEL<2, 3><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);          \
-        else if (hp.K == 4 && hp.S == 5) KERNEL<4, 5><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);     \
-        else if (hp.K == 8 && hp.S == 9) KERNEL<8, 9><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);     \
-        else KERNEL<0, 0><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);                                 \
+#define CRCNN_BEHZ_DISPATCH(KERNEL, GRID, ...)                                                                  \
+    do {                                                                                                       \
+        if (behz_fold_ok(hp)) {                                                                                \
+            if (hp.K == 2 && hp.S == 3) KERNEL<2, 3, true><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);          \
+            else if (hp.K == 4 && hp.S == 5) KERNEL<4, 5, true><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);     \
+            else if (hp.K == 8 && hp.S == 9) KERNEL<8, 9, true><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);     \
+            else KERNEL<0, 0, true><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);                                 \
+        } else {                                                                                               \
+            if (hp.K == 2 && hp.S == 3) KERNEL<2, 3, false><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);         \
+            else if (hp.K == 4 && hp.S == 5) KERNEL<4, 5, false><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);    \
+            else if (hp.K == 8 && hp.S == 9) KERNEL<8, 9, false><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);    \
+            else KERNEL<0, 0, false><<<GRID, 128, 0, stream>>>(hp, __VA_ARGS__);                                \
+        }                                                                                                      \
     } while (0)
+
+// every modulus the BEHZ kernels reduce by (coefficient primes, Bsk primes incl. m_sk) has the 2^k - delta shape reduce128_fold needs
+static bool behz_fold_ok(const DeviceParams &hp) {
+    static const int env = [] { const char *e = getenv("CRCNN_BEHZ_FOLD"); return e ? atoi(e) : 1; }();
+    if (!env) return false;
+    for (int i = 0; i < hp.K + hp.S; i++)
+        if (!fold128_make(hp.tab[i].mod.q).ok) return false;
+    return true;
+}
 
 cudaError_t launch_behz_lift(const DeviceParams &hp, int n, const uint64_t *in, const uint64_t *in_ntt, long count, uint64_t *ext,
                                 cudaStream_t stream) {

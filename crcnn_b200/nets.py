@@ -105,14 +105,17 @@ class Network:
         w = weights if weights is not None else load_weights(model)
         self.evk = evk
         self.packs = {}
+        self.params = {}   # the float32 values every pack was encoded from (what a checker re-encodes)
         for layer in self.layers:
             kind, name = layer[0], layer[1]
             if kind in ("conv", "fc"):
+                self.params[name] = (w[name + ".weight"].ravel().astype(np.float32), w[name + ".bias"].ravel().astype(np.float32))
                 self.packs[name] = (eng.plain_encode(w[name + ".weight"].ravel()), eng.plain_encode(w[name + ".bias"].ravel()))
             elif kind == "bn":
                 # CnnBuilder::buildBatchNormLayer, cnnBuilder.cpp:89-105 (float32 arithmetic as in the reference)
                 var = w[name + ".running_var"].astype(np.float32)
                 invstd = (1.0 / np.sqrt(var.astype(np.float64) + 0.00001)).astype(np.float32)  # double arithmetic, float result: cnnBuilder.cpp:101
+                self.params[name] = (w[name + ".running_mean"].astype(np.float32), invstd)
                 self.packs[name] = (eng.plain_encode(w[name + ".running_mean"]), eng.plain_encode(invstd))
             elif kind == "avgpool":
                 xf, yf = layer[7], layer[8]
