@@ -474,6 +474,16 @@ def main_b200(args, rank, world, local_rank):
     # integer pipe: 64x64->128-bit multiply-accumulates per second of a register-only loop, measured in this run
     probe_ms = eng.probe_imad(148 * 8, 256, 4096)
     probe_rate = 148 * 8 * 256 * 4096 * 8 / (probe_ms / 1000.0)
+    # hard denominators, measured in this run on this device (crcnn_probe_pipe): the IMAD.WIDE issue rate (independent chains, nothing
+    # else in the loop) and the kind::i8 UMMA rate with smem-resident operands and no epilogue
+    eng.probe_pipe(1, 148 * 8, 256, 512); eng.probe_pipe(2, 148, 128, 256)            # warm
+    wide_rate, _ = eng.probe_pipe(1, 148 * 8, 256, 4096)                               # IMAD.WIDE thread-instructions / s
+    umma_rate, _ = eng.probe_pipe(2, 148, 128, 4096)                                   # int8 MACs / s
+    counters = {}  # ncu counters of each class's main kernel from the committed capture of this round (tools/make_traffic.py)
+    try:
+        counters = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("counters", {})
+    except Exception:
+        pass
     traffic = {}   # measured DRAM bytes per launch of each class's main kernel, from the committed ncu capture (tools/make_traffic.py)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -483,6 +493,9 @@ def main_b200(args, rank, world, local_rank):
     MAC_CLASSES = ("weighted_sum_mac", "behz_lift", "behz_floor_sk")
     BFLY_CLASSES = ("ntt_forward", "ntt_inverse", "plain_expand_ntt", "relinearize")
     BFLY_MACS = 2.5  # one Harvey butterfly = 10 IMAD-pipe instructions (mulhi64 + two mullo64) = 2.5 split-accumulator MACs of 4
+    # IMAD-pipe instruction slots per counted operation (an IMAD / IMAD.WIDE occupies the pipe 2 clk per warp, an IMAD.HI 4):
+    # 64x64->128 MAC = 4 IMAD.WIDE; 64-bit Harvey butterfly = mulhi64 (4) + two mullo64 (3 each) = 10; 32-bit butterfly = IMAD.HI (2) + 2 IMAD = 4
+    IMAD_SLOTS = {"mac": 4.0, "bfly64": 10.0, "bfly32": 4.0}
     kernel_ms, classes = {}, {}
     for name, (launches_c, ms_c) in prof.items():
         if not launches_c:
@@ -494,39 +507,45 @@ def main_b200(args, rank, world, local_rank):
                "hbm_gbs": byts / sec / 1e9 if sec else None, "hbm_frac": byts / sec / 1e9 / hbm_peak if sec else None}
         if name == "weighted_sum_tc_i8":
             ent["int8_tops"] = 2 * ops / sec / 1e12
-            ent["tensor_frac"] = ent["int8_tops"] / (2 * bf16_peak)
+            ent["tensor_frac"] = ops / sec / umma_rate                       # vs the UMMA kind::i8 rate measured in this run
+            ent["tensor_frac_vs_2x_bf16"] = ent["int8_tops"] / (2 * bf16_peak)   # round 1's derived denominator, kept for comparison
         elif name in MAC_CLASSES:
             ent["gmac_s"] = ops / sec / 1e9
-            ent["int_pipe_frac"] = ops / sec / probe_rate
+            ent["int_pipe_frac"] = IMAD_SLOTS["mac"] * ops / sec / wide_rate
+            ent["int_pipe_frac_vs_mac_chain"] = ops / sec / probe_rate
         elif name in BFLY_CLASSES:
             ent["gbutterfly_s"] = ops / sec / 1e9
-            ent["int_pipe_frac"] = BFLY_MACS * ops / sec / probe_rate
+            ent["int_pipe_frac"] = IMAD_SLOTS["bfly64"] * ops / sec / wide_rate
+            ent["int_pipe_frac_vs_mac_chain"] = BFLY_MACS * ops / sec / probe_rate
         elif name == "relinearize_u32":
-            # relinearize through 30-bit auxiliary primes (relin32.cuh): ops = 32-bit Harvey butterflies, each 1 IMAD.HI + 2 IMAD
-            # = 0.75 of the probe's 4-instruction MAC; the transforms are bound by instruction issue and the L1 data pipe (ncu)
+            # relinearize through 30-bit auxiliary primes (relin32.cuh): ops = 32-bit Harvey butterflies (1 IMAD.HI + 2 IMAD)
             ent["gbutterfly32_s"] = ops / sec / 1e9
-            ent["int_pipe_frac"] = 0.75 * ops / sec / probe_rate
+            ent["int_pipe_frac"] = IMAD_SLOTS["bfly32"] * ops / sec / wide_rate
+            ent["int_pipe_frac_vs_mac_chain"] = 0.75 * ops / sec / probe_rate
+        if name in counters:
+            ent["ncu"] = counters[name]      # pipe_tensor / pipe_fma / issue_active ... of the class's main kernel (committed capture)
         classes[name] = ent
         kernel_ms[name] = {"launches_per_step": ent["launches_per_step"], "ms_per_step": ent["ms_per_step"]}
     dom = max(classes.items(), key=lambda kv: kv[1]["ms_per_step"])
     dname, d = dom
     avg_launch_ms = d["ms_per_step"] / d["launches_per_step"]
     if dname == "weighted_sum_tc_i8":
-        roofline = {"kernel": dname, "bound": "tensor", "achieved": d["int8_tops"], "peak": 2 * bf16_peak, "unit": "TFLOP/s",
+        roofline = {"kernel": dname, "bound": "tensor", "achieved": d["int8_tops"], "peak": 2 * umma_rate / 1e12, "unit": "TFLOP/s",
                     "frac": d["tensor_frac"],
-                    "peak_source": "2 x measured sustained bf16 (MEASURED_PEAKS.json): kind::i8 runs at twice the bf16 rate; "
-                                   "achieved counts 2 ops per int8 multiply-accumulate of the unpadded GEMM"}
+                    "peak_source": "tcgen05.mma kind::i8 M128xN256xK32 issued back to back from shared-memory operands on all SMs, measured in "
+                                   "this run (crcnn_probe_pipe which=2); achieved counts 2 ops per int8 multiply-accumulate of the unpadded GEMM",
+                    "frac_vs_2x_measured_bf16": d["tensor_frac_vs_2x_bf16"]}
     else:
         roofline = {"kernel": dname, "bound": "hbm", "achieved": d["hbm_gbs"], "peak": hbm_peak, "unit": "GB/s",
                     "frac": d["hbm_frac"], "peak_source": peak_src}
         if "int_pipe_frac" in d:
-            roofline["int_pipe"] = {"frac": d["int_pipe_frac"], "probe_gmac_s": probe_rate / 1e9,
-                                    "note": "the binding resource of this kernel: 64-bit integer multiply pipe; peak = register-only "
-                                            "64x64->128 multiply-accumulate loop measured in this run"
-                                            + ("; one butterfly counted as %.1f MACs" % BFLY_MACS if dname in BFLY_CLASSES else "")}
+            roofline["int_pipe"] = {"frac": d["int_pipe_frac"], "imad_wide_ginstr_s": wide_rate / 1e9,
+                                    "note": "the binding resource of this kernel: the IMAD pipe; peak = independent IMAD.WIDE.U32 chains "
+                                            "measured in this run; counted IMAD-pipe slots per operation: %r" % (IMAD_SLOTS,)}
     roofline.update({"traffic": traffic.get(dname), "avg_launch_ms": avg_launch_ms, "launches_per_step": d["launches_per_step"],
                      "share_of_step": d["share_of_step"], "alg_bytes_per_launch": d["alg_gb_per_step"] * 1e9 / d["launches_per_step"],
-                     "int_pipe_probe_gmac_s": probe_rate / 1e9, "classes": classes})
+                     "int_pipe_probe_gmac_s": probe_rate / 1e9, "imad_wide_probe_ginstr_s": wide_rate / 1e9,
+                     "umma_i8_probe_tops": 2 * umma_rate / 1e12, "classes": classes})
     launches = int(sum(v[0] for v in prof.values()))
 
     line = {

@@ -86,7 +86,7 @@ struct crcnn_ctx {
     int tap_mode = 1;                // 1: avg-pool / batch-norm on coefficient-form inputs multiply in the coefficient domain (tapmul_kernel); env CRCNN_TAP
     int relin_mode = 1;              // 1: relinearize through 30-bit auxiliary primes when exact for the parameters (relin32.cuh); 0: 64-bit transforms
     int tcn_mode = 1;                // 1: weighted sums whose staged weights fit the weight cache run as the NTT-domain limb-split GEMM (tcn_mac.cuh)
-    int tcn_fold = 0;                // 1: the limb-split GEMM reduces its class sums through the 2^k - delta shape of the primes when they have it (modarith.cuh: tcn_fold_reduce), 0: 128-bit recombination + Barrett; same bytes, measured equally fast on B200 (the epilogue is not instruction bound); env CRCNN_TCN_FOLD
+    int tcn_fold = 1;                // 1 (default): the limb-split GEMM reduces its class sums through the 2^k - delta shape of the primes when every prime has it (modarith.cuh: tcn_fold_reduce), 0: 128-bit recombination + Barrett; same bytes; env CRCNN_TCN_FOLD
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
@@ -1329,9 +1329,9 @@ int crcnn_prof_get_work(crcnn_ctx *ctx, int cls, double *bytes, double *ops) {
     return CRCNN_OK;
 }
 
-int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms) {
+int crcnn_probe_pipe(crcnn_ctx *ctx, int which, int blocks, int threads, int iters, double *ms, double *ops) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
-    REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && ms, "bad probe arguments");
+    REQUIRE(which >= 0 && which <= 2 && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && ms, "bad probe arguments");
     CU(cudaSetDevice(ctx->device));
     uint64_t *sink = nullptr;
     int rc = dev_alloc(ctx, 8, (void **)&sink);
@@ -1340,16 +1340,23 @@ int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double 
     CU(cudaEventCreate(&a));
     CU(cudaEventCreate(&b));
     ctx->launches[KC_PROBE]++;
+    double work = 0;
     CU(cudaEventRecord(a, ctx->stream));
-    CU(launch_imad_probe(blocks, threads, iters, sink, ctx->stream));
+    if (which == 0) { CU(launch_imad_probe(blocks, threads, iters, sink, ctx->stream)); work = (double)blocks * threads * iters * 8.0; }
+    else if (which == 1) { CU(launch_imad_wide_probe(blocks, threads, iters, sink, ctx->stream)); work = (double)blocks * threads * iters * 16.0; }
+    else CU(launch_umma_i8_probe(blocks, iters, &work, ctx->stream));
     CU(cudaEventRecord(b, ctx->stream));
     CU(cudaEventSynchronize(b));
     float t = 0;
     cudaEventElapsedTime(&t, a, b);
     *ms = t;
+    if (ops) *ops = work;
     cudaEventDestroy(a); cudaEventDestroy(b);
     dev_free(ctx, sink);
     return CRCNN_OK;
+}
+int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms) {
+    return crcnn_probe_pipe(ctx, 0, blocks, threads, iters, ms, nullptr);
 }
 
 }  // extern "C"

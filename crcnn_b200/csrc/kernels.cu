@@ -1012,4 +1012,30 @@ cudaError_t launch_imad_probe(int blocks, int threads, int iters, uint64_t *sink
     return cudaGetLastError();
 }
 
+// =====================================================================================
+// IMAD.WIDE issue-rate probe: 16 independent 32x32+64 -> 64-bit multiply-add chains per thread, nothing else in the loop.
+// This is the ceiling of the pipe every 64-bit modular multiplication on this path runs on (a 64x64->128-bit product is 4
+// IMAD.WIDE.U32); the dependent-carry MAC probe above reaches well under half of it.  iters * 16 IMAD.WIDE per thread.
+// =====================================================================================
+__global__ void imad_wide_probe_kernel(int iters, uint64_t *sink) {
+    uint32_t a = 0x9E3779B9u * (threadIdx.x + 1), b = 0x85EBCA6Bu + blockIdx.x;
+    uint64_t acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = (uint64_t)i * 0x100000001ull;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"(a + i), "r"(b));
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s ^= acc[i];
+    if (s == 0x1234567) sink[0] = s;
+}
+
+cudaError_t launch_imad_wide_probe(int blocks, int threads, int iters, uint64_t *sink, cudaStream_t stream) {
+    imad_wide_probe_kernel<<<blocks, threads, 0, stream>>>(iters, sink);
+    return cudaGetLastError();
+}
+
 }  // namespace crcnn

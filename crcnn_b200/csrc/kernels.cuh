@@ -120,5 +120,6 @@ cudaError_t launch_strip_pad(const uint64_t *src_padded, uint64_t *dst, long row
 // ---- integer-pipe roofline probe: register-only 64x64->128 multiply-accumulate loop.
 // Returns nothing; caller times it.  total MACs = blocks * threads * iters * 8.
 cudaError_t launch_imad_probe(int blocks, int threads, int iters, uint64_t *sink, cudaStream_t stream);
+cudaError_t launch_imad_wide_probe(int blocks, int threads, int iters, uint64_t *sink, cudaStream_t stream);
 
 }  // namespace crcnn

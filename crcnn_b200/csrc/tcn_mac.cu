@@ -643,12 +643,15 @@ cudaError_t launch_tcn_mac(const DeviceParams *P, const TcnMacArgs &a, int sm_co
     for (int j = 0; j < a.K && fold; j++) fold = a.fold[j].ok != 0;
     // CRCNN_TCN2_BIAS=0|1 overrides where the column-major kernel takes its bias from (A/B runs; same bytes either way)
     static const int bias_env = [] { const char *e = getenv("CRCNN_TCN2_BIAS"); return e ? atoi(e) : -1; }();
-    // EXPERIMENTAL (see the kernel's NS comment): CRCNN_TCN2_NS=4 gives the 32-byte-row kernel items of four
-    // consecutive slots, with the per-item bias (the variant that needs well-behaved stores)
-    static const int ns_env = [] { const char *e = getenv("CRCNN_TCN2_NS"); return e ? atoi(e) : 1; }();
-    static const int stage_env = [] { const char *e = getenv("CRCNN_TCN2_STAGE"); return e ? atoi(e) : 0; }();
+    // The 32-byte-row kernel (fan-in <= 32: conv1) takes items of FOUR consecutive slots with the per-item bias, stages slots 0-2 of an
+    // item in shared memory and writes whole 32-byte sectors (one STG.E.256 per (column, output)): a sector is then completed by ONE
+    // thread instead of four CTAs that have to stay in step.  Measured on B200 (profiles/r02a_first.txt): conv1's
+    // GEMM 23.6 -> 21.3 ms per step (20.1 with the folded reduction).  CRCNN_TCN2_NS=1 selects the one-slot kernel, CRCNN_TCN2_STAGE=0
+    // the four-slot kernel with 8-byte stores (A/B runs; same bytes).
+    static const int ns_env = [] { const char *e = getenv("CRCNN_TCN2_NS"); return e ? atoi(e) : 4; }();
+    static const int stage_env = [] { const char *e = getenv("CRCNN_TCN2_STAGE"); return e ? atoi(e) : 1; }();
     if (use2 && ns_env == 4 && bk == 32 && a.nslots % 4 == 0 && a.slot0 % 4 == 0 && a.n % 4 == 0) {
-        if (stage_env && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0)   // whole-sector stores: NOT YET RUN ON HARDWARE
+        if (stage_env && (reinterpret_cast<uintptr_t>(a.out) & 31) == 0)
             return fold ? launch_tcn2_mac_t<32, true, 1, 4, true>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 1, 4, true>(P, a, sm_count, stream);
         return fold ? launch_tcn2_mac_t<32, true, 1, 4>(P, a, sm_count, stream) : launch_tcn2_mac_t<32, false, 1, 4>(P, a, sm_count, stream);
     }

@@ -75,6 +75,7 @@ SYMBOLS = [
     ("crcnn_prof_get", _I, [_vp, _I, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_double)]),
     ("crcnn_prof_get_work", _I, [_vp, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("crcnn_probe_imad", _I, [_vp, _I, _I, _I, C.POINTER(C.c_double)]),
+    ("crcnn_probe_pipe", _I, [_vp, _I, _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 
 _lib = None
@@ -338,6 +339,12 @@ class Engine:
             self._chk(self.lib.crcnn_prof_get_work(self.h, i, C.byref(b), C.byref(o)))
             out[name.value.decode()] = (b.value, o.value)
         return out
+
+    def probe_pipe(self, which, blocks, threads, iters):
+        """(ops per second, ms) of roofline probe `which` (0: 64x64->128 MAC chain, 1: IMAD.WIDE issue rate, 2: UMMA kind::i8)."""
+        ms, ops = C.c_double(), C.c_double()
+        self._chk(self.lib.crcnn_probe_pipe(self.h, which, blocks, threads, iters, C.byref(ms), C.byref(ops)))
+        return ops.value / (ms.value / 1000.0), ms.value
 
     def probe_imad(self, blocks, threads, iters):
         ms = C.c_double()

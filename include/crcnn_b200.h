@@ -82,7 +82,7 @@ int crcnn_ctx_set_limb_split_mode(crcnn_ctx *ctx, int mode);
 /* How the limb-split GEMM turns its 13 class sums into a residue: mode 1 (default) uses the shape of SEAL's coefficient primes,
  * q = 2^k - delta with delta < 2^25 (SEAL/seal/util/globals.cpp:50-74): the classes are gathered into four sums, 2^56 and the bits
  * above k are folded through 2^56 mod q and delta, one conditional subtraction (crcnn_b200/csrc/modarith.cuh: tcn_fold_reduce); it
- * applies when every prime of the context has that shape, otherwise, or with mode 0, the classes are recombined into a 128-bit
+ * applies when every prime of the context has that shape (the engine checks: tcn_fold_make(q).ok), otherwise, or with mode 0, the classes are recombined into a 128-bit
  * integer and reduced by the generic Barrett step (barrett_reduce_128, SEAL/seal/util/uintarithsmallmod.h:137-176).  Both produce
  * the canonical residue, i.e. the same bytes.  Env CRCNN_TCN_FOLD sets the initial mode. */
 int crcnn_ctx_set_limb_split_reduction(crcnn_ctx *ctx, int mode);
@@ -215,6 +215,14 @@ int crcnn_prof_get_work(crcnn_ctx *ctx, int cls, double *bytes, double *ops);
 /* Register-only 64x64->128-bit multiply-accumulate probe (integer-pipe roofline): runs
  * blocks*threads*iters*8 MACs and returns the elapsed device time in ms. */
 int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms);
+/* Roofline denominators measured on the device the context is bound to, at the clocks of the run ("integer-pipe
+ * peak must be measured on the box"); *ops = operations issued, *ms = elapsed device time.
+ *   which 0: the dependent 64x64->128-bit multiply-accumulate chain above          (ops = multiply-accumulates)
+ *   which 1: independent IMAD.WIDE.U32 chains, nothing else in the loop: the issue-rate ceiling of the pipe every 64-bit
+ *            modular product runs on (4 IMAD.WIDE per 64x64 product)                (ops = IMAD.WIDE thread-instructions)
+ *   which 2: tcgen05.mma kind::i8, M128 x N256 x K32, operands resident in shared memory, no epilogue, one CTA per SM
+ *            (blocks = SM count, threads ignored)                                   (ops = int8 multiply-accumulates) */
+int crcnn_probe_pipe(crcnn_ctx *ctx, int which, int blocks, int threads, int iters, double *ms, double *ops);
 
 #ifdef __cplusplus
 }

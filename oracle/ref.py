@@ -174,6 +174,28 @@ class Ref:
                                           _p(out, _u64p)))
         return out
 
+    def conv_timed(self, x, xd, yd, zd, xs, ys, xf, yf, nf, w, b, th=8, reps=1):
+        """(encode_s, first_forward_s, steady_forward_s): ONE layer object, weights transformed in its first forward
+        (convolutionalLayer.cpp:149-168) and reused by the `reps` later ones -- what the reference pays per image."""
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        w = np.ascontiguousarray(w, dtype=np.float32).ravel()
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        times = np.zeros(3, dtype=np.float64)
+        self.lib.ref_conv_forward_timed.argtypes = [_u64p] + [C.c_int] * 9 + [_f32p, _f32p, C.c_int, _f64p, _u64p]
+        self._chk(self.lib.ref_conv_forward_timed(_p(x, _u64p), xd, yd, zd, xs, ys, xf, yf, nf, th, _p(w, _f32p), _p(b, _f32p),
+                                                  reps, _p(times, _f64p), None))
+        return tuple(float(t) for t in times)
+
+    def fc_timed(self, x, in_dim, out_dim, w, b, th=8, reps=1):
+        x = np.ascontiguousarray(x, dtype=np.uint64)
+        w = np.ascontiguousarray(w, dtype=np.float32).ravel()
+        b = np.ascontiguousarray(b, dtype=np.float32).ravel()
+        times = np.zeros(3, dtype=np.float64)
+        self.lib.ref_fc_forward_timed.argtypes = [_u64p, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_int, _f64p, _u64p]
+        self._chk(self.lib.ref_fc_forward_timed(_p(x, _u64p), in_dim, out_dim, th, _p(w, _f32p), _p(b, _f32p), reps,
+                                                _p(times, _f64p), None))
+        return tuple(float(t) for t in times)
+
     def fc3d(self, x, zd, xd, yd, out_dim, w, b, th=8):
         x = np.ascontiguousarray(x, dtype=np.uint64)
         w = np.ascontiguousarray(w, dtype=np.float32).ravel()

@@ -13,6 +13,7 @@
 // is a deterministic UniformRandomGeneratorFactory so that keys and
 // encryptions are reproducible (EncryptionParameters::set_random_generator,
 // SEAL/seal/encryptionparams.h:223).
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -404,6 +405,64 @@ int ref_square_forward(const uint64_t *in, int zd, int xd, int yd, int th_count,
     return guarded([&] {
         SquareLayer layer("square", th_count);
         put_tensor(layer.forward(make_tensor(in, zd, xd, yd)), out);
+    });
+}
+
+// ---- steady-state timing of the weighted-sum layers.  The reference encodes its weights once (CnnBuilder) and transforms them to
+// NTT form lazily inside the FIRST forward (transform_kernel_to_ntt, CrCNN/src/convolutionalLayer.cpp:149-168, 195;
+// fullyConnectedLayer.cpp:129-131); every later image skips both.  times[0] = FractionalEncoder::encode of all weights,
+// times[1] = first forward (includes the weight NTTs), times[2] = mean of `reps` further forwards of the SAME layer object
+// (what the reference pays per image).  Seconds, wall clock.  out may be null.
+static double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+int ref_conv_forward_timed(const uint64_t *in, int xd, int yd, int zd, int xs, int ys, int xf, int yf, int nf,
+                           int th_count, const float *w, const float *b, int reps, double *times, uint64_t *out) {
+    return guarded([&] {
+        double t0 = now_s();
+        plaintext4D ew(nf, plaintext3D(zd, plaintext2D(xf, vector<Plaintext>(yf))));
+        vector<Plaintext> eb(nf);
+        size_t k = 0;
+        for (int n = 0; n < nf; n++) {
+            for (int z = 0; z < zd; z++)
+                for (int i = 0; i < xf; i++)
+                    for (int j = 0; j < yf; j++) ew[n][z][i][j] = fraencoder->encode(w[k++]);
+            eb[n] = fraencoder->encode(b[n]);
+        }
+        ConvolutionalLayer layer("conv", xd, yd, zd, xs, ys, xf, yf, nf, th_count, ew, eb);
+        double t1 = now_s();
+        ciphertext3D x = make_tensor(in, zd, xd, yd);
+        ciphertext3D y = layer.forward(x);
+        double t2 = now_s();
+        for (int r = 0; r < reps; r++) y = layer.forward(x);
+        double t3 = now_s();
+        times[0] = t1 - t0; times[1] = t2 - t1; times[2] = reps > 0 ? (t3 - t2) / reps : 0.0;
+        if (out) put_tensor(y, out);
+    });
+}
+
+int ref_fc_forward_timed(const uint64_t *in, int in_dim, int out_dim, int th_count, const float *w, const float *b,
+                         int reps, double *times, uint64_t *out) {
+    return guarded([&] {
+        double t0 = now_s();
+        plaintext2D ew(out_dim, vector<Plaintext>(in_dim));
+        vector<Plaintext> eb(out_dim);
+        size_t k = 0;
+        for (int i = 0; i < out_dim; i++) {
+            for (int j = 0; j < in_dim; j++) ew[i][j] = fraencoder->encode(w[k++]);
+            eb[i] = fraencoder->encode(b[i]);
+        }
+        FullyConnectedLayer layer("fc", in_dim, out_dim, th_count, ew, eb);
+        double t1 = now_s();
+        ciphertext3D x = make_tensor(in, 1, in_dim, 1);
+        ciphertext3D y = layer.forward(x);
+        double t2 = now_s();
+        for (int r = 0; r < reps; r++) y = layer.forward(x);
+        double t3 = now_s();
+        times[0] = t1 - t0; times[1] = t2 - t1; times[2] = reps > 0 ? (t3 - t2) / reps : 0.0;
+        if (out) put_tensor(y, out);
     });
 }
 

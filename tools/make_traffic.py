@@ -12,12 +12,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CLASS_OF = {"ntt_fwd_digits_kernel": "relinearize", "r32_digits_kernel": "relinearize_u32", "ntt_inv_tensor_kernel": "ntt_inverse", "ntt_inv_kernel": "ntt_inverse_plain", "ntt_fwd_kernel": "ntt_forward",
             "tc_mac_kernel": "weighted_sum_tc_i8", "tcn2_mac_kernel": "weighted_sum_tcn_i8", "tcn_mac_kernel": "weighted_sum_tcn_i8_rowmajor", "tcn_split_kernel": "tcn_plane_split",
             "behz_floor_kernel": "behz_floor_sk", "pool_kernel": "pool_sum", "bn_kernel": "batch_norm", "mac_kernel": "weighted_sum_mac"}
+# ncu counters bench.py prints next to every roofline fraction (percent of peak while the kernel was active)
+COUNTERS = {"pipe_tensor_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "pipe_fma_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+            "pipe_alu_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+            "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "l2_hit_pct": "lts__t_sector_hit_rate.pct"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def main():
     tag = sys.argv[1]
-    out = {}
+    out, counters = {}, {}
     for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", tag + "_*_raw.csv"))):
         rows = list(csv.reader(open(path)))
         h, u = rows[0], rows[1]
@@ -31,12 +39,18 @@ def main():
                 i = h.index(m)
                 tot += float(r[i].replace(",", "")) * UNIT.get(u[i], 1.0)
             d = float(r[h.index("gpu__time_duration.sum")].replace(",", ""))
+            cls = CLASS_OF[key]
+            cn = counters.setdefault(cls, {"kernel": key})
+            for short, m in COUNTERS.items():
+                if m in h and r[h.index(m)] not in ("", "n/a"):
+                    cn[short] = round(float(r[h.index(m)].replace(",", "")), 2)
             ent = out.setdefault(CLASS_OF[key], {"kernel": key, "launches": []})
             ent["launches"].append({"dram_bytes": tot, "duration": d, "duration_unit": u[h.index("gpu__time_duration.sum")],
                                     "grid": r[h.index("launch__grid_size")]})
     for ent in out.values():
         ent["dram_bytes_per_launch"] = sum(l["dram_bytes"] for l in ent["launches"]) / len(ent["launches"])
-    json.dump({"source": "ncu --set full --clock-control none, one forward at batch 8 (tools/gpu_profile.sh %s)" % tag, "classes": out},
+    json.dump({"source": "ncu --set full --clock-control none, one forward at batch 8 (tools/gpu_profile.sh %s)" % tag, "classes": out,
+               "counters": counters},
               open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     print(json.dumps({k: v["dram_bytes_per_launch"] for k, v in out.items()}, indent=1))
 
