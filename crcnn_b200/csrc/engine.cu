@@ -1331,7 +1331,7 @@ int crcnn_prof_get_work(crcnn_ctx *ctx, int cls, double *bytes, double *ops) {
 
 int crcnn_probe_pipe(crcnn_ctx *ctx, int which, int blocks, int threads, int iters, double *ms, double *ops) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
-    REQUIRE(which >= 0 && which <= 2 && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && ms, "bad probe arguments");
+    REQUIRE(which >= 0 && which <= 4 && blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && ms, "bad probe arguments");
     CU(cudaSetDevice(ctx->device));
     uint64_t *sink = nullptr;
     int rc = dev_alloc(ctx, 8, (void **)&sink);
@@ -1344,7 +1344,7 @@ int crcnn_probe_pipe(crcnn_ctx *ctx, int which, int blocks, int threads, int ite
     CU(cudaEventRecord(a, ctx->stream));
     if (which == 0) { CU(launch_imad_probe(blocks, threads, iters, sink, ctx->stream)); work = (double)blocks * threads * iters * 8.0; }
     else if (which == 1) { CU(launch_imad_wide_probe(blocks, threads, iters, sink, ctx->stream)); work = (double)blocks * threads * iters * 16.0; }
-    else CU(launch_umma_i8_probe(blocks, iters, &work, ctx->stream));
+    else CU(launch_umma_i8_probe(blocks, iters, which - 2, &work, ctx->stream));
     CU(cudaEventRecord(b, ctx->stream));
     CU(cudaEventSynchronize(b));
     float t = 0;

@@ -211,7 +211,8 @@ struct Tc2Cfg {
     static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE + 4 * TC_SCRATCH_WARP + 16 * STAGES + 32 + 16;
 };
 
-template <int PLANES>
+// DBG (timing builds only, results wrong by construction): 1 = epilogue does nothing but the barrier hand-shake, 2 = no MMAs are issued
+template <int PLANES, int DBG = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const DeviceParams *__restrict__ P, TcMacArgs a) {
@@ -268,6 +269,7 @@ tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int mt = min(2 * pt + (int)rank, m_tiles - 1);   // an odd tile count: the last pair's second half recomputes the last tile (never stored)
                 for (int u = 0; u < NU; u++)
                     for (int kb = 0; kb < KB; kb++) {
+                        if (DBG == 3) continue;
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, 2 * C::STAGE);
                         tma_load_2d_pair(sA + stage * TC_A_STAGE, &tmA, bar_full + 8 * stage, kb * TC_BK, mt * TC_BM);
@@ -288,12 +290,13 @@ tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * TC_ACC_STRIDE;
                     for (int kb = 0; kb < KB; kb++) {
-                        mbar_wait(bar_full + 8 * stage, phase);
+                        if (DBG != 3) mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
                         const uint64_t da = umma_desc_sw128(sA + stage * TC_A_STAGE), db = umma_desc_sw128(sB + stage * C::B_STAGE);
                         const int nks = min(4, ksteps - kb * 4);
-                        for (int ks = 0; ks < nks; ks++)
-                            umma_i8_pair(d_tmem, da + 2 * ks, db + 2 * ks, IDESC, (kb | ks) != 0);
+                        if (DBG != 2)
+                            for (int ks = 0; ks < nks; ks++)
+                                umma_i8_pair(d_tmem, da + 2 * ks, db + 2 * ks, IDESC, (kb | ks) != 0);
                         umma_commit_pair(bar_empty + 8 * stage);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -305,7 +308,6 @@ tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
         // ===================================================================== epilogue (both CTAs, own row tile)
         const int lg = warp & 3;
-        int *S = reinterpret_cast<int *>(base_ptr + off_scratch + (warp - 2) * TC_SCRATCH_WARP);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long item = cluster; item < items; item += nclusters) {
@@ -330,24 +332,22 @@ tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int lo[PLANES], hi[PLANES];
 #pragma unroll
                 for (int l = 0; l < PLANES; l++) {
+                    if (DBG == 1 || DBG == 3) { lo[l] = hi[l] = u; continue; }
                     int v[32];
                     const uint32_t t0 = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_ACC_STRIDE + l * (TC_CB / 2);
                     tmem_ld16_nowait(t0, v);                 // coefficients 0..15 of plane l: CTA 0's rows of B
                     tmem_ld16_nowait(t0 + C::NH, v + 16);    // coefficients 16..31: CTA 1's
                     tmem_ld_wait();
-#pragma unroll
-                    for (int cc = 0; cc < 32; cc++) S[(cc - lane + 31) * 32 + lane] = v[cc];
-                    __syncwarp();
+                    // diagonal sum by warp shuffles (no shared memory: the skew scratch of the one-CTA kernel competes with the TMA
+                    // writes and the UMMA operand reads for the SM's shared-memory bandwidth).  Entry (tap lane L, column cc) belongs to
+                    // row cc - L + 31 of the skewed array; lane l collects rows l (previous block, cc <= l) and l + 32 (this block,
+                    // cc > l), and for a given cc exactly one source lane qualifies: L = (cc + 31 - l) mod 32.
                     int slo = 0, shi = 0;
 #pragma unroll
-                    for (int st = 0; st < 32; st++) {
-                        const int i = (st + lane) & 31;
-                        const bool is_lo = i >= 31 - lane;
-                        const int val = S[(lane + (is_lo ? 0 : 32)) * 32 + i];
-                        slo += is_lo ? val : 0;
-                        shi += is_lo ? 0 : val;
+                    for (int cc = 0; cc < 32; cc++) {
+                        const int x = __shfl_sync(0xffffffffu, v[cc], (cc + 31 - lane) & 31);
+                        if (cc > lane) shi += x; else slo += x;
                     }
-                    __syncwarp();
                     lo[l] = slo;
                     hi[l] = shi;
                 }
@@ -357,7 +357,7 @@ tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (rank == 0) mbar_arrive(bar_tempty + 8 * acc); else mbar_arrive_remote(bar_tempty + 8 * acc, 0);
                 }
                 if ((acc ^= 1) == 0) acc_phase ^= 1;
-                if (u >= 1 && valid) {
+                if (u >= 1 && valid && DBG != 1 && DBG != 3) {
                     long long v0 = 0, v1 = 0;
 #pragma unroll
                     for (int l = 0; l < PLANES; l++) {
@@ -392,17 +392,23 @@ tc_mac2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // tiles that stay in shared memory (no TMA, no epilogue), alternating between two TMEM accumulators.  What it measures is the
 // denominator of the tensor-bound kernels' roofline fraction (int8 multiply-accumulates per second), on the box and at the clocks
 // of the run -- not a figure derived from the bf16 GEMM of MEASURED_PEAKS.json.
+// VAR 0: N = 256, one operand tile reused by every MMA (the peak).  VAR 1: N = 224 (the ternary GEMM's tile), same.  VAR 2: N = 224,
+// operands taken in turn from four 44 KB stages, tcgen05.commit after every fourth MMA (the ternary GEMM's issue pattern without
+// its TMA traffic and epilogue).
+template <int VAR>
 __global__ void __launch_bounds__(128, 1)
 umma_i8_probe_kernel(int iters) {
-    constexpr int N = 256;
+    constexpr int N = VAR == 0 ? 256 : 224;
+    constexpr int NST = VAR == 2 ? 4 : 1;
+    constexpr int STAGE = (TC_BM + N) * TC_BK;
     constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *bp = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sA = base, sB = base + TC_BM * TC_BK, bar = sB + N * TC_BK, tmem_slot = bar + 8;
-    for (int i = threadIdx.x; i < (TC_BM + N) * TC_BK / 4; i += blockDim.x)
+    const uint32_t bar = base + NST * STAGE, tmem_slot = bar + 64;
+    for (int i = threadIdx.x; i < NST * STAGE / 4; i += blockDim.x)
         reinterpret_cast<uint32_t *>(bp)[i] = 0x01010101u * (uint32_t)((i * 2654435761u) >> 28);   // small bytes: products stay far from overflow
-    if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { for (int b = 0; b < 5; b++) mbar_init(bar + 8 * b, 1); fence_barrier_init(); }
     fence_proxy_async();
     if (threadIdx.x < 32) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -410,13 +416,16 @@ umma_i8_probe_kernel(int iters) {
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(bp + (tmem_slot - base));
     if (threadIdx.x == 0) {
-        const uint64_t da = umma_desc_sw128(sA), db = umma_desc_sw128(sB);
-        for (int it = 0; it < iters; it++)
+        for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-                umma_i8(tmem_base, da + 2 * ks, db + 2 * ks, IDESC, (it | ks) != 0);
-                umma_i8(tmem_base + 256, da + 2 * ks, db + 2 * ks, IDESC, (it | ks) != 0);
+            for (int half = 0; half < 2; half++) {
+                const uint32_t st = VAR == 2 ? (uint32_t)((2 * it + half) & 3) : 0u;
+                const uint64_t da = umma_desc_sw128(base + st * STAGE), db = umma_desc_sw128(base + st * STAGE + TC_BM * TC_BK);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) umma_i8(tmem_base + half * 256, da + 2 * ks, db + 2 * ks, IDESC, (it | ks) != 0);
+                if (VAR == 2) umma_commit(bar + 8 * (1 + st));     // nobody waits on these: the cost of the commit itself
             }
+        }
         umma_commit(bar);
         mbar_wait(bar, 0);
     }
@@ -510,17 +519,24 @@ size_t tc_b_bytes(const TcMacArgs &a) { return (size_t)a.npos * 2 * a.K * a.plan
 
 cudaError_t tc_mac_available() { return encode_tiled() ? cudaSuccess : cudaErrorNotSupported; }
 
-// blocks CTAs (one per SM), iters * 8 UMMAs of 128 x 256 x 32 each; *macs = int8 multiply-accumulates issued in total
-cudaError_t launch_umma_i8_probe(int blocks, int iters, double *macs, cudaStream_t stream) {
-    const size_t smem = 1024 + (size_t)(TC_BM + 256) * TC_BK + 64;
+// blocks CTAs (one per SM), iters * 8 UMMAs of 128 x N x 32 each; *macs = int8 multiply-accumulates issued in total
+template <int VAR>
+static cudaError_t launch_umma_probe_t(int blocks, int iters, double *macs, cudaStream_t stream) {
+    constexpr int N = VAR == 0 ? 256 : 224;
+    const size_t smem = 1024 + (size_t)(VAR == 2 ? 4 : 1) * (TC_BM + N) * TC_BK + 128;
     static DeviceOnce once;
     if (once.first()) {
-        cudaError_t e = cudaFuncSetAttribute(umma_i8_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(umma_i8_probe_kernel<VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    umma_i8_probe_kernel<<<blocks, 128, smem, stream>>>(iters);
-    if (macs) *macs = (double)blocks * iters * 8.0 * TC_BM * 256 * 32;
+    umma_i8_probe_kernel<VAR><<<blocks, 128, smem, stream>>>(iters);
+    if (macs) *macs = (double)blocks * iters * 8.0 * TC_BM * N * 32;
     return cudaGetLastError();
+}
+cudaError_t launch_umma_i8_probe(int blocks, int iters, int variant, double *macs, cudaStream_t stream) {
+    if (variant == 1) return launch_umma_probe_t<1>(blocks, iters, macs, stream);
+    if (variant == 2) return launch_umma_probe_t<2>(blocks, iters, macs, stream);
+    return launch_umma_probe_t<0>(blocks, iters, macs, stream);
 }
 
 cudaError_t launch_tc_split(const DeviceParams *P, const TcMacArgs &a, cudaStream_t stream) {
@@ -553,7 +569,8 @@ cudaError_t launch_tc_mac2_t(const DeviceParams *P, const TcMacArgs &a, int sm_c
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    auto k = tc_mac2_kernel<PLANES>;
+    static const int dbg_env = [] { const char *e = getenv("CRCNN_TC_DEBUG"); return e ? atoi(e) : 0; }();
+    auto k = dbg_env == 1 ? tc_mac2_kernel<PLANES, 1> : dbg_env == 2 ? tc_mac2_kernel<PLANES, 2> : dbg_env == 3 ? tc_mac2_kernel<PLANES, 3> : tc_mac2_kernel<PLANES, 0>;
     static DeviceOnce once;
     static int max_clusters[64];
     int dev = 0;
@@ -580,8 +597,10 @@ cudaError_t launch_tc_mac2_t(const DeviceParams *P, const TcMacArgs &a, int sm_c
 cudaError_t launch_tc_mac(const DeviceParams *P, const TcMacArgs &a, int sm_count, cudaStream_t stream) {
     if (a.npos <= 0 || a.M <= 0) return cudaSuccess;
     if (a.Kpad % TC_BK || a.Mpad % TC_BM || a.n % TC_CB || (long)a.npos * 2 * a.K > 65535) return cudaErrorInvalidValue;
-    // CTA pairs (tcgen05 cta_group::2) whenever the layer has at least two row tiles; CRCNN_TC_PAIR=0 forces the one-CTA kernel (A/B runs)
-    static const int pair_env = [] { const char *e = getenv("CRCNN_TC_PAIR"); return e ? atoi(e) : 1; }();
+    // CRCNN_TC_PAIR=1: CTA pairs (tcgen05 cta_group::2, tc_mac2_kernel) for layers with at least two row tiles.  Bit-exact (tests/
+    // test_gpu_tc.py runs it), but NOT faster on B200 (fc3 of the bench: 67.0 vs 66.1 ms), so the one-CTA kernel stays the default;
+    // DESIGN.md section 6 has the measurements that rule out operand traffic as this GEMM's limiter.
+    static const int pair_env = [] { const char *e = getenv("CRCNN_TC_PAIR"); return e ? atoi(e) : 0; }();
     if (pair_env && a.Mpad / TC_BM >= 2) {
         if (a.planes == 7) return launch_tc_mac2_t<7>(P, a, sm_count, stream);
         if (a.planes == 8) return launch_tc_mac2_t<8>(P, a, sm_count, stream);

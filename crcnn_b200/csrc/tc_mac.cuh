@@ -58,7 +58,7 @@ struct TcMacArgs {
 };
 
 size_t tc_b_bytes(const TcMacArgs &a);                       // size of the B scratch
-cudaError_t launch_umma_i8_probe(int blocks, int iters, double *macs, cudaStream_t stream);  // tensor-pipe roofline probe
+cudaError_t launch_umma_i8_probe(int blocks, int iters, int variant, double *macs, cudaStream_t stream);  // tensor-pipe roofline probe
 cudaError_t tc_mac_available();                              // driver entry point for tensor maps resolved?
 cudaError_t launch_tc_split(const DeviceParams *P, const TcMacArgs &a, cudaStream_t stream);
 cudaError_t launch_tc_mac(const DeviceParams *P, const TcMacArgs &a, int sm_count, cudaStream_t stream);

@@ -178,6 +178,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {   // rows of 64 B, 8-row atoms of 512 B, layout type 4 = SWIZZLE_64B
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
 __device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
 }
