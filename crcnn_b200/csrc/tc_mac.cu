@@ -12,7 +12,6 @@ namespace crcnn {
 
 namespace {
 
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_STAGE = TC_BM * TC_BK;  // 16 KB
 constexpr int TC_THREADS = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int TC_ACC_STRIDE = 256;         // TMEM columns between the two accumulator buffers
@@ -21,12 +20,15 @@ constexpr int TC_SCRATCH_WARP = 64 * 32 * 4;
 using namespace tcptx;
 
 // ------------------------------------------------------------------------------------ the GEMM kernel
-template <int PLANES>
+// SUB = K blocks of 128 bytes per ring stage (one barrier flip and one tcgen05.commit per stage): 1 -> 4 stages of 44 KB, 2 -> 2 stages of 88 KB
+template <int PLANES, int SUB = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const DeviceParams *__restrict__ P, TcMacArgs a) {
     constexpr int N = PLANES * TC_CB;               // UMMA N: 224 or 256
-    constexpr int B_STAGE = N * TC_BK;              // 28 / 32 KB
+    constexpr int B_BLK = N * TC_BK;                // 28 / 32 KB
+    constexpr int TC_STAGES = 4 / SUB;
+    constexpr int A_STAGE = SUB * TC_A_STAGE, B_STAGE = SUB * B_BLK;
     constexpr uint32_t IDESC = (2u << 4)            // accumulator format S32
                                | (1u << 7)          // A = signed 8 bit
                                | (0u << 10)         // B = unsigned 8 bit
@@ -35,8 +37,8 @@ tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t sA = base, sB = base + TC_STAGES * TC_A_STAGE;
-    const uint32_t off_scratch = TC_STAGES * (TC_A_STAGE + B_STAGE);
+    const uint32_t sA = base, sB = base + TC_STAGES * A_STAGE;
+    const uint32_t off_scratch = TC_STAGES * (A_STAGE + B_STAGE);
     const uint32_t off_bar = off_scratch + 4 * TC_SCRATCH_WARP;
     const uint32_t bar_full = base + off_bar, bar_empty = bar_full + 8 * TC_STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * TC_STAGES, bar_tempty = bar_tfull + 16;
@@ -49,7 +51,8 @@ tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const long items = (long)a.npos * 2 * K * m_tiles;
     const int NU = n / TC_CB + 1;                   // coefficient blocks incl. the negated wrap-around block
     const int ksteps = (a.R + 31) / 32;
-    const int KB = (ksteps + 3) / 4;
+    const int KBLK = (ksteps + 3) / 4;                // 128-byte K blocks
+    const int KB = (KBLK + SUB - 1) / SUB;            // ring stages per coefficient block
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -74,9 +77,12 @@ tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 for (int u = 0; u < NU; u++)
                     for (int kb = 0; kb < KB; kb++) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        mbar_expect_tx(bar_full + 8 * stage, TC_A_STAGE + B_STAGE);
-                        tma_load_2d(sA + stage * TC_A_STAGE, &tmA, bar_full + 8 * stage, kb * TC_BK, mt * TC_BM);
-                        tma_load_4d(sB + stage * B_STAGE, &tmB, bar_full + 8 * stage, kb * TC_BK, u * TC_CB, 0, g);
+                        const int nsub = min(SUB, KBLK - kb * SUB);
+                        mbar_expect_tx(bar_full + 8 * stage, nsub * (TC_A_STAGE + B_BLK));
+                        for (int sb = 0; sb < nsub; sb++) {
+                            tma_load_2d(sA + stage * A_STAGE + sb * TC_A_STAGE, &tmA, bar_full + 8 * stage, (kb * SUB + sb) * TC_BK, mt * TC_BM);
+                            tma_load_4d(sB + stage * B_STAGE + sb * B_BLK, &tmB, bar_full + 8 * stage, (kb * SUB + sb) * TC_BK, u * TC_CB, 0, g);
+                        }
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
             }
@@ -95,10 +101,12 @@ tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     for (int kb = 0; kb < KB; kb++) {
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
-                        const uint64_t da = umma_desc_sw128(sA + stage * TC_A_STAGE), db = umma_desc_sw128(sB + stage * B_STAGE);
-                        const int nks = min(4, ksteps - kb * 4);
-                        for (int ks = 0; ks < nks; ks++)
-                            umma_i8(d_tmem, da + 2 * ks, db + 2 * ks, IDESC, (kb | ks) != 0);  // +32 B per K-step
+                        for (int sb = 0; sb < SUB && kb * SUB + sb < KBLK; sb++) {
+                            const uint64_t da = umma_desc_sw128(sA + stage * A_STAGE + sb * TC_A_STAGE), db = umma_desc_sw128(sB + stage * B_STAGE + sb * B_BLK);
+                            const int nks = min(4, ksteps - (kb * SUB + sb) * 4);
+                            for (int ks = 0; ks < nks; ks++)
+                                umma_i8(d_tmem, da + 2 * ks, db + 2 * ks, IDESC, (kb | sb | ks) != 0);  // +32 B per K-step
+                        }
                         umma_commit(bar_empty + 8 * stage);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -475,7 +483,7 @@ tc_split_kernel(const DeviceParams *__restrict__ P, TcMacArgs a) {
 // ------------------------------------------------------------------------------------ host side
 template <int PLANES>
 size_t tc_smem_bytes() {
-    return 1024 + (size_t)TC_STAGES * (TC_A_STAGE + PLANES * TC_CB * TC_BK) + 4 * TC_SCRATCH_WARP + 16 * TC_STAGES + 32 + 16;
+    return 1024 + (size_t)4 * (TC_A_STAGE + PLANES * TC_CB * TC_BK) + 4 * TC_SCRATCH_WARP + 16 * 4 + 32 + 16;
 }
 
 template <int PLANES>
@@ -500,12 +508,16 @@ cudaError_t launch_tc_mac_t(const DeviceParams *P, const TcMacArgs &a, int sm_co
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return cudaErrorInvalidValue;
     }
-    auto k = tc_mac_kernel<PLANES>;
+    // two 128-byte K blocks per ring stage (2 stages of 88 KB, half as many barrier flips and commits): fc3 of the bench 64.8 -> 62.1 ms on B200; CRCNN_TC_SUB=1 = four 44 KB stages
+    static const int sub_env = [] { const char *e = getenv("CRCNN_TC_SUB"); return e ? atoi(e) : 2; }();
+    auto k = sub_env == 2 ? tc_mac_kernel<PLANES, 2> : tc_mac_kernel<PLANES, 1>;
     const size_t smem = tc_smem_bytes<PLANES>();
     static DeviceOnce once;
     if (once.first()) {
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
+        for (auto kk : {tc_mac_kernel<PLANES, 1>, tc_mac_kernel<PLANES, 2>}) {
+            cudaError_t e = cudaFuncSetAttribute(kk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
     }
     const long items = (long)a.npos * 2 * a.K * (a.Mpad / TC_BM);
     const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
