@@ -65,8 +65,13 @@ public:
     Network buildNetwork(std::string file_name = "") { return buildNetwork("Tiny", file_name); }
 
     Network buildNetwork(const std::string &topology, std::string file_name) {
-        const int th_count = 40, th_count2 = 50, th_tiny = 32, th_tiny2 = 42;  // cnnBuilder.cpp:109 (accepted and ignored by the layers)
         Network net;
+        buildLayers(net, topology, file_name);
+        return net;
+    }
+    // The same blocks appended to a caller-owned network (e.g. a ShardedNetwork, which cannot be returned by value)
+    void buildLayers(Network &net, const std::string &topology, std::string file_name) {
+        const int th_count = 40, th_count2 = 50, th_tiny = 32, th_tiny2 = 42;  // cnnBuilder.cpp:109 (accepted and ignored by the layers)
         std::ifstream *infile = NULL;
         if (file_name != "") {
             infile = new std::ifstream(file_name, std::ifstream::binary);
@@ -103,7 +108,10 @@ public:
             throw;
         }
         if (infile != NULL) { infile->close(); delete infile; }
-        return net;
+    }
+    // input shape (z, x, y) and number of score ciphertexts of a topology
+    static void topologyShape(const std::string &topology, int *zd, int *xd, int *yd, int *outputs) {
+        *zd = 1; *xd = *yd = topology == "PlainModel" ? 32 : 28; *outputs = 10;
     }
 
     // cnnBuilder.cpp:181-196.  Precondition as in the reference: Runtime::init() (their setParameters) has been called.

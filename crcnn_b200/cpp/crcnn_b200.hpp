@@ -200,17 +200,20 @@ private:
 struct DeviceTensor {
     crcnn_tensor *t = nullptr;
     int zd = 0, xd = 0, yd = 0;
+    int batch = 1;     // independent images stacked in front: device layout [batch][z][x][y] (the reference processes one image per call)
+    bool owned = true; // false: a view of a tensor somebody else frees (the input buffers of a BatchServer)
     DeviceTensor() = default;
-    DeviceTensor(crcnn_tensor *p, int z, int x, int y) : t(p), zd(z), xd(x), yd(y) {}
-    DeviceTensor(DeviceTensor &&o) noexcept : t(o.t), zd(o.zd), xd(o.xd), yd(o.yd) { o.t = nullptr; }
+    DeviceTensor(crcnn_tensor *p, int z, int x, int y, int b = 1, bool own = true) : t(p), zd(z), xd(x), yd(y), batch(b), owned(own) {}
+    DeviceTensor(DeviceTensor &&o) noexcept : t(o.t), zd(o.zd), xd(o.xd), yd(o.yd), batch(o.batch), owned(o.owned) { o.t = nullptr; }
     DeviceTensor &operator=(DeviceTensor &&o) noexcept {
-        if (this != &o) { release(); t = o.t; zd = o.zd; xd = o.xd; yd = o.yd; o.t = nullptr; }
+        if (this != &o) { release(); t = o.t; zd = o.zd; xd = o.xd; yd = o.yd; batch = o.batch; owned = o.owned; o.t = nullptr; }
         return *this;
     }
     DeviceTensor(const DeviceTensor &) = delete;
     DeviceTensor &operator=(const DeviceTensor &) = delete;
     ~DeviceTensor() { release(); }
-    void release() { if (t) crcnn_tensor_free(Runtime::get().ctx(), t); t = nullptr; }
+    void release() { if (t && owned) crcnn_tensor_free(Runtime::get().ctx(), t); t = nullptr; }
+    long count() const { return (long)batch * zd * xd * yd; }
 };
 
 struct PlainPack {
@@ -397,8 +400,16 @@ public:
         Runtime &rt = Runtime::get();
         ensure_packs();
         crcnn_tensor *o = nullptr;
-        rt.check(crcnn_conv_forward(rt.ctx(), in.t, w_.p, b_.p, 1, xd, yd, zd, xs, ys, xf, yf, nf, &o));
-        return DeviceTensor(o, zo, xo, yo);
+        rt.check(crcnn_conv_forward(rt.ctx(), in.t, w_.p, b_.p, in.batch, xd, yd, zd, xs, ys, xf, yf, nf, &o));
+        return DeviceTensor(o, zo, xo, yo, in.batch);
+    }
+    // Output channels [k0, k0+kc) only: this GPU's share of the reference's filter split (convolutionalLayer.cpp:177-187)
+    DeviceTensor forward_shard(const DeviceTensor &in, int k0, int kc) {
+        Runtime &rt = Runtime::get();
+        ensure_packs();
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_conv_forward_shard(rt.ctx(), in.t, w_.p, b_.p, in.batch, xd, yd, zd, xs, ys, xf, yf, nf, k0, kc, &o));
+        return DeviceTensor(o, kc, xo, yo, in.batch);
     }
     plaintext3D getKernel(int kernel_index) { materializeHostParameters(); return filters[kernel_index]; }
     Plaintext getBias(int bias_index) { materializeHostParameters(); return biases[bias_index]; }
@@ -496,8 +507,16 @@ public:
         ensure_packs();
         // the device layout [z][x][y] is already the row-major flattening reshapeInput produces
         crcnn_tensor *o = nullptr;
-        rt.check(crcnn_fc_forward(rt.ctx(), in.t, w_.p, b_.p, 1, in_dim, out_dim, &o));
-        return DeviceTensor(o, 1, out_dim, 1);
+        rt.check(crcnn_fc_forward(rt.ctx(), in.t, w_.p, b_.p, in.batch, in_dim, out_dim, &o));
+        return DeviceTensor(o, 1, out_dim, 1, in.batch);
+    }
+    // Output rows [o0, o0+oc) only: this GPU's share of the reference's row split (fullyConnectedLayer.cpp:148-158)
+    DeviceTensor forward_shard(const DeviceTensor &in, int o0, int oc) {
+        Runtime &rt = Runtime::get();
+        ensure_packs();
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_fc_forward_shard(rt.ctx(), in.t, w_.p, b_.p, in.batch, in_dim, out_dim, o0, oc, &o));
+        return DeviceTensor(o, 1, oc, 1, in.batch);
     }
     Plaintext getWeight(int x_index, int y_index) { materializeHostParameters(); return weights[x_index][y_index]; }
     Plaintext getBias(int x_index) { materializeHostParameters(); return biases[x_index]; }
@@ -546,8 +565,8 @@ public:
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
         crcnn_tensor *o = nullptr;
-        rt.check(crcnn_pool_forward(rt.ctx(), in.t, 1, xd, yd, zo, xs, ys, xf, yf, scale(), &o));
-        return DeviceTensor(o, zo, xo, yo);
+        rt.check(crcnn_pool_forward(rt.ctx(), in.t, in.batch, xd, yd, in.zd, xs, ys, xf, yf, scale(), &o));   // in.zd: a channel shard pools its own channels
+        return DeviceTensor(o, in.zd, xo, yo, in.batch);
     }
     void printLayerStructure() override {
         std::fprintf(stderr, "Pooling %s : input (%d,%d,%d); kernel(%d,%d); stride(%d,%d); output(%d,%d,%d)\n", name.c_str(), zo, xd, yd, xf, yf, xs, ys, zo, xo, yo);
@@ -593,6 +612,26 @@ public:
         : Layer(name), num_channels(num_channels) {
         if ((int)mean_values.size() != num_channels || (int)invstd_values.size() != num_channels) throw std::invalid_argument("statistics do not match the channel count");
         m_.encode(mean_values); v_.encode(invstd_values);
+        mean_f_ = mean_values; invstd_f_ = invstd_values;
+    }
+    // Channels [k0, k0+kc) of a channel-sharded activation (batch-norm is per channel: no exchange)
+    DeviceTensor forward_shard(const DeviceTensor &in, int k0, int kc) {
+        Runtime &rt = Runtime::get();
+        if (k0 < 0 || kc < 0 || k0 + kc > num_channels || in.zd != kc) throw std::invalid_argument("bad channel shard");
+        if (!sm_.p || s0_ != k0 || sc_ != kc) {
+            if (!mean_f_.empty()) {
+                sm_.encode(std::vector<float>(mean_f_.begin() + k0, mean_f_.begin() + k0 + kc));
+                sv_.encode(std::vector<float>(invstd_f_.begin() + k0, invstd_f_.begin() + k0 + kc));
+            } else {
+                std::vector<const Plaintext *> ms, vs;
+                for (int i = k0; i < k0 + kc; i++) { ms.push_back(&mean[i]); vs.push_back(&var[i]); }
+                sm_.assign(ms); sv_.assign(vs);
+            }
+            s0_ = k0; sc_ = kc;
+        }
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_bn_forward(rt.ctx(), in.t, in.batch, kc, in.xd, in.yd, sm_.p, sv_.p, &o));
+        return DeviceTensor(o, kc, in.xd, in.yd, in.batch);
     }
     void materializeHostParameters() {
         if (!mean.empty() || !m_.p) return;
@@ -608,8 +647,8 @@ public:
             m_.assign(ms); v_.assign(vs);
         }
         crcnn_tensor *o = nullptr;
-        rt.check(crcnn_bn_forward(rt.ctx(), in.t, 1, in.zd, in.xd, in.yd, m_.p, v_.p, &o));
-        return DeviceTensor(o, in.zd, in.xd, in.yd);
+        rt.check(crcnn_bn_forward(rt.ctx(), in.t, in.batch, in.zd, in.xd, in.yd, m_.p, v_.p, &o));
+        return DeviceTensor(o, in.zd, in.xd, in.yd, in.batch);
     }
     Plaintext getMean(int index) { materializeHostParameters(); return mean[index]; }
     Plaintext getVar(int index) { materializeHostParameters(); return var[index]; }
@@ -626,7 +665,9 @@ public:
     }
     void printLayerStructure() override { std::fprintf(stderr, "BatchNormLayer2D %s :num_channels %d\n", name.c_str(), num_channels); }
 private:
-    PlainPack m_, v_;
+    PlainPack m_, v_, sm_, sv_;
+    std::vector<float> mean_f_, invstd_f_;
+    int s0_ = -1, sc_ = -1;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -641,7 +682,7 @@ public:
         Runtime &rt = Runtime::get();
         crcnn_tensor *o = nullptr;
         rt.check(crcnn_square_forward(rt.ctx(), in.t, rt.evk(), &o));
-        return DeviceTensor(o, in.zd, in.xd, in.yd);
+        return DeviceTensor(o, in.zd, in.xd, in.yd, in.batch);
     }
     void printLayerStructure() override { std::fprintf(stderr, "SquareLayer %s\n", name.c_str()); }
     void savePlaintextParameters(std::ostream *) override {}
@@ -661,36 +702,255 @@ private:
     std::string msg_;
 };
 
+// Several images -> ONE device tensor [batch][z][x][y] (one pinned staging buffer, one H2D copy)
+inline DeviceTensor upload_batch(const std::vector<ciphertext3D> &images) {
+    Runtime &rt = Runtime::get();
+    if (images.empty()) throw std::invalid_argument("empty batch");
+    const int B = (int)images.size(), zd = (int)images[0].size(), xd = (int)images[0][0].size(), yd = (int)images[0][0][0].size();
+    const size_t w = rt.ct_words(2), per = (size_t)zd * xd * yd;
+    void *pin = nullptr;
+    if (crcnn_pinned_alloc(B * per * w * 8, &pin)) throw std::runtime_error("crcnn_b200: cannot allocate pinned staging memory");
+    std::uint64_t *stage = static_cast<std::uint64_t *>(pin);
+    size_t i = 0;
+    try {
+        for (auto &in : images) {
+            if ((int)in.size() != zd || (int)in[0].size() != xd || (int)in[0][0].size() != yd) throw std::invalid_argument("images of a batch must have one shape");
+            for (auto &plane : in)
+                for (auto &row : plane)
+                    for (auto &ct : row) {
+                        if (ct.size() != 2 || ct.poly_coeff_count() != rt.n() + 1 || ct.coeff_mod_count() != rt.K())
+                            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+                        std::memcpy(stage + i * w, ct.data(), w * 8);
+                        i++;
+                    }
+        }
+        crcnn_tensor *t = nullptr;
+        rt.check(crcnn_tensor_upload(rt.ctx(), stage, (long)(B * per), 2, &t));
+        rt.check(crcnn_ctx_sync(rt.ctx()));
+        crcnn_pinned_free(pin);
+        return DeviceTensor(t, zd, xd, yd, B);
+    } catch (...) { crcnn_pinned_free(pin); throw; }
+}
+
+inline std::vector<ciphertext3D> download_batch(const DeviceTensor &d) {
+    Runtime &rt = Runtime::get();
+    const size_t w = rt.ct_words(2), per = (size_t)d.zd * d.xd * d.yd;
+    std::vector<std::uint64_t> stage((size_t)d.batch * per * w);
+    rt.check(crcnn_tensor_download(rt.ctx(), d.t, stage.data()));
+    std::vector<ciphertext3D> out(d.batch, ciphertext3D(d.zd, ciphertext2D(d.xd, std::vector<Ciphertext>(d.yd))));
+    size_t i = 0;
+    for (auto &img : out)
+        for (auto &plane : img)
+            for (auto &row : plane)
+                for (auto &ct : row) {
+#ifdef CRCNN_WITH_SEAL
+                    Ciphertext alias(rt.parms(), 2, stage.data() + i * w);
+                    ct = alias;
+#else
+                    ct = Ciphertext(2, rt.n() + 1, rt.K());
+                    std::memcpy(ct.data(), stage.data() + i * w, w * 8);
+#endif
+                    i++;
+                }
+    return out;
+}
+
 class Network {
 public:
     std::vector<std::shared_ptr<Layer>> layers;
     // The reference re-encrypts (decrypt + encrypt with the SECRET key) unconditionally before layer 6
-    // (network.cpp:23,30-38).  That step belongs to the key holder: install it here if wanted; by default
-    // no re-encryption happens and the whole network runs device-resident.
+    // (network.cpp:23,30-38).  That step belongs to the key holder: install it in `reencrypt`.  A network with more than
+    // layer_before_reenc layers and NO callback does not silently skip it: forward() throws std::logic_error unless the caller
+    // has opted out with skip_reencryption = true (at n = 8192 the nine-layer networks have the budget to run without it, SURVEY
+    // 8(d) config 2 -- but then outputs and noise budgets differ from a reference run, and the caller should know).
     int layer_before_reenc = 6;
     std::function<ciphertext3D(ciphertext3D)> reencrypt;
+    bool skip_reencryption = false;
 
     Network() {}
-    ~Network() {}
+    virtual ~Network() {}
     int getNumLayers() { return (int)layers.size(); }
     virtual std::shared_ptr<Layer> getLayer(int i) { return layers[i]; }
     std::vector<std::shared_ptr<Layer>> &getLayers() { return layers; }
     void printNetworkStructure() {
         for (size_t i = 0; i < layers.size(); i++) { std::fprintf(stderr, "(%zu) : ", i); layers[i]->printLayerStructure(); }
     }
-    // Segment API: layers [first, last) without leaving the device.
-    DeviceTensor forward_dev(DeviceTensor x, int first, int last) {
+    // Segment API: layers [first, last) without leaving the device; any batch.
+    virtual DeviceTensor forward_dev(DeviceTensor x, int first, int last) {
+        if (first < 0 || last > (int)layers.size() || first > last) throw std::invalid_argument("bad layer range");
         for (int i = first; i < last; i++) x = layers[i]->forward_dev(std::move(x));
         return x;
     }
+    bool needs_reencryption() const { return layer_before_reenc > 0 && layer_before_reenc < (int)layers.size(); }
     ciphertext3D forward(ciphertext3D input) {
         const int L = (int)layers.size();
-        if (reencrypt && layer_before_reenc > 0 && layer_before_reenc < L) {
+        if (needs_reencryption() && !skip_reencryption) {
+            if (!reencrypt)
+                throw std::logic_error("crcnn_b200::Network::forward: the reference re-encrypts before layer " + std::to_string(layer_before_reenc) +
+                                       " (CrCNN/src/network.cpp:30); install Network::reencrypt (the key holder's decrypt + encrypt) or set skip_reencryption = true");
             ciphertext3D mid = download(forward_dev(upload(input), 0, layer_before_reenc));
             return download(forward_dev(upload(reencrypt(mid)), layer_before_reenc, L));
         }
         return download(forward_dev(upload(input), 0, L));
     }
+    // Same for a batch of independent images in one pass (what the reference's per-image loop, mainparams.cpp:84-111, does one by one).
+    std::vector<ciphertext3D> forward_batch(const std::vector<ciphertext3D> &inputs) {
+        const int L = (int)layers.size();
+        if (needs_reencryption() && !skip_reencryption) {
+            if (!reencrypt) throw std::logic_error("crcnn_b200::Network::forward_batch: re-encryption before layer " + std::to_string(layer_before_reenc) + " is not installed (see Network::forward)");
+            std::vector<ciphertext3D> mid = download_batch(forward_dev(upload_batch(inputs), 0, layer_before_reenc));
+            for (auto &m : mid) m = reencrypt(m);
+            return download_batch(forward_dev(upload_batch(mid), layer_before_reenc, L));
+        }
+        return download_batch(forward_dev(upload_batch(inputs), 0, L));
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// BatchServer: the inference loop of the reference's program (CrCNN/src/mainparams.cpp:84-111: encrypt -> forward -> decrypt, one
+// image at a time) as a double-buffered pipeline over batches.  Two device input tensors and one staging buffer are allocated
+// once; while batch i runs on the context's stream, batch i+1 is copied host -> device on a copy stream
+// (crcnn_tensor_upload_into) and the scores of batch i-1 are on their way back (crcnn_tensor_download_async).  Nothing is
+// allocated per request and the host never blocks on the device except in wait().
+// ------------------------------------------------------------------------------------------------
+class BatchServer {
+public:
+    // zd, xd, yd: input shape of the network; batch: images per request; outputs: score ciphertexts per image
+    BatchServer(Network &net, int zd, int xd, int yd, int batch, int outputs)
+        : net_(net), zd_(zd), xd_(xd), yd_(yd), batch_(batch), outputs_(outputs) {
+        Runtime &rt = Runtime::get();
+        rt.check(crcnn_stream_create(rt.ctx(), &copy_));
+        for (int i = 0; i < 2; i++) {
+            rt.check(crcnn_tensor_wrap_alloc(rt.ctx(), (long)batch * zd * xd * yd, 2, 0, &in_[i]));
+            rt.check(crcnn_event_create(rt.ctx(), &consumed_[i]));
+            rt.check(crcnn_event_create(rt.ctx(), &done_[i]));
+        }
+    }
+    ~BatchServer() {
+        Runtime &rt = Runtime::get();
+        crcnn_ctx_sync(rt.ctx());
+        for (int i = 0; i < 2; i++) {
+            if (in_[i]) crcnn_tensor_free(rt.ctx(), in_[i]);
+            crcnn_event_destroy(rt.ctx(), consumed_[i]);
+            crcnn_event_destroy(rt.ctx(), done_[i]);
+        }
+        crcnn_stream_destroy(rt.ctx(), copy_);
+    }
+    size_t input_words() const { return (size_t)batch_ * zd_ * xd_ * yd_ * Runtime::get().ct_words(2); }
+    size_t output_words() const { return (size_t)batch_ * outputs_ * Runtime::get().ct_words(2); }
+
+    // Stage request `seq` (0, 1, 2 ...): enqueue the upload of its input (pinned, SEAL layout, [batch][z][x][y]) on the copy stream.
+    void stage(long seq, const std::uint64_t *pinned_in) {
+        Runtime &rt = Runtime::get();
+        const int slot = (int)(seq & 1);
+        if (seq >= 2) rt.check(crcnn_stream_wait_event(rt.ctx(), copy_, consumed_[slot]));   // the forward that read this buffer has finished
+        rt.check(crcnn_tensor_upload_into(rt.ctx(), pinned_in, in_[slot], 0, copy_));
+    }
+    // Run request `seq` (staged before) and enqueue the download of its scores into pinned_out; returns without waiting.
+    void run(long seq, std::uint64_t *pinned_out) {
+        Runtime &rt = Runtime::get();
+        const int slot = (int)(seq & 1);
+        rt.check(crcnn_ctx_wait_stream(rt.ctx(), copy_));
+        DeviceTensor y = net_.forward_dev(DeviceTensor(in_[slot], zd_, xd_, yd_, batch_, /*own=*/false), 0, net_.getNumLayers());
+        rt.check(crcnn_event_record(rt.ctx(), consumed_[slot], nullptr));
+        if (y.count() != (long)batch_ * outputs_) throw std::logic_error("network output does not match BatchServer::outputs");
+        rt.check(crcnn_tensor_download_async(rt.ctx(), y.t, pinned_out));
+        rt.check(crcnn_event_record(rt.ctx(), done_[slot], nullptr));
+    }
+    // Block until the scores of request `seq` are in host memory.
+    void wait(long seq) {
+        Runtime &rt = Runtime::get();
+        double ms;
+        rt.check(crcnn_event_elapsed_ms(rt.ctx(), done_[seq & 1], done_[seq & 1], &ms));
+    }
+    // The whole loop for `requests` requests reading in(i) and writing out(i): upload of i+1 overlaps forward of i.
+    void serve(long requests, const std::function<const std::uint64_t *(long)> &in, const std::function<std::uint64_t *(long)> &out) {
+        if (requests <= 0) return;
+        stage(0, in(0));
+        for (long i = 0; i < requests; i++) {
+            run(i, out(i));                       // waits (on the device) for upload i, then forward + async score download
+            if (i + 1 < requests) stage(i + 1, in(i + 1));
+            if (i >= 1) wait(i - 1);              // scores of the previous request are complete: the caller may decrypt them
+        }
+        wait(requests - 1);
+    }
+    void *copy_stream() { return copy_; }
+
+private:
+    Network &net_;
+    int zd_, xd_, yd_, batch_, outputs_;
+    void *copy_ = nullptr;
+    crcnn_tensor *in_[2] = {nullptr, nullptr};
+    void *consumed_[2] = {nullptr, nullptr}, *done_[2] = {nullptr, nullptr};
+};
+
+// ------------------------------------------------------------------------------------------------
+// ShardedNetwork: one network split across the GPUs of a box by OUTPUT NEURON -- the reference's own
+// thread split (convolutionalLayer.cpp:177-187, fullyConnectedLayer.cpp:148-158) with GPUs in place of threads.  One process per
+// GPU; every process holds the whole encoded network and calls forward_dev with the same input; conv / fc layers compute this
+// rank's contiguous range of output channels / rows; pooling, batch-norm and square act on the local channels without any
+// exchange; before a conv / fc layer (and at the end) the ranks all-gather their ciphertexts over NVLink (crcnn_comm_all_gather:
+// one NCCL group on the context's stream, no host synchronisation).  Bit-identical to the unsharded forward.
+// ------------------------------------------------------------------------------------------------
+class ShardedNetwork : public Network {
+public:
+    ShardedNetwork(int world, int rank, const void *nccl_id128) : world_(world), rank_(rank) {
+        Runtime &rt = Runtime::get();
+        rt.check(crcnn_comm_create(rt.ctx(), nccl_id128, world, rank, &comm_));
+    }
+    ~ShardedNetwork() override { if (comm_) crcnn_comm_destroy(Runtime::get().ctx(), comm_); }
+    int world() const { return world_; }
+    int rank() const { return rank_; }
+    // contiguous, balanced split: the first total % world ranks get one more (a rank may get none when world > total)
+    static void shard_range(int total, int world, int rank, int *first, int *count) {
+        const int base = total / world, extra = total % world;
+        *first = rank * base + (rank < extra ? rank : extra);
+        *count = base + (rank < extra ? 1 : 0);
+    }
+    DeviceTensor all_gather(const DeviceTensor &x, int channels, int per_channel, int xd, int yd) {
+        Runtime &rt = Runtime::get();
+        std::vector<long> counts(world_);
+        for (int r = 0; r < world_; r++) { int f, c; shard_range(channels, world_, r, &f, &c); counts[r] = (long)c * per_channel; }
+        crcnn_tensor *full = nullptr;
+        rt.check(crcnn_comm_all_gather(rt.ctx(), comm_, x.t, x.batch, counts.data(), gather_ntt_form, &full));
+        return DeviceTensor(full, channels, xd, yd, x.batch);
+    }
+    // x holds the FULL input on every rank; the result is the full output of layer last-1 on every rank.
+    DeviceTensor forward_dev(DeviceTensor x, int first, int last) override {
+        bool sharded = false;       // x holds only this rank's channels
+        bool rows = false;          // ... which are output rows of a fully connected layer
+        int channels = x.zd;
+        for (int i = first; i < last; i++) {
+            Layer *l = layers[i].get();
+            if (auto *c = dynamic_cast<ConvolutionalLayer *>(l)) {
+                if (sharded) x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);
+                int k0, kc; shard_range(c->nf, world_, rank_, &k0, &kc);
+                x = c->forward_shard(x, k0, kc);
+                channels = c->nf; sharded = true; rows = false;
+            } else if (auto *f = dynamic_cast<FullyConnectedLayer *>(l)) {
+                if (sharded) x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);
+                int o0, oc; shard_range(f->out_dim, world_, rank_, &o0, &oc);
+                x = f->forward_shard(x, o0, oc);
+                x.zd = oc; x.xd = 1;            // rows play the part of channels for the next gather
+                channels = f->out_dim; sharded = true; rows = true;
+            } else if (auto *bn = dynamic_cast<BatchNormLayer *>(l)) {
+                if (sharded) { int k0, kc; shard_range(channels, world_, rank_, &k0, &kc); x = bn->forward_shard(x, k0, kc); }
+                else x = bn->forward_dev(std::move(x));
+            } else {
+                x = l->forward_dev(std::move(x));   // pooling and square are per channel / per ciphertext: local channels, no exchange
+            }
+        }
+        if (sharded) {
+            x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);
+            if (rows) { x.zd = 1; x.xd = channels; }   // a fully connected output is [1][out_dim][1] (fullyConnectedLayer.cpp:113-168)
+        }
+        return x;
+    }
+    int gather_ntt_form = -1;  // domain the activations are exchanged in: -1 as produced (no transform), 0 coefficient form, 1 NTT form
+
+private:
+    int world_, rank_;
+    crcnn_comm *comm_ = nullptr;
 };
 
 }  // namespace crcnn_b200

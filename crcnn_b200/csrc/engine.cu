@@ -2,6 +2,7 @@
 // evaluation keys, the layer forwards and the evaluator-level operations, all on top of the
 // kernels in kernels.cu.  Host code only orchestrates; every arithmetic step runs on the GPU.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -419,7 +420,9 @@ int run_weighted_sum_tcn(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn
 
 int run_weighted_sum(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, const int *d_index, int R,
                      int Npos, int Pimg, int Mall, int m_first, int M, crcnn_tensor *out) {
-    if (ctx->tc_mode && R >= ctx->tc_min_fanin && (ctx->tc_mode == 2 || M >= ctx->tc_min_outputs) && w->sparse_shape && tc_mac_available() == cudaSuccess) {
+    // the kernel (and with it the domain of the output) is chosen from the LAYER's output count Mall, not the shard's M: every rank of a
+    // neuron-sharded layer then produces its rows in the same domain, whatever the split (63 rows on 2 ranks: 32 + 31)
+    if (ctx->tc_mode && R >= ctx->tc_min_fanin && (ctx->tc_mode == 2 || Mall >= ctx->tc_min_outputs) && w->sparse_shape && tc_mac_available() == cudaSuccess) {
         int rc = ensure_tc_form(ctx, w, R);
         if (rc) return rc;
         if (w->tc_state == 1) return run_weighted_sum_tc(ctx, in, w, b, d_index, R, Npos, Pimg, m_first, M, out);
@@ -919,7 +922,7 @@ int crcnn_conv_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, c
     REQUIRE(in && w && b && out, "null argument");
     REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && nf > 0 && xf <= xd && yf <= yd,
             "bad convolution geometry");
-    REQUIRE(k0 >= 0 && kc > 0 && k0 + kc <= nf, "bad output-channel shard");
+    REQUIRE(k0 >= 0 && kc >= 0 && k0 + kc <= nf, "bad output-channel shard");
     REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
     const int R = zd * xf * yf;
     REQUIRE(w->count == (long)nf * R && b->count == nf, "kernel/bias count does not match the layer geometry");  // convolutionalLayer.cpp:57-59
@@ -967,7 +970,7 @@ int crcnn_fc_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crc
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(in && w && b && out, "null argument");
     REQUIRE(batch > 0 && in_dim > 0 && out_dim > 0, "bad fully-connected geometry");
-    REQUIRE(o0 >= 0 && oc > 0 && o0 + oc <= out_dim, "bad output-row shard");
+    REQUIRE(o0 >= 0 && oc >= 0 && o0 + oc <= out_dim, "bad output-row shard");
     REQUIRE(in->size == 2 && in->count == (long)batch * in_dim, "input tensor does not match the layer geometry");
     REQUIRE(w->count == (long)out_dim * in_dim && b->count == out_dim, "weight/bias count does not match the layer geometry");
     CU(cudaSetDevice(ctx->device));
@@ -1357,6 +1360,215 @@ int crcnn_probe_pipe(crcnn_ctx *ctx, int which, int blocks, int threads, int ite
 }
 int crcnn_probe_imad(crcnn_ctx *ctx, int blocks, int threads, int iters, double *ms) {
     return crcnn_probe_pipe(ctx, 0, blocks, threads, iters, ms, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------- host support
+// What a C++17 serving loop needs besides the layer calls, without linking the CUDA runtime itself: page-locked staging
+// memory, a copy stream, events to time on the device and to order the two streams.
+int crcnn_pinned_alloc(size_t bytes, void **out) {
+    if (!out) return CRCNN_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? CRCNN_ERR_OUT_OF_MEMORY : CRCNN_ERR_CUDA; }
+    return CRCNN_OK;
+}
+int crcnn_pinned_free(void *p) { return (!p || cudaFreeHost(p) == cudaSuccess) ? CRCNN_OK : CRCNN_ERR_CUDA; }
+
+int crcnn_stream_create(crcnn_ctx *ctx, void **stream) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(stream, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t s;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return CRCNN_OK;
+}
+int crcnn_stream_destroy(crcnn_ctx *ctx, void *stream) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (stream) CU(cudaStreamDestroy((cudaStream_t)stream));
+    return CRCNN_OK;
+}
+int crcnn_event_create(crcnn_ctx *ctx, void **event) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(event, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    *event = e;
+    return CRCNN_OK;
+}
+int crcnn_event_record(crcnn_ctx *ctx, void *event, void *stream) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(event, "null argument");
+    CU(cudaEventRecord((cudaEvent_t)event, stream ? (cudaStream_t)stream : ctx->stream));
+    return CRCNN_OK;
+}
+int crcnn_stream_wait_event(crcnn_ctx *ctx, void *stream, void *event) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(event, "null argument");
+    CU(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : ctx->stream, (cudaEvent_t)event, 0));
+    return CRCNN_OK;
+}
+int crcnn_event_elapsed_ms(crcnn_ctx *ctx, void *first, void *second, double *ms) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(first && second && ms, "null argument");
+    CU(cudaEventSynchronize((cudaEvent_t)second));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, (cudaEvent_t)first, (cudaEvent_t)second));
+    *ms = t;
+    return CRCNN_OK;
+}
+int crcnn_event_destroy(crcnn_ctx *ctx, void *event) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (event) CU(cudaEventDestroy((cudaEvent_t)event));
+    return CRCNN_OK;
+}
+/* Non-blocking download: enqueues the device->host copy of t (coefficient form) on the context's stream; host_words must be pinned
+ * and is complete once an event recorded afterwards has fired (or after crcnn_ctx_sync).  The pad words are written too. */
+int crcnn_tensor_download_async(crcnn_ctx *ctx, crcnn_tensor *t, uint64_t *host) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(t && host, "null argument");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_domain(ctx, t, 0);
+    if (rc) return rc;
+    const size_t n = ctx->n, rows = (size_t)t->count * t->size * ctx->K;
+    if (!rows) return CRCNN_OK;
+    // re-pad on the device (pad word = 0), then ONE contiguous copy: a strided cudaMemcpy2D reaches a tenth of the link rate
+    uint64_t *padded = nullptr;
+    rc = dev_alloc(ctx, rows * (n + 1) * 8, (void **)&padded);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(padded, 0, rows * (n + 1) * 8, ctx->stream));
+    CU(cudaMemcpy2DAsync(padded, (n + 1) * 8, t->d, n * 8, n * 8, rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(host, padded, rows * (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    dev_free(ctx, padded);
+    return CRCNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------- NCCL all-gather of ciphertexts
+// Output-neuron sharding (the reference's thread split, CrCNN/src/convolutionalLayer.cpp:177-187,
+// fullyConnectedLayer.cpp:148-158, taken across GPUs): every rank computes a contiguous range of a layer's output channels /
+// rows; before a layer that consumes all channels the ranks exchange their ciphertexts over NVLink.  The exchange is one NCCL
+// group of point-to-point sends and receives (an all-gather with per-rank counts) enqueued on the context's stream: no host
+// synchronisation, no staging copy -- each rank's block lands at its final offset of the gathered tensor.  NCCL is loaded at run
+// time (dlopen of libnccl.so.2: the copy torch has already mapped when there is one, else the system's), so the library has no
+// link-time dependency and single-GPU users never touch it.
+namespace {
+struct NcclId128 { char b[128]; };   // ncclUniqueId is passed BY VALUE (nccl.h: struct { char internal[128]; })
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId128, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    std::string why;
+};
+NcclApi &nccl() {
+    static NcclApi api = [] {
+        NcclApi a;
+        const char *names[] = {getenv("CRCNN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) { a.why = std::string("libnccl.so.2 not found (set CRCNN_NCCL_LIB): ") + (dlerror() ? dlerror() : ""); return a; }
+        auto sym = [&](const char *n) { void *p = dlsym(a.lib, n); if (!p) a.why = std::string("missing NCCL symbol ") + n; return p; };
+        a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+        a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+        a.Send = (decltype(a.Send))sym("ncclSend");
+        a.Recv = (decltype(a.Recv))sym("ncclRecv");
+        a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+        return a;
+    }();
+    return api;
+}
+constexpr int kNcclUint64 = 5;   // ncclUint64 (nccl.h: ncclDataType_t)
+}  // namespace
+
+struct crcnn_comm {
+    void *comm = nullptr;
+    int world = 1, rank = 0;
+};
+
+#define NCCLCHECK(call)                                                                                              \
+    do {                                                                                                             \
+        int r__ = (call);                                                                                            \
+        if (r__ != 0) return fail(ctx, CRCNN_ERR_CUDA, std::string(#call) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r__) : "NCCL error")); \
+    } while (0)
+
+int crcnn_comm_unique_id(void *id128) {
+    crcnn_ctx *ctx = nullptr;
+    if (!id128) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (!nccl().why.empty()) return fail(nullptr, CRCNN_ERR_UNSUPPORTED, nccl().why);
+    NCCLCHECK(nccl().GetUniqueId(id128));
+    return CRCNN_OK;
+}
+int crcnn_comm_create(crcnn_ctx *ctx, const void *id128, int world, int rank, crcnn_comm **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(id128 && out && world >= 1 && rank >= 0 && rank < world, "bad communicator arguments");
+    if (!nccl().why.empty()) return fail(ctx, CRCNN_ERR_UNSUPPORTED, nccl().why);
+    CU(cudaSetDevice(ctx->device));
+    NcclId128 id;
+    std::memcpy(id.b, id128, 128);
+    auto *c = new crcnn_comm;
+    c->world = world; c->rank = rank;
+    int r = nccl().CommInitRank(&c->comm, world, id, rank);
+    if (r != 0) { delete c; return fail(ctx, CRCNN_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r)); }
+    *out = c;
+    return CRCNN_OK;
+}
+int crcnn_comm_destroy(crcnn_ctx *ctx, crcnn_comm *c) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (!c) return CRCNN_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (c->comm) nccl().CommDestroy(c->comm);
+    delete c;
+    return CRCNN_OK;
+}
+int crcnn_comm_all_gather(crcnn_ctx *ctx, crcnn_comm *c, crcnn_tensor *local, int batch, const long *counts, int want_ntt_form,
+                          crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(c && local && counts && out && batch > 0, "null argument");
+    long total = 0, before = 0;
+    for (int r = 0; r < c->world; r++) { REQUIRE(counts[r] >= 0, "negative shard size"); if (r < c->rank) before += counts[r]; total += counts[r]; }
+    REQUIRE(local->count == (long)batch * counts[c->rank], "local tensor does not hold batch x counts[rank] ciphertexts");
+    CU(cudaSetDevice(ctx->device));
+    // the gathered tensor carries ONE domain flag: with want_ntt_form >= 0 every rank first brings its block into that domain; with -1 the
+    // blocks are exchanged as they are (all ranks of a sharded layer produce the same domain: the kernel is chosen from the layer's
+    // total output count, run_weighted_sum, and pooling / batch-norm / square map a domain to a domain)
+    int rc = want_ntt_form >= 0 ? ensure_domain(ctx, local, want_ntt_form ? 1 : 0) : CRCNN_OK;
+    if (rc) return rc;
+    crcnn_tensor *full = nullptr;
+    rc = new_tensor(ctx, (long)batch * total, local->size, local->ntt, &full);
+    if (rc) return rc;
+    const size_t ctw = (size_t)local->size * poly_words(ctx);
+    // image b of the gathered tensor = [rank 0's ciphertexts of b | rank 1's | ...]
+    if (c->world > 1) NCCLCHECK(nccl().GroupStart());
+    for (int b = 0; b < batch; b++) {
+        const uint64_t *mine = local->d + (size_t)b * counts[c->rank] * ctw;
+        long off = 0;
+        for (int r = 0; r < c->world; r++) {
+            uint64_t *dst = full->d + ((size_t)b * total + off) * ctw;
+            if (r == c->rank) {
+                if (counts[r]) CU(cudaMemcpyAsync(dst, mine, (size_t)counts[r] * ctw * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            } else {
+                if (counts[c->rank]) NCCLCHECK(nccl().Send(mine, (size_t)counts[c->rank] * ctw, kNcclUint64, r, c->comm, ctx->stream));
+                if (counts[r]) NCCLCHECK(nccl().Recv(dst, (size_t)counts[r] * ctw, kNcclUint64, r, c->comm, ctx->stream));
+            }
+            off += counts[r];
+        }
+    }
+    if (c->world > 1) NCCLCHECK(nccl().GroupEnd());
+    (void)before;
+    *out = full;
+    return CRCNN_OK;
 }
 
 }  // extern "C"

@@ -75,6 +75,20 @@ SYMBOLS = [
     ("crcnn_prof_get", _I, [_vp, _I, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_double)]),
     ("crcnn_prof_get_work", _I, [_vp, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("crcnn_probe_imad", _I, [_vp, _I, _I, _I, C.POINTER(C.c_double)]),
+    ("crcnn_pinned_alloc", _I, [C.c_size_t, _vpp]),
+    ("crcnn_pinned_free", _I, [_vp]),
+    ("crcnn_stream_create", _I, [_vp, _vpp]),
+    ("crcnn_stream_destroy", _I, [_vp, _vp]),
+    ("crcnn_event_create", _I, [_vp, _vpp]),
+    ("crcnn_event_record", _I, [_vp, _vp, _vp]),
+    ("crcnn_stream_wait_event", _I, [_vp, _vp, _vp]),
+    ("crcnn_event_elapsed_ms", _I, [_vp, _vp, _vp, C.POINTER(C.c_double)]),
+    ("crcnn_event_destroy", _I, [_vp, _vp]),
+    ("crcnn_tensor_download_async", _I, [_vp, _vp, _vp]),
+    ("crcnn_comm_unique_id", _I, [_vp]),
+    ("crcnn_comm_create", _I, [_vp, _vp, _I, _I, _vpp]),
+    ("crcnn_comm_destroy", _I, [_vp, _vp]),
+    ("crcnn_comm_all_gather", _I, [_vp, _vp, _vp, _I, C.POINTER(C.c_long), _I, _vpp]),
     ("crcnn_probe_pipe", _I, [_vp, _I, _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 

@@ -164,7 +164,9 @@ class Network:
 # Output-neuron sharding: the reference splits a layer's output
 # filters / rows across std::threads (convolutionalLayer.cpp:177-187, fullyConnectedLayer.cpp:148-158);
 # across GPUs the same split applies, followed by an all-gather of the layer's output ciphertexts
-# before the next layer that consumes every channel.
+# before the next layer that consumes every channel.  The sharded network itself is C++
+# (crcnn_b200::ShardedNetwork in cpp/crcnn_b200.hpp, driven through host.HostNetwork); these two helpers
+# restate its split for the CPU tests of the gather order (tests/test_sharding_gloo.py).
 # ------------------------------------------------------------------------------------------------
 def shard_range(total, world, rank):
     """Contiguous, balanced split of `total` output channels/rows: the first total % world ranks get one more."""
@@ -176,100 +178,3 @@ def shard_range(total, world, rank):
 def gather_counts(total, world, per_channel):
     """Ciphertexts each rank contributes to the all-gather of a [channels][per_channel] activation."""
     return [shard_range(total, world, r)[1] * per_channel for r in range(world)]
-
-
-class ShardedNetwork(Network):
-    """One image (batch 1) with every conv / fc layer split by output channel / row across the ranks of a
-    torch.distributed group; pool, batch-norm and square act on the local channels without any exchange;
-    an all-gather of ciphertexts (NCCL over NVLink on GPUs) precedes every conv / fc layer."""
-
-    def __init__(self, eng, model, dist, weights=None, evk=None):
-        self.dist, self.rank, self.world = dist, dist.get_rank(), dist.get_world_size()
-        super().__init__(eng, model, weights=weights, evk=evk)
-        w = weights if weights is not None else load_weights(model)
-        # per-rank slices of the per-channel parameters of batch-norm layers
-        self.local_bn = {}
-        channels = self.input_shape[0]
-        for layer in self.layers:
-            if layer[0] == "conv":
-                channels = layer[9]
-            elif layer[0] == "bn":
-                k0, kc = shard_range(channels, self.world, self.rank)
-                var = w[layer[1] + ".running_var"].astype(np.float32)
-                invstd = (1.0 / np.sqrt(var.astype(np.float64) + 0.00001)).astype(np.float32)  # double arithmetic, float result: cnnBuilder.cpp:101
-                self.local_bn[layer[1]] = (eng.plain_encode(w[layer[1] + ".running_mean"][k0:k0 + kc]),
-                                           eng.plain_encode(invstd[k0:k0 + kc]))
-
-    def all_gather(self, t, channels, per_channel):
-        """Local [kc][per_channel] ciphertexts -> full [channels][per_channel] on every rank."""
-        import torch
-        eng = self.eng
-        counts = gather_counts(channels, self.world, per_channel)
-        words_per_ct = 2 * eng.K * eng.n
-        full = eng.alloc(sum(counts), 2, ntt_form=eng.device_ptr(t)[1])
-        # shards may differ by one channel: gather max-sized slots, then compact
-        slot = max(counts) * words_per_ct
-        src = _as_torch(eng.device_ptr(t)[0], counts[self.rank] * words_per_ct)
-        dst = _as_torch(eng.device_ptr(full)[0], sum(counts) * words_per_ct)
-        eng.sync()  # the engine's stream produced `t`; the collective runs on torch's stream
-        padded = torch.empty(self.world * slot, dtype=torch.int64, device="cuda")
-        mine = padded[self.rank * slot:self.rank * slot + counts[self.rank] * words_per_ct]
-        mine.copy_(src)
-        self.dist.all_gather_into_tensor(padded, padded[self.rank * slot:(self.rank + 1) * slot].clone())
-        off = 0
-        for r, c in enumerate(counts):
-            dst[off:off + c * words_per_ct].copy_(padded[r * slot:r * slot + c * words_per_ct])
-            off += c * words_per_ct
-        torch.cuda.current_stream().synchronize()
-        return full
-
-    def forward(self, x, on_layer=None):
-        eng = self.eng
-        channels, sharded = self.input_shape[0], False  # `sharded`: x holds only this rank's channels
-        for i, layer in enumerate(self.layers):
-            kind, name = layer[0], layer[1]
-            if kind in ("conv", "fc"):
-                if sharded:
-                    per = (layer[2] * layer[3]) if kind == "conv" else (layer[2] // channels)
-                    y = self.all_gather(x, channels, per)
-                    x.free()
-                    x = y
-                out_total = layer[9] if kind == "conv" else layer[3]
-                k0, kc = shard_range(out_total, self.world, self.rank)
-                wp, bp = self.packs[name]
-                if kind == "conv":
-                    y = eng.conv(x, wp, bp, 1, *layer[2:], shard=(k0, kc))
-                else:
-                    y = eng.fc(x, wp, bp, 1, layer[2], layer[3], shard=(k0, kc))
-                channels, sharded = out_total, True
-            else:
-                k0, kc = shard_range(channels, self.world, self.rank) if sharded else (0, channels)
-                if kind == "pool":
-                    y = eng.pool(x, 1, layer[2], layer[3], kc, *layer[5:])
-                elif kind == "avgpool":
-                    y = eng.pool(x, 1, layer[2], layer[3], kc, *layer[5:], scale=self.packs[name][0])
-                elif kind == "bn":
-                    m, v = self.local_bn[name] if sharded else self.packs[name]
-                    y = eng.bn(x, 1, kc, layer[3], layer[4], m, v)
-                else:
-                    y = eng.square_layer(x, self.evk)
-            if i > 0:
-                x.free()
-            x = y
-            if on_layer is not None:
-                on_layer(i, layer)
-        if sharded:  # final scores: gather the output rows
-            y = self.all_gather(x, channels, 1)
-            x.free()
-            x = y
-        return x
-
-
-class _CudaView:
-    def __init__(self, ptr, words):
-        self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i8", "data": (ptr, False), "version": 2}
-
-
-def _as_torch(ptr, words):
-    import torch
-    return torch.as_tensor(_CudaView(ptr, words), device="cuda")

@@ -34,6 +34,7 @@ typedef struct crcnn_ctx crcnn_ctx;
 typedef struct crcnn_tensor crcnn_tensor; /* device tensor of ciphertexts */
 typedef struct crcnn_plain crcnn_plain;   /* device pack of plaintexts (weights, biases, scale factors) */
 typedef struct crcnn_evk crcnn_evk;       /* device copy of evaluation (relinearisation) keys */
+typedef struct crcnn_comm crcnn_comm;     /* NCCL communicator of a group of contexts, one per GPU (output-neuron sharding) */
 
 typedef enum {
     CRCNN_OK = 0,
@@ -199,6 +200,41 @@ int crcnn_add_many(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_tensor **out);
 int crcnn_square(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_tensor **out3);
 /* Evaluator::relinearize, size 3 -> 2 (SEAL/seal/evaluator.cpp:886-1069). */
 int crcnn_relinearize(crcnn_ctx *ctx, crcnn_tensor *in3, crcnn_evk *evk, crcnn_tensor **out2);
+
+/* ---- host support for a serving loop ------------------------------------------------------------
+ * Replaces: nothing in the reference (its inference loop, CrCNN/src/mainparams.cpp:64-116, is synchronous host code);
+ * these are what a C++17 caller needs to drive the double-buffered loop of crcnn_tensor_upload_into without linking the
+ * CUDA runtime itself: page-locked staging memory, a copy stream, events to order the streams and to time on the device. */
+int crcnn_pinned_alloc(size_t bytes, void **out);
+int crcnn_pinned_free(void *p);
+int crcnn_stream_create(crcnn_ctx *ctx, void **stream);
+int crcnn_stream_destroy(crcnn_ctx *ctx, void *stream);
+int crcnn_event_create(crcnn_ctx *ctx, void **event);
+int crcnn_event_record(crcnn_ctx *ctx, void *event, void *stream);      /* stream NULL: the context's stream */
+int crcnn_stream_wait_event(crcnn_ctx *ctx, void *stream, void *event); /* stream NULL: the context's stream */
+int crcnn_event_elapsed_ms(crcnn_ctx *ctx, void *first, void *second, double *ms); /* waits for `second` */
+int crcnn_event_destroy(crcnn_ctx *ctx, void *event);
+/* Enqueue the download of t (coefficient form, pad words written) into PINNED host memory on the context's stream and return;
+ * the data is complete when an event recorded afterwards has fired.  Lets the score download of request i overlap request i+1. */
+int crcnn_tensor_download_async(crcnn_ctx *ctx, crcnn_tensor *t, uint64_t *host_words);
+
+/* ---- output-neuron sharding across GPUs ------------------------------------------------------------
+ * Replaces: the reference's split of a layer's output filters / rows over std::threads
+ * (CrCNN/src/convolutionalLayer.cpp:177-187, fullyConnectedLayer.cpp:148-158); across GPUs the same split is
+ * crcnn_conv_forward_shard / crcnn_fc_forward_shard on every rank followed by this all-gather of the layer's output
+ * ciphertexts over NVLink before the next layer that consumes every channel.
+ * One process per GPU: rank 0 calls crcnn_comm_unique_id and hands the 128 bytes to the other ranks by any means (file, socket,
+ * torch.distributed), every rank then calls crcnn_comm_create with its context.  NCCL is loaded at run time (libnccl.so.2;
+ * env CRCNN_NCCL_LIB overrides), CRCNN_ERR_UNSUPPORTED if it is absent. */
+int crcnn_comm_unique_id(void *id128);
+int crcnn_comm_create(crcnn_ctx *ctx, const void *id128, int world, int rank, crcnn_comm **out);
+int crcnn_comm_destroy(crcnn_ctx *ctx, crcnn_comm *comm);
+/* local holds batch x counts[rank] ciphertexts ([batch][own channels][positions]); *out gets batch x sum(counts), image b being
+ * rank 0's ciphertexts of b, then rank 1's, ... .  Enqueued on the context's stream as ONE NCCL group of sends / receives, no
+ * host synchronisation.  want_ntt_form 0 / 1: every rank first brings its block into that domain; -1: the blocks are exchanged as
+ * they are (all ranks of a sharded layer produce one domain: kernels are chosen from the layer's total output count). */
+int crcnn_comm_all_gather(crcnn_ctx *ctx, crcnn_comm *comm, crcnn_tensor *local, int batch, const long *counts,
+                          int want_ntt_form, crcnn_tensor **out);
 
 /* ---- measurement ------------------------------------------------------------------------------
  * Kernel classes are timed with CUDA events on the context's stream while profiling is on. */

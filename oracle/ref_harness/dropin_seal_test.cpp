@@ -113,9 +113,35 @@ int main(int argc, char **argv) {
             b = net.getLayer(i)->forward(b);
             ok = same(a, b, ref.getLayer(i)->getName().c_str()) && ok;
         }
-        // whole network device-resident
+        // whole network device-resident.  Seven layers > layer_before_reenc = 6: without a re-encryption callback and without an
+        // explicit opt-out Network::forward refuses (the reference would re-encrypt here, network.cpp:30)
+        bool refused = false;
+        try { net.forward(x); } catch (const std::logic_error &) { refused = true; }
+        std::cout << "forward without re-encryption policy refused: " << refused << "\n";
+        ok = ok && refused;
+        net.skip_reencryption = true;
         ciphertext3D c = net.forward(x);
-        ok = same(a, c, "Network::forward (device resident)") && ok;
+        ok = same(a, c, "Network::forward (device resident, re-encryption skipped)") && ok;
+        // the reference's behaviour: decrypt + encrypt before layer 6 (network.cpp:30-33), done by the key holder in the callback.
+        // Encryption is randomised, so the re-encrypted tensor is captured and pushed through the REFERENCE's layer 6 for comparison.
+        net.skip_reencryption = false;
+        ciphertext3D captured;
+        int calls = 0;
+        net.reencrypt = [&](gpu::ciphertext3D mid) {
+            calls++;
+            floatCube image = decryptImage(mid);   // CrCNN/src/globals.cpp (SEAL Decryptor + FractionalEncoder::decode)
+            captured = encryptImage(image);        // fresh ciphertexts, full noise budget
+            return captured;
+        };
+        ciphertext3D d = net.forward(x);
+        ciphertext3D e = captured;
+        for (int i = 6; i < ref.getNumLayers(); i++) e = ref.getLayer(i)->forward(e);
+        ok = same(e, d, "Network::forward with the re-encryption callback (segments [0,6) + [6,7))") && ok;
+        ok = ok && calls == 1 && captured.size() == 4 && captured[0].size() == 2 && captured[0][0].size() == 2;
+        int nb_d = decryptor->invariant_noise_budget(d[0][0][0]);
+        std::cout << "re-encryption callback calls " << calls << ", budget after re-encrypted tail " << nb_d << " bits\n";
+        net.reencrypt = nullptr;
+        net.skip_reencryption = true;
 
         floatCube sa = decryptImage(a), sc = decryptImage(c);  // SEAL decryption, client side
         int arg_a = 0, arg_c = 0;

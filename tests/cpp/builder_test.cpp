@@ -43,8 +43,40 @@ int main(int argc, char **argv) {
         auto *conv1 = static_cast<ConvolutionalLayer *>(net.getLayer(0).get());
         conv1->getKernel(0)[0][0][0].save(out);
         conv1->getBias(0).save(out);
+        // nine-layer topologies reach the reference's re-encryption point (network.cpp:23,30): refuse unless the caller decides
+        bool refused = !net.needs_reencryption();
+        try { net.forward(x); } catch (const logic_error &) { refused = true; }
+        cout << "reencryption_policy_enforced " << refused << "\n";
+        net.skip_reencryption = true;
         ciphertext3D y = net.forward(x);
         for (auto &pl : y) for (auto &row : pl) for (auto &ct : row) ct.save(out);
+        // segment API on proper sub-ranges + an identity "re-encryption" callback: same bytes as the single pass
+        auto equal3 = [&](const ciphertext3D &p, const ciphertext3D &q) {
+            if (p.size() != q.size() || p[0].size() != q[0].size() || p[0][0].size() != q[0][0].size()) return false;
+            for (size_t a = 0; a < p.size(); a++) for (size_t b = 0; b < p[a].size(); b++) for (size_t c = 0; c < p[a][b].size(); c++)
+                if (memcmp(p[a][b][c].data(), q[a][b][c].data(), rt.ct_words() * 8)) return false;
+            return true;
+        };
+        const int L = net.getNumLayers(), cut = L > 6 ? 6 : 3;
+        ciphertext3D seg = download(net.forward_dev(net.forward_dev(upload(x), 0, 2), 2, cut));
+        ciphertext3D rest = download(net.forward_dev(upload(seg), cut, L));
+        cout << "segments_compose " << equal3(rest, y) << "\n";
+        int calls = 0;
+        net.skip_reencryption = false;
+        net.layer_before_reenc = cut;
+        net.reencrypt = [&](ciphertext3D mid) { calls++; return mid; };
+        ciphertext3D y2 = net.forward(x);
+        cout << "reencrypt_callback_path " << (equal3(y2, y) && calls == 1) << "\n";
+        // a batch of two images in one pass == two forwards
+        ciphertext3D x2 = x;
+        swap(x2[0][0][0], x2[0][yd > 1 ? 0 : 0][yd > 1 ? 1 : 0]);
+        swap(x2[0][xd - 1][yd - 1], x2[0][1 % xd][2 % yd]);
+        vector<ciphertext3D> two = {x, x2};
+        vector<ciphertext3D> yb = net.forward_batch(two);
+        ciphertext3D y3 = net.forward(x2);
+        cout << "forward_batch " << (yb.size() == 2 && equal3(yb[0], y) && equal3(yb[1], y3) && !equal3(y3, y) && calls == 4) << "\n";
+        net.reencrypt = nullptr;
+        net.skip_reencryption = true;
 
         // the encoded-network stream of one layer written by savePlaintextParameters is what the istream constructor reads back
         stringstream ss(ios::in | ios::out | ios::binary);

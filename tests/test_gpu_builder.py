@@ -41,6 +41,8 @@ def test_builder_network_matches_python_path(tmp_path, topology, model):
     assert res.returncode == 0 and res.stdout.strip().endswith("OK"), res.stdout + res.stderr
     assert "fc4_bias_count 10" in res.stdout and "saveload_same 1" in res.stdout and "missing_tensor_throws 1" in res.stdout
     assert "image_file_same 1" in res.stdout
+    for flag in ("reencryption_policy_enforced 1", "segments_compose 1", "reencrypt_callback_path 1", "forward_batch 1"):
+        assert flag in res.stdout, res.stdout
     raw = open(out, "rb").read()
     # the two encoded parameters: Plaintext::save records of n+1 words, equal to the oracle's FractionalEncoder restatement
     o = Oracle(n, primes, t)

@@ -80,4 +80,5 @@ def test_seal_mode_dropin_against_reference_classes(n, t):
     exe = os.path.join(ROOT, "oracle", "_ref", "dropin_seal_test")
     res = subprocess.run([exe, str(n), str(t)], capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "DROPIN OK" in res.stdout, res.stdout[-2000:] + res.stderr[-500:]
-    assert res.stdout.count("bit-identical") == 8
+    assert res.stdout.count("bit-identical") == 9   # 7 layers + Network::forward skipped / with the re-encryption callback
+    assert "forward without re-encryption policy refused: 1" in res.stdout and "re-encryption callback calls 1" in res.stdout
