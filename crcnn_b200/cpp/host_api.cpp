@@ -18,6 +18,7 @@ namespace {
 std::string g_err;
 std::unique_ptr<Network> g_net;
 std::unique_ptr<BatchServer> g_srv;
+std::unique_ptr<DeviceTensor> g_x0;   // resident input of crcnn_host_resident_*
 int g_zd = 0, g_xd = 0, g_yd = 0, g_outputs = 0, g_batch = 0;
 
 template <class F> int guarded(F &&f) {
@@ -33,7 +34,7 @@ const char *crcnn_host_last_error() { return g_err.c_str(); }
 
 // setParameters (CrCNN/src/globals.cpp:25-56) as far as evaluation goes
 int crcnn_host_init(int n, int K, const uint64_t *q, uint64_t t, int device) {
-    return guarded([&] { g_srv.reset(); g_net.reset(); Runtime::get().init(n, std::vector<uint64_t>(q, q + K), t, device); });
+    return guarded([&] { g_x0.reset(); g_srv.reset(); g_net.reset(); Runtime::get().init(n, std::vector<uint64_t>(q, q + K), t, device); });
 }
 int crcnn_host_set_evk(const uint64_t *words, const int *sizes, int dbc) {
     return guarded([&] { Runtime::get().setEvaluationKeys(words, sizes, dbc); });
@@ -44,7 +45,7 @@ void *crcnn_host_ctx() { try { return Runtime::get().ctx(); } catch (...) { retu
 // made from nccl_id (crcnn_comm_unique_id on rank 0, handed to every rank by the launcher).
 int crcnn_host_build(const char *h5_path, const char *topology, int world, int rank, const void *nccl_id, int skip_reencryption) {
     return guarded([&] {
-        g_srv.reset(); g_net.reset();
+        g_x0.reset(); g_srv.reset(); g_net.reset();
         CnnBuilder builder(h5_path);
         if (world > 1 || nccl_id) g_net.reset(new ShardedNetwork(world, rank, nccl_id));
         else g_net.reset(new Network());
@@ -81,44 +82,51 @@ int crcnn_host_forward_range(const uint64_t *in_words, int batch, int zd, int xd
     });
 }
 
-// `steps` forwards of the whole network with the input resident in HBM (uploaded once; every step starts from a fresh
-// coefficient-form copy so the input transform is inside the timed region).  ms_total: CUDA events around the steps on the
-// context's stream; per_layer_ms (may be null): mean event time of every layer.
-int crcnn_host_resident_steps(const uint64_t *pinned_in, int batch, int warmup, int steps, double *ms_total, double *per_layer_ms) {
+// Forwards of the whole network with the input resident in HBM.  begin: upload the batch once and keep it; run: `steps` forwards,
+// every one from a fresh coefficient-form copy of the resident input (so the input transform is inside the timed region), timed with
+// CUDA events on the context's stream (ms_total) and per layer (per_layer_ms, mean over the steps; may be null); end: release.
+// Warm-up and timed steps are separate run() calls on the SAME resident tensor, so the caller can put its barrier between them and the
+// stream-ordered allocator sees one steady allocation pattern.
+int crcnn_host_resident_begin(const uint64_t *pinned_in, int batch) {
     return guarded([&] {
         if (!g_net) throw std::invalid_argument("no network built");
         Runtime &rt = Runtime::get();
-        crcnn_ctx *ctx = rt.ctx();
-        const long count = (long)batch * g_zd * g_xd * g_yd;
         crcnn_tensor *x0 = nullptr;
-        rt.check(crcnn_tensor_upload(ctx, pinned_in, count, 2, &x0));
-        DeviceTensor keep(x0, g_zd, g_xd, g_yd, batch);
+        rt.check(crcnn_tensor_upload(rt.ctx(), pinned_in, (long)batch * g_zd * g_xd * g_yd, 2, &x0));
+        g_x0.reset(new DeviceTensor(x0, g_zd, g_xd, g_yd, batch));
+    });
+}
+int crcnn_host_resident_run(int steps, double *ms_total, double *per_layer_ms) {
+    return guarded([&] {
+        if (!g_net || !g_x0) throw std::invalid_argument("crcnn_host_resident_begin has not been called");
+        Runtime &rt = Runtime::get();
+        crcnn_ctx *ctx = rt.ctx();
+        const long count = g_x0->count();
         const int L = g_net->getNumLayers();
         std::vector<void *> ev((size_t)steps * (L + 1), nullptr);
         for (auto &e : ev) rt.check(crcnn_event_create(ctx, &e));
-        auto one = [&](int s) {
+        for (int s = 0; s < steps; s++) {
             crcnn_tensor *c = nullptr;
-            rt.check(crcnn_tensor_slice(ctx, x0, 0, count, &c));
-            DeviceTensor x(c, g_zd, g_xd, g_yd, batch);
-            if (s >= 0) rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1)], nullptr));
+            rt.check(crcnn_tensor_slice(ctx, g_x0->t, 0, count, &c));
+            DeviceTensor x(c, g_zd, g_xd, g_yd, g_x0->batch);
+            rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1)], nullptr));
             for (int i = 0; i < L; i++) {
                 x = g_net->forward_dev(std::move(x), i, i + 1);
-                if (s >= 0) rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1) + i + 1], nullptr));
+                rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1) + i + 1], nullptr));
             }
-        };
-        for (int w = 0; w < warmup; w++) one(-1);
-        rt.check(crcnn_ctx_sync(ctx));
-        for (int s = 0; s < steps; s++) one(s);
-        rt.check(crcnn_event_elapsed_ms(ctx, ev[0], ev[(size_t)(steps - 1) * (L + 1) + L], ms_total));
+        }
+        if (steps > 0 && ms_total) rt.check(crcnn_event_elapsed_ms(ctx, ev[0], ev[(size_t)(steps - 1) * (L + 1) + L], ms_total));
         if (per_layer_ms)
             for (int i = 0; i < L; i++) {
                 double acc = 0;
                 for (int s = 0; s < steps; s++) { double ms; rt.check(crcnn_event_elapsed_ms(ctx, ev[(size_t)s * (L + 1) + i], ev[(size_t)s * (L + 1) + i + 1], &ms)); acc += ms; }
-                per_layer_ms[i] = acc / steps;
+                per_layer_ms[i] = steps ? acc / steps : 0;
             }
+        rt.check(crcnn_ctx_sync(ctx));
         for (auto &e : ev) crcnn_event_destroy(ctx, e);
     });
 }
+int crcnn_host_resident_end() { return guarded([&] { g_x0.reset(); }); }
 
 // The serving loop (BatchServer): `requests` requests of `batch` images, every one uploaded from pinned_in (host, SEAL layout)
 // and its scores downloaded into pinned_out, upload of request i+1 overlapping the forward of request i.  ms_total = device time
@@ -141,6 +149,6 @@ int crcnn_host_serve(const uint64_t *pinned_in, uint64_t *pinned_out, int batch,
     });
 }
 
-void crcnn_host_shutdown() { g_srv.reset(); g_net.reset(); Runtime::get().reset(); }
+void crcnn_host_shutdown() { g_x0.reset(); g_srv.reset(); g_net.reset(); Runtime::get().reset(); }
 
 }  // extern "C"

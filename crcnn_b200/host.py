@@ -35,7 +35,8 @@ def load():
     h.crcnn_host_shape.argtypes = [C.POINTER(_I)] * 5
     h.crcnn_host_layer_name.argtypes = [_I, C.c_char_p, _I]
     h.crcnn_host_forward_range.argtypes = [_vp, _I, _I, _I, _I, _I, _I, _vp, C.c_long, C.POINTER(_I)]
-    h.crcnn_host_resident_steps.argtypes = [_vp, _I, _I, _I, _dp, _dp]
+    h.crcnn_host_resident_begin.argtypes = [_vp, _I]
+    h.crcnn_host_resident_run.argtypes = [_I, _dp, _dp]
     h.crcnn_host_serve.argtypes = [_vp, _vp, _I, C.c_long, _dp]
     _h = h
     return h
@@ -110,11 +111,27 @@ class HostNetwork:
         cnt = batch * z * a * b
         return out[:cnt * self.ct_words()].reshape(cnt, 2, self.K, self.stride).copy(), (z, a, b)
 
-    def resident_steps(self, pinned_ptr, batch, warmup, steps):
+    def resident_begin(self, pinned_ptr, batch):
+        """Upload the batch once; resident_run() then times forwards that start from a fresh device copy of it."""
+        self._chk(self.h.crcnn_host_resident_begin(pinned_ptr, batch))
+
+    def resident_run(self, steps):
+        """(total ms by CUDA events, [ms per layer]) of `steps` forwards of the resident batch."""
         ms = C.c_double()
         per = (C.c_double * self.num_layers)()
-        self._chk(self.h.crcnn_host_resident_steps(pinned_ptr, batch, warmup, steps, C.byref(ms), per))
+        self._chk(self.h.crcnn_host_resident_run(steps, C.byref(ms), per))
         return ms.value, list(per)
+
+    def resident_end(self):
+        self._chk(self.h.crcnn_host_resident_end())
+
+    def resident_steps(self, pinned_ptr, batch, warmup, steps):
+        self.resident_begin(pinned_ptr, batch)
+        if warmup:
+            self.resident_run(warmup)
+        out = self.resident_run(steps)
+        self.resident_end()
+        return out
 
     def serve(self, pinned_in_ptr, pinned_out_ptr, batch, requests):
         ms = C.c_double()

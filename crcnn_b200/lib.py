@@ -154,10 +154,23 @@ class Engine:
         self.h = h
         self.S = self.lib.crcnn_ctx_bsk_count(self.h)
 
+    @classmethod
+    def adopt(cls, ctx_ptr, n, primes, t):
+        """Engine view of a context somebody else owns (the C++ Runtime behind crcnn_b200/host.py): same C ABI calls, no destroy."""
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.n, self.K, self.t = int(n), len(primes), int(t)
+        self.primes = [int(p) for p in primes]
+        self.stride = self.n + 1
+        self.h = C.c_void_p(ctx_ptr)
+        self.owned = False
+        self.S = self.lib.crcnn_ctx_bsk_count(self.h)
+        return self
+
     def close(self):
-        if self.h:
+        if self.h and getattr(self, "owned", True):
             self.lib.crcnn_ctx_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

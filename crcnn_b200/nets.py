@@ -15,6 +15,16 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 WEIGHTS_DIR = os.path.join(os.path.dirname(_HERE), "weights")
 
+# coeff_modulus_128(n) of SEAL 2.3.1 (SEAL/seal/util/globals.cpp:50-74 via defaultparams.h:22-26): the reference's parameter choice
+# (CrCNN/src/globals.cpp:30); tests pin the same table against the compiled reference
+DEFAULT_PRIMES_128 = {
+    2048: [0x3fffffff000001],
+    4096: [0x7fffffff380001, 0x3fffffff000001],
+    8192: [0x7fffffff380001, 0x7ffffffef00001, 0x3fffffff000001, 0x3ffffffef40001],
+    16384: [0x7fffffff380001, 0x7ffffffef00001, 0x7ffffffeac0001, 0x7ffffffe700001,
+            0x7ffffffe600001, 0x7ffffffe4c0001, 0x3fffffff000001, 0x3ffffffef40001],
+}
+
 # layer tuples: (kind, name, args...) with the reference's constructor argument order
 TOPOLOGIES = {
     # cnnBuilder.cpp:115-134
