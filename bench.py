@@ -25,8 +25,18 @@ import time
 
 import numpy as np
 
-# stdout carries exactly ONE JSON line: whatever NCCL has to say (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr
+# stdout carries exactly ONE JSON line: whatever NCCL has to say (its version banner under NCCL_DEBUG=VERSION/INFO) goes to stderr ...
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# ... and so does anything a native library writes to file descriptor 1 directly: fd 1 points at stderr for the whole run, the JSON line
+# goes to a duplicate of the original stdout (emit()).
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -250,7 +260,7 @@ def main_reference(args, rank, world):
     from oracle import ref as oref
     steps, warm = max(1, args.steps), max(0, args.warmup)
     if not oref.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libcrcnn_ref.so was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libcrcnn_ref.so was not built (needs /root/reference at build time)"})
         return
     rng = np.random.default_rng(0)
     per_step = max(4.0, 150.0 / (steps + warm))
@@ -271,7 +281,7 @@ def main_reference(args, rank, world):
         "per_layer_ms": {k: 1000 * s for k, s in full.items()},
     }
     line["cpu_baseline"].update(extra)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------
@@ -363,13 +373,13 @@ def main_shard(args, rank, world, local_rank):
     res = run_sharded(dist, rank, world, local_rank, args.batch, args.steps, max(3, args.warmup))
     clocks = sampler.stop()
     if rank == 0:
-        print(json.dumps({
+        emit({
             "metric": "encrypted MNIST images/sec", "value": res["images_per_s"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_batch"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic: uniform residues in SEAL ciphertext layout; weights = ApproxPlainModel.h5",
             "config": {"workload": "ApproxPlainModel.h5 encoded net, n=8192, K=4, t=2^30, one batch of %d images, conv/fc layers sharded by output neuron" % args.batch,
                        "parallelism": "output-neuron shards x%d, NCCL all-gather of activation ciphertexts before conv2 / fc3 / fc4 and of the scores" % world},
-            "shard": res, "clocks": clocks}))
+            "shard": res, "clocks": clocks})
     if dist is not None:
         dist.destroy_process_group()
 
@@ -610,7 +620,7 @@ def main_b200(args, rank, world, local_rank):
             if rank == 0:
                 line["shard"] = {"failed": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

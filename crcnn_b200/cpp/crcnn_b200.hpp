@@ -583,8 +583,8 @@ public:
     AvgPoolingLayer(std::string name, int xd, int yd, int zd, int xs, int ys, int xf, int yf)
         : PoolingLayer(name, xd, yd, zd, xs, ys, xf, yf) {
         Runtime &rt = Runtime::get();
-        float v = (float)(1. / (xf * yf));
-        rt.check(crcnn_plain_encode(rt.ctx(), &v, 1, &pack_.p));
+        double v = 1. / (xf * yf);   // a double, as in the reference (avgPoolingLayer.cpp:12): 1/9 as a float has other base-3 digits
+        rt.check(crcnn_plain_encode_f64(rt.ctx(), &v, 1, &pack_.p));
         div_factor = Plaintext(rt.n() + 1);
         rt.check(crcnn_plain_get(rt.ctx(), pack_.p, 0, div_factor.data()));
     }
@@ -778,9 +778,15 @@ public:
     // Segment API: layers [first, last) without leaving the device; any batch.
     virtual DeviceTensor forward_dev(DeviceTensor x, int first, int last) {
         if (first < 0 || last > (int)layers.size() || first > last) throw std::invalid_argument("bad layer range");
-        for (int i = first; i < last; i++) x = layers[i]->forward_dev(std::move(x));
+        for (int i = first; i < last; i++) {
+            x = layers[i]->forward_dev(std::move(x));
+            if (after_layer) after_layer(i);
+        }
         return x;
     }
+    // Called after layer i has been ENQUEUED (nothing has necessarily run yet): the place to record a CUDA event for per-layer timing,
+    // the counterpart of the reference's commented-out chrono timers around layers[i]->forward (network.cpp:39-43).
+    std::function<void(int)> after_layer;
     bool needs_reencryption() const { return layer_before_reenc > 0 && layer_before_reenc < (int)layers.size(); }
     ciphertext3D forward(ciphertext3D input) {
         const int L = (int)layers.size();
@@ -939,6 +945,7 @@ public:
             } else {
                 x = l->forward_dev(std::move(x));   // pooling and square are per channel / per ciphertext: local channels, no exchange
             }
+            if (after_layer) after_layer(i);        // a layer's time includes the all-gather in front of it
         }
         if (sharded) {
             x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);

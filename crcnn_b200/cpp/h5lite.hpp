@@ -52,11 +52,26 @@ public:
         auto it = ds_.find(name);
         if (it == ds_.end()) throw std::runtime_error("h5lite: no dataset named " + name);
         const H5Dataset &d = it->second;
-        const std::uint64_t cnt = d.count();
+        // sizes come from the file: nothing below trusts them (element size in {1,2,4,8}, element count x size computed without wrap-around
+        // and compared with what is really there)
+        if (d.type_size != 1 && d.type_size != 2 && d.type_size != 4 && d.type_size != 8)
+            throw std::runtime_error("h5lite: unsupported element size " + std::to_string(d.type_size) + " in " + name);
+        if (d.type_class == 1 && d.type_size < 4) throw std::runtime_error("h5lite: unsupported float size in " + name);
+        std::uint64_t cnt = 1;
+        for (auto dim : d.dims) {
+            if (dim != 0 && cnt > (std::uint64_t)buf_.size() / dim) throw std::runtime_error("h5lite: dataset dimensions exceed the file: " + name);
+            cnt *= dim;
+        }
+        if (cnt > (std::uint64_t)buf_.size() / (unsigned)d.type_size) throw std::runtime_error("h5lite: dataset payload beyond end of file: " + name);
+        const std::uint64_t need_bytes = cnt * (unsigned)d.type_size;
         const unsigned char *p;
-        if (!d.compact.empty()) p = d.compact.data();
-        else {
-            if (d.address + cnt * d.type_size > buf_.size()) throw std::runtime_error("h5lite: dataset payload beyond end of file: " + name);
+        if (!d.compact.empty()) {
+            if (need_bytes > d.compact.size()) throw std::runtime_error("h5lite: compact payload shorter than the dataspace: " + name);
+            p = d.compact.data();
+        } else {
+            if (cnt == 0) return {};
+            if (d.address > buf_.size() || need_bytes > buf_.size() - d.address || need_bytes > d.bytes)
+                throw std::runtime_error("h5lite: dataset payload beyond end of file: " + name);
             p = bytes(d.address);
         }
         std::vector<double> out(cnt);
@@ -80,6 +95,7 @@ private:
     std::vector<char> buf_;
     std::map<std::string, H5Dataset> ds_;
     int so_ = 8, sl_ = 8;  // size of offsets / lengths
+    long nodes_ = 0;       // B-tree nodes visited (cycle guard)
     std::uint64_t base_ = 0;
 
     const unsigned char *bytes(std::uint64_t off) const { return reinterpret_cast<const unsigned char *>(buf_.data()) + off; }
@@ -104,6 +120,7 @@ private:
         so_ = bytes(0)[13];
         sl_ = bytes(0)[14];
         if (so_ != 8 && so_ != 4) throw std::runtime_error("h5lite: unsupported offset size");
+        if (sl_ != 8 && sl_ != 4) throw std::runtime_error("h5lite: unsupported length size");
         std::uint64_t at = 24 + (version == 1 ? 4 : 0);
         base_ = le(at, so_);
         at += 4 * so_;  // base, free-space info, end of file, driver info
@@ -119,7 +136,8 @@ private:
         return base_ + le(heap + 8 + 2 * sl_, so_);
     }
 
-    void walk_tree(std::uint64_t node, std::uint64_t names) {
+    void walk_tree(std::uint64_t node, std::uint64_t names, int depth = 0) {
+        if (depth > 32 || ++nodes_ > 1000000) throw std::runtime_error("h5lite: B-tree too deep or cyclic");
         if (!sig(node, "TREE")) throw std::runtime_error("h5lite: bad B-tree node");
         const int type = bytes(node)[4], level = bytes(node)[5];
         const int used = (int)le(node + 6, 2);
@@ -129,7 +147,7 @@ private:
             at += sl_;  // key i
             const std::uint64_t child = base_ + le(at, so_);
             at += so_;
-            if (level > 0) walk_tree(child, names);
+            if (level > 0) walk_tree(child, names, depth + 1);
             else symbol_node(child, names);
         }
     }
@@ -156,6 +174,7 @@ private:
         if (bytes(at)[0] != 1) throw std::runtime_error("h5lite: object header version " + std::to_string(bytes(at)[0]) + " not supported");
         int remaining = (int)le(at + 2, 2);
         std::uint64_t block = at + 16, block_end = block + le(at + 8, 4);
+        need(block, block_end - block);
         std::vector<std::pair<std::uint64_t, std::uint64_t>> more;
         bool have_space = false, have_type = false, have_layout = false;
         while (remaining > 0) {
@@ -171,12 +190,15 @@ private:
             need(body, size);
             remaining--;
             if (type == 0x0001) {  // dataspace
+                if (size < 4) throw std::runtime_error("h5lite: truncated dataspace message");
                 const int ver = bytes(body)[0], rank = bytes(body)[1];
+                if (rank > 32) throw std::runtime_error("h5lite: dataspace rank out of range");
                 const std::uint64_t dims = body + (ver == 1 ? 8 : 4);
                 d.dims.clear();
                 for (int r = 0; r < rank; r++) d.dims.push_back(le(dims + (std::uint64_t)r * sl_, sl_));
                 have_space = true;
             } else if (type == 0x0003) {  // datatype
+                if (size < 8) throw std::runtime_error("h5lite: truncated datatype message");
                 d.type_class = bytes(body)[0] & 0x0f;
                 d.big_endian = (bytes(body)[1] & 1) != 0;
                 d.is_signed = d.type_class == 0 ? (bytes(body)[1] & 8) != 0 : true;
@@ -197,7 +219,10 @@ private:
                 } else throw std::runtime_error("h5lite: chunked datasets are not supported");
                 have_layout = true;
             } else if (type == 0x0010) {  // continuation
-                more.push_back({base_ + le(body, so_), le(body + so_, sl_)});
+                if (more.size() > 64) throw std::runtime_error("h5lite: too many header continuation blocks");
+                const std::uint64_t cont = base_ + le(body, so_), clen = le(body + so_, sl_);
+                need(cont, clen);
+                more.push_back({cont, clen});
             }
             block = body + ((size + 7) & ~7);
         }

@@ -110,10 +110,12 @@ int crcnn_host_resident_run(int steps, double *ms_total, double *per_layer_ms) {
             rt.check(crcnn_tensor_slice(ctx, g_x0->t, 0, count, &c));
             DeviceTensor x(c, g_zd, g_xd, g_yd, g_x0->batch);
             rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1)], nullptr));
-            for (int i = 0; i < L; i++) {
-                x = g_net->forward_dev(std::move(x), i, i + 1);
-                rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1) + i + 1], nullptr));
-            }
+            // ONE pass over the whole network (a sharded network keeps its activations sharded between layers); an event after every layer.
+            // The final all-gather of a sharded network lands after the last layer's event: one more event closes the step.
+            g_net->after_layer = [&](int i) { rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1) + i + 1], nullptr)); };
+            x = g_net->forward_dev(std::move(x), 0, L);
+            g_net->after_layer = nullptr;
+            rt.check(crcnn_event_record(ctx, ev[(size_t)s * (L + 1) + L], nullptr));
         }
         if (steps > 0 && ms_total) rt.check(crcnn_event_elapsed_ms(ctx, ev[0], ev[(size_t)(steps - 1) * (L + 1) + L], ms_total));
         if (per_layer_ms)

@@ -837,6 +837,18 @@ int crcnn_plain_encode(crcnn_ctx *ctx, const float *values, long count, crcnn_pl
     return make_plain(ctx, std::move(off), std::move(idx), std::move(val), out);
 }
 
+int crcnn_plain_encode_f64(crcnn_ctx *ctx, const double *values, long count, crcnn_plain **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(values && out && count >= 0, "bad encode arguments");
+    std::vector<uint32_t> off(count + 1, 0), idx;
+    std::vector<uint64_t> val;
+    for (long i = 0; i < count; i++) {
+        encode_fractional_sparse(values[i], ctx->n, ctx->hp.d.t, idx, val);
+        off[i + 1] = (uint32_t)idx.size();
+    }
+    return make_plain(ctx, std::move(off), std::move(idx), std::move(val), out);
+}
+
 int crcnn_plain_get(crcnn_ctx *ctx, const crcnn_plain *p, long index, uint64_t *out_words) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(p && out_words && index >= 0 && index < p->count, "plaintext index out of range");

@@ -50,6 +50,7 @@ SYMBOLS = [
     ("crcnn_plain_upload", _I, [_vp, _u64p, _L, _I, _L, _vpp]),
     ("crcnn_plain_upload_sparse", _I, [_vp, _u32p, _u64p, _u32p, _L, _vpp]),
     ("crcnn_plain_encode", _I, [_vp, _f32p, _L, _vpp]),
+    ("crcnn_plain_encode_f64", _I, [_vp, C.POINTER(C.c_double), _L, _vpp]),
     ("crcnn_plain_get", _I, [_vp, _vp, _L, _u64p]),
     ("crcnn_plain_get_ntt", _I, [_vp, _vp, _L, _u64p]),
     ("crcnn_plain_free", _I, [_vp, _vp]),
@@ -282,6 +283,11 @@ class Engine:
     def plain_encode(self, values):
         v = np.ascontiguousarray(values, dtype=np.float32).ravel()
         return self._new(self.lib.crcnn_plain_encode, "plain", v.ctypes.data_as(_f32p), len(v))
+
+    def plain_encode_f64(self, values):
+        """FractionalEncoder::encode on doubles (avg-pool's 1./(xf*yf), avgPoolingLayer.cpp:10-13)."""
+        v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+        return self._new(self.lib.crcnn_plain_encode_f64, "plain", v.ctypes.data_as(C.POINTER(C.c_double)), len(v))
 
     def plain_get(self, p, index):
         out = np.zeros(self.stride, dtype=np.uint64)

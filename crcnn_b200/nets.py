@@ -129,7 +129,7 @@ class Network:
                 self.packs[name] = (eng.plain_encode(w[name + ".running_mean"]), eng.plain_encode(invstd))
             elif kind == "avgpool":
                 xf, yf = layer[7], layer[8]
-                self.packs[name] = (eng.plain_encode([1.0 / (xf * yf)]),)  # avgPoolingLayer.cpp:10-13
+                self.packs[name] = (eng.plain_encode_f64([1.0 / (xf * yf)]),)  # encode(1./(xf*yf)) on a DOUBLE: avgPoolingLayer.cpp:10-13
 
     def num_layers(self):
         return len(self.layers)

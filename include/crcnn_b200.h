@@ -143,6 +143,10 @@ int crcnn_plain_upload_sparse(crcnn_ctx *ctx, const uint32_t *idx, const uint64_
 /* Encode floats exactly as CnnBuilder does: FractionalEncoder(t, x^n+1, 64, 32, base 3).encode(v)
  * (CrCNN/src/cnnBuilder.cpp:25-105, CrCNN/src/globals.cpp:52) -- SURVEY 8(f) row N1. */
 int crcnn_plain_encode(crcnn_ctx *ctx, const float *values, long count, crcnn_plain **out);
+/* The same encoder on doubles: FractionalEncoder::encode takes a double, and the reference hands it one where it does not come
+ * from a float tensor -- AvgPoolingLayer's div_factor = encode(1./(xf*yf)) (CrCNN/src/avgPoolingLayer.cpp:10-13): for a window
+ * area that is not a power of two the base-3 digits of the float and the double differ from about the 15th on. */
+int crcnn_plain_encode_f64(crcnn_ctx *ctx, const double *values, long count, crcnn_plain **out);
 /* Coefficient-form words of plaintext `index` (n+1 words, zero padded) -- for parity checks. */
 int crcnn_plain_get(crcnn_ctx *ctx, const crcnn_plain *p, long index, uint64_t *out_words);
 int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p);

@@ -126,7 +126,7 @@ def check_layer(eng, orc, net, i, x, y, B, rng, samples, evk_host=None, pool=Non
         elif kind in ("pool", "avgpool"):
             _, _, xd, yd, zd, xs, ys, xf, yf = layer
             if kind == "avgpool":
-                d, cc = orc.encode(float(np.float32(1.0 / (xf * yf))))
+                d, cc = orc.encode(1.0 / (xf * yf))   # a double: avgPoolingLayer.cpp:10-13
                 want = orc.pool(xin, xf, yf, 1, 1, 1, xf, yf, d, cc)
             else:
                 want = orc.pool(xin, xf, yf, 1, 1, 1, xf, yf)

@@ -243,16 +243,17 @@ def test_fc_layer_batched(env):
 @pytest.mark.parametrize("avg", [False, True])
 def test_pool_layers(env, avg):
     n, primes, t, eng, orc, rng = env
-    for (xd, yd, zd, xs, ys, xf, yf) in [(5, 5, 2, 1, 1, 2, 2), (6, 4, 3, 2, 2, 2, 2)]:
+    # 3x3 windows: 1/9 is not a dyadic value -- the scale factor must be encoded from the DOUBLE (avgPoolingLayer.cpp:10-13)
+    for (xd, yd, zd, xs, ys, xf, yf) in [(5, 5, 2, 1, 1, 2, 2), (6, 4, 3, 2, 2, 2, 2), (5, 4, 2, 1, 1, 3, 3), (6, 6, 1, 3, 3, 3, 3)]:
         x = random_cts(rng, n, primes, zd * xd * yd)
         if avg:
             d, cc = orc.encode(1.0 / (xf * yf))
             want = orc.pool(x, xd, yd, zd, xs, ys, xf, yf, d, cc)
-            got = eng.download(eng.pool(eng.upload(x), 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode([1.0 / (xf * yf)])))
+            got = eng.download(eng.pool(eng.upload(x), 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode_f64([1.0 / (xf * yf)])))
             # coefficient-form input takes the coefficient-domain multiply; NTT-form input the NTT-domain kernel
             tn = eng.upload(x)
             eng.to_ntt(tn)
-            got_n = eng.download(eng.pool(tn, 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode([1.0 / (xf * yf)])))
+            got_n = eng.download(eng.pool(tn, 1, xd, yd, zd, xs, ys, xf, yf, scale=eng.plain_encode_f64([1.0 / (xf * yf)])))
             assert np.array_equal(got_n.reshape(want.shape), want)
         else:
             want = orc.pool(x, xd, yd, zd, xs, ys, xf, yf)

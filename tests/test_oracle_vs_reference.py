@@ -79,6 +79,13 @@ def test_layers(pair):
     assert np.array_equal(r.pool(xi, 3, 3, 2, 1, 1, 2, 2), o.pool(xi, 3, 3, 2, 1, 1, 2, 2))
     d, cc = o.encode(0.25)
     assert np.array_equal(r.pool(xi, 3, 3, 2, 1, 1, 2, 2, avg=True), o.pool(xi, 3, 3, 2, 1, 1, 2, 2, d, cc))
+    # a window area that is not a power of two: the reference encodes the DOUBLE 1./(xf*yf) (avgPoolingLayer.cpp:10-13); the float32
+    # value of 1/9 has other base-3 digits from about the 15th on and must NOT reproduce the reference's bytes
+    d9, cc9 = o.encode(1.0 / 9.0)
+    want9 = r.pool(xi, 3, 3, 2, 1, 1, 3, 3, avg=True)
+    assert np.array_equal(want9, o.pool(xi, 3, 3, 2, 1, 1, 3, 3, d9, cc9))
+    f9, fc9 = o.encode(float(np.float32(1.0 / 9.0)))
+    assert not np.array_equal(d9, f9) and not np.array_equal(want9, o.pool(xi, 3, 3, 2, 1, 1, 3, 3, f9, fc9))
     assert np.array_equal(r.bn(xi, 2, 3, 3, [0.3, -0.2], [1.7, 0.9]),
                           o.bn(xi, 2, 3, 3, o.encode_many([0.3, -0.2]), o.encode_many([1.7, 0.9])))
     ev, sizes, dbc = r.evk()

@@ -45,7 +45,7 @@ class _Net:
                 w, bias = self.params[name]
                 y = o.conv(xs_[b], *layer[2:], o.encode_many(w), o.encode_many(bias))
             elif kind == "avgpool":
-                d, cc = o.encode(float(np.float32(1.0 / (layer[7] * layer[8]))))
+                d, cc = o.encode(1.0 / (layer[7] * layer[8]))
                 y = o.pool(xs_[b], *layer[2:], d, cc)
             elif kind == "pool":
                 y = o.pool(xs_[b], *layer[2:])
