@@ -221,11 +221,15 @@ def run_reference_sample(budget_s, rng, literal_threads=False):
         if kind == "conv":
             _, _, xd, yd, zd, xs, ys, xf, yf, nf = crop
             w = weights[name + ".weight"][:nf].ravel(); b = weights[name + ".bias"][:nf]
-            th = LITERAL[name] if literal_threads else min(cores, nf)
+            # literal constants matter where th_count exceeds the layer's REAL output count: nf / th_count = 0 filters per thread and
+            # the last thread takes them all (convolutionalLayer.cpp:177-187); elsewhere 40-50 threads on these cores are just oversubscribed
+            serial = literal_threads and LITERAL[name] > layer[9]
+            th = LITERAL[name] if serial else min(cores, nf)
             _, first, dt = r.conv_timed(x, xd, yd, zd, xs, ys, xf, yf, nf, w, b, th=th, reps=1)
         elif kind == "fc":
             _, _, i, o = crop
-            th = LITERAL[name] if literal_threads else min(cores, o)
+            serial = literal_threads and LITERAL[name] > layer[3]
+            th = LITERAL[name] if serial else min(cores, o)
             _, first, dt = r.fc_timed(x, i, o, weights[name + ".weight"][:o].ravel(), weights[name + ".bias"][:o], th=th, reps=1)
         else:
             if kind in ("pool", "avgpool"):
@@ -237,7 +241,7 @@ def run_reference_sample(budget_s, rng, literal_threads=False):
                 r.bn(x, zd, xd, yd, weights[name + ".running_mean"][:zd], 1 / np.sqrt(var + 1e-5))
             elif kind == "square":
                 _, _, zd, xd, yd = crop
-                r.square_layer(x, zd, xd, yd, th=(LITERAL[name] if literal_threads else min(cores, zd)))
+                r.square_layer(x, zd, xd, yd, th=min(cores, zd))
             dt = time.perf_counter() - t0
         full_times[name] = dt * scale
         first_times[name] = (first if first is not None else dt) * scale
