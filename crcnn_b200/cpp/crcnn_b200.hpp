@@ -766,6 +766,30 @@ public:
     int layer_before_reenc = 6;
     std::function<ciphertext3D(ciphertext3D)> reencrypt;
     bool skip_reencryption = false;
+    // The same step WITHOUT leaving the device: decrypt -> decode -> float -> encode -> encrypt of every activation
+    // ciphertext on the GPU (crcnn_reencrypt), for a key holder who runs the evaluator himself -- the reference's own situation
+    // (its Network::forward holds the secret key in process globals).  Takes precedence over `reencrypt` when set.
+    std::function<DeviceTensor(DeviceTensor)> reencrypt_dev;
+    // Installs reencrypt_dev from the key holder's keys: secret_key_ntt = SecretKey::data() (NTT form, [K][n+1] words),
+    // public_key_ntt = PublicKey::data() ([2][K][n+1], NTT form); every call draws fresh randomness from (seed, call number).
+    void use_device_reencryption(const std::uint64_t *secret_key_ntt, const std::uint64_t *public_key_ntt, std::uint64_t seed) {
+        Runtime &rt = Runtime::get();
+        crcnn_keys *k = nullptr;
+        rt.check(crcnn_keys_upload(rt.ctx(), secret_key_ntt, public_key_ntt, &k));
+        std::shared_ptr<crcnn_keys> keys(k, [](crcnn_keys *p) { crcnn_keys_free(Runtime::get().ctx(), p); });
+        auto calls = std::make_shared<std::uint64_t>(0);
+        reencrypt_dev = [keys, seed, calls](DeviceTensor x) {
+            Runtime &r = Runtime::get();
+            crcnn_tensor *o = nullptr;
+            r.check(crcnn_reencrypt(r.ctx(), keys.get(), x.t, seed + 0x9E3779B97F4A7C15ull * (*calls)++, 0.0, nullptr, &o, nullptr, nullptr));
+            return DeviceTensor(o, x.zd, x.xd, x.yd, x.batch);
+        };
+    }
+#ifdef CRCNN_WITH_SEAL
+    void use_device_reencryption(const seal::SecretKey &sk, const seal::PublicKey &pk, std::uint64_t seed) {
+        use_device_reencryption(sk.data().data(), pk.data().data(), seed);
+    }
+#endif
 
     Network() {}
     virtual ~Network() {}
@@ -791,9 +815,11 @@ public:
     ciphertext3D forward(ciphertext3D input) {
         const int L = (int)layers.size();
         if (needs_reencryption() && !skip_reencryption) {
+            if (reencrypt_dev)
+                return download(forward_dev(reencrypt_dev(forward_dev(upload(input), 0, layer_before_reenc)), layer_before_reenc, L));
             if (!reencrypt)
                 throw std::logic_error("crcnn_b200::Network::forward: the reference re-encrypts before layer " + std::to_string(layer_before_reenc) +
-                                       " (CrCNN/src/network.cpp:30); install Network::reencrypt (the key holder's decrypt + encrypt) or set skip_reencryption = true");
+                                       " (CrCNN/src/network.cpp:30); install Network::reencrypt (the key holder's decrypt + encrypt), call use_device_reencryption, or set skip_reencryption = true");
             ciphertext3D mid = download(forward_dev(upload(input), 0, layer_before_reenc));
             return download(forward_dev(upload(reencrypt(mid)), layer_before_reenc, L));
         }
@@ -803,6 +829,8 @@ public:
     std::vector<ciphertext3D> forward_batch(const std::vector<ciphertext3D> &inputs) {
         const int L = (int)layers.size();
         if (needs_reencryption() && !skip_reencryption) {
+            if (reencrypt_dev)
+                return download_batch(forward_dev(reencrypt_dev(forward_dev(upload_batch(inputs), 0, layer_before_reenc)), layer_before_reenc, L));
             if (!reencrypt) throw std::logic_error("crcnn_b200::Network::forward_batch: re-encryption before layer " + std::to_string(layer_before_reenc) + " is not installed (see Network::forward)");
             std::vector<ciphertext3D> mid = download_batch(forward_dev(upload_batch(inputs), 0, layer_before_reenc));
             for (auto &m : mid) m = reencrypt(m);

@@ -16,6 +16,7 @@
 #include "tc_mac.cuh"
 #include "tcn_mac.cuh"
 #include "relin32.cuh"
+#include "reenc.cuh"
 
 using namespace crcnn;
 
@@ -23,12 +24,12 @@ namespace {
 
 enum KernelClass {
     KC_NTT_FWD = 0, KC_NTT_INV, KC_MAC, KC_PLAIN_EXPAND, KC_POOL, KC_BN, KC_PLAIN_OP,
-    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_TCN_SPLIT, KC_TCN_MAC, KC_RELIN32, KC_COUNT
+    KC_BEHZ_LIFT, KC_SQ_TENSOR, KC_BEHZ_FLOOR, KC_RELIN, KC_PROBE, KC_TC_SPLIT, KC_TC_MAC, KC_TCN_SPLIT, KC_TCN_MAC, KC_RELIN32, KC_REENC, KC_COUNT
 };
 const char *kClassNames[KC_COUNT] = {"ntt_forward", "ntt_inverse", "weighted_sum_mac", "plain_expand_ntt", "pool_sum",
                                      "batch_norm", "plain_op", "behz_lift", "square_tensor", "behz_floor_sk",
                                      "relinearize", "imad_probe", "tc_plane_split", "weighted_sum_tc_i8", "tcn_plane_split",
-                                     "weighted_sum_tcn_i8", "relinearize_u32"};
+                                     "weighted_sum_tcn_i8", "relinearize_u32", "reencrypt"};
 
 thread_local std::string g_create_error;
 
@@ -69,6 +70,12 @@ struct crcnn_evk {
     int dbc;
     bool has_r32 = false;  // keys also converted for the word-size auxiliary-prime path (relin32.cuh)
     Relin32 r32;
+};
+
+struct crcnn_keys {
+    uint64_t *sk = nullptr;   // [K][n]    secret key, NTT form
+    uint64_t *pk = nullptr;   // [2][K][n] public key, NTT form
+    ReencConsts c;
 };
 
 struct crcnn_ctx {
@@ -1580,6 +1587,141 @@ int crcnn_comm_all_gather(crcnn_ctx *ctx, crcnn_comm *c, crcnn_tensor *local, in
     if (c->world > 1) NCCLCHECK(nccl().GroupEnd());
     (void)before;
     *out = full;
+    return CRCNN_OK;
+}
+
+// ---------------------------------------------------------------------------------------- re-encryption
+int crcnn_keys_upload(crcnn_ctx *ctx, const uint64_t *secret_key_ntt, const uint64_t *public_key_ntt, crcnn_keys **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(secret_key_ntt && public_key_ntt && out, "null argument");
+    REQUIRE(ctx->hp.d.t >= 2 && REENC_GAMMA % ctx->hp.d.t != 0, "plain modulus not usable with the decryptor's gamma");
+    CU(cudaSetDevice(ctx->device));
+    auto *k = new crcnn_keys;
+    k->c = make_reenc_consts(ctx->hp.d);
+    const size_t pw = poly_words(ctx);
+    int rc = dev_alloc(ctx, pw * 8, (void **)&k->sk);
+    if (!rc) rc = dev_alloc(ctx, 2 * pw * 8, (void **)&k->pk);
+    if (!rc) rc = upload_rows(ctx, secret_key_ntt, (size_t)ctx->K, k->sk, ctx->stream);
+    if (!rc) rc = upload_rows(ctx, public_key_ntt, (size_t)2 * ctx->K, k->pk, ctx->stream);
+    if (!rc) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    if (rc) { dev_free(ctx, k->sk); dev_free(ctx, k->pk); delete k; return rc; }
+    *out = k;
+    return CRCNN_OK;
+}
+int crcnn_keys_free(crcnn_ctx *ctx, crcnn_keys *k) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    if (!k) return CRCNN_OK;
+    const size_t pw = poly_words(ctx);
+    if (k->sk) cudaMemsetAsync(k->sk, 0, pw * 8, ctx->stream);      // do not leave key material in freed device memory
+    dev_free(ctx, k->sk); dev_free(ctx, k->pk);
+    delete k;
+    return CRCNN_OK;
+}
+
+namespace {
+// plaintext polynomials [count][n] of ciphertexts [first, first+count) of t (Decryptor::decrypt); scratch = count*K*n words
+int decrypt_range(crcnn_ctx *ctx, crcnn_keys *k, crcnn_tensor *t, long first, long count, uint64_t *scratch, uint64_t *plain) {
+    const size_t n = ctx->n, pw = poly_words(ctx);
+    const uint64_t *ct = t->d + first * 2 * pw;
+    ProfScope ps(ctx, KC_REENC, lp_bytes(ctx, (double)count * 2 * ctx->K) + (double)count * n * 8, lp_bfly(ctx, (double)count * 2 * ctx->K));
+    if (!t->ntt) {
+        // copy the c1 polynomials and transform them (decryptor.cpp:153-158)
+        CU(cudaMemcpy2DAsync(scratch, pw * 8, ct + pw, 2 * pw * 8, pw * 8, count, cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(launch_ntt(ctx->dP, ctx->logn, scratch, count * ctx->K, 0, ctx->K, false, ctx->stream));
+    }
+    CU(launch_dec_dot(k->c, ct, t->ntt, k->sk, scratch, count, ctx->stream));
+    CU(launch_ntt(ctx->dP, ctx->logn, scratch, count * ctx->K, 0, ctx->K, true, ctx->stream));
+    CU(launch_dec_scale(k->c, t->ntt ? nullptr : ct, scratch, plain, count, ctx->stream));
+    return CRCNN_OK;
+}
+}  // namespace
+
+int crcnn_decrypt(crcnn_ctx *ctx, crcnn_keys *k, crcnn_tensor *t, uint64_t *host_plain) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(k && t && host_plain, "null argument");
+    REQUIRE(t->size == 2, "decrypt is implemented for size-2 ciphertexts");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n;
+    const long step = std::max<long>(1, std::min<long>(t->count, (long)((1ull << 30) / ((size_t)(ctx->K + 1) * n * 8))));
+    uint64_t *scratch = nullptr, *plain = nullptr;
+    int rc = dev_alloc(ctx, (size_t)step * ctx->K * n * 8, (void **)&scratch);
+    if (!rc) rc = dev_alloc(ctx, (size_t)step * n * 8, (void **)&plain);
+    for (long c0 = 0; c0 < t->count && !rc; c0 += step) {
+        const long cnt = std::min<long>(step, t->count - c0);
+        rc = decrypt_range(ctx, k, t, c0, cnt, scratch, plain);
+        if (!rc) {
+            cudaError_t e = cudaMemcpy2DAsync(host_plain + c0 * (n + 1), (n + 1) * 8, plain, n * 8, n * 8, cnt, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e));
+            for (long r = 0; r < cnt; r++) host_plain[(c0 + r) * (n + 1) + n] = 0;
+        }
+    }
+    dev_free(ctx, scratch); dev_free(ctx, plain);
+    return rc;
+}
+
+int crcnn_reencrypt(crcnn_ctx *ctx, crcnn_keys *k, crcnn_tensor *in, uint64_t seed, double noise_standard_deviation,
+                    const int8_t *host_noise, crcnn_tensor **out, uint64_t *host_reencoded, float *host_values) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(k && in && out, "null argument");
+    REQUIRE(in->size == 2, "re-encryption is implemented for size-2 ciphertexts");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n, pw = poly_words(ctx);
+    const int K = ctx->K;
+    const double sigma = noise_standard_deviation > 0 ? noise_standard_deviation : 3.19;   // SEAL/seal/util/globals.cpp: default_noise_standard_deviation
+    const double max_dev = 6.0 * sigma;                                                   // noise_distribution_width_multiplier = 6 (encryptionparams.h:204-211)
+    crcnn_tensor *o = nullptr;
+    int rc = new_tensor(ctx, in->count, 2, 0, &o);
+    if (rc) return rc;
+    // per ciphertext of a chunk: K*n words (dot product / u), n words (plaintext), 96 slots, 2n + 3n noise bytes
+    const size_t per_ct = (size_t)(K + 1) * n * 8 + REENC_SLOTS * 8 + 5 * n + 8;
+    const long step = std::max<long>(1, std::min<long>(in->count, (long)((1ull << 30) / per_ct)));
+    uint64_t *scratch = nullptr, *plain = nullptr, *slots = nullptr;
+    int8_t *e = nullptr, *given = nullptr;
+    float *vals = nullptr;
+    rc = dev_alloc(ctx, (size_t)step * K * n * 8, (void **)&scratch);
+    if (!rc) rc = dev_alloc(ctx, (size_t)step * n * 8, (void **)&plain);
+    if (!rc) rc = dev_alloc(ctx, (size_t)step * REENC_SLOTS * 8, (void **)&slots);
+    if (!rc) rc = dev_alloc(ctx, (size_t)step * 2 * n, (void **)&e);
+    if (!rc && host_noise) rc = dev_alloc(ctx, (size_t)step * 3 * n, (void **)&given);
+    if (!rc && host_values) rc = dev_alloc(ctx, (size_t)step * 4, (void **)&vals);
+    for (long c0 = 0; c0 < in->count && !rc; c0 += step) {
+        const long cnt = std::min<long>(step, in->count - c0);
+        rc = decrypt_range(ctx, k, in, c0, cnt, scratch, plain);
+        if (rc) break;
+        uint64_t *dst = o->d + c0 * 2 * pw;
+        cudaError_t er = cudaSuccess;
+        {
+            ProfScope ps(ctx, KC_REENC, lp_bytes(ctx, (double)cnt * 2 * K), lp_bfly(ctx, (double)cnt * 3 * K));
+            er = launch_reencode(k->c, plain, slots, vals, cnt, ctx->stream);
+            if (er == cudaSuccess && host_noise) er = cudaMemcpyAsync(given, host_noise + c0 * 3 * n, (size_t)cnt * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
+            if (er == cudaSuccess) er = launch_enc_sample(k->c, seed, c0, sigma, max_dev, given, scratch, e, cnt, ctx->stream);
+            if (er == cudaSuccess) er = launch_ntt(ctx->dP, ctx->logn, scratch, cnt * K, 0, K, false, ctx->stream);
+            if (er == cudaSuccess) er = launch_enc_mul(k->c, scratch, k->pk, dst, cnt, ctx->stream);
+            if (er == cudaSuccess) er = launch_ntt(ctx->dP, ctx->logn, dst, cnt * 2 * K, 0, K, true, ctx->stream);
+            if (er == cudaSuccess) er = launch_enc_finish(k->c, slots, e, dst, cnt, ctx->stream);
+        }
+        if (er == cudaSuccess && host_reencoded) {     // the re-encoded plaintexts, n+1 words each (parity checks)
+            std::vector<uint64_t> hs((size_t)cnt * REENC_SLOTS);
+            er = cudaMemcpyAsync(hs.data(), slots, hs.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+            if (er == cudaSuccess) er = cudaStreamSynchronize(ctx->stream);
+            for (long r = 0; r < cnt && er == cudaSuccess; r++) {
+                uint64_t *p = host_reencoded + (c0 + r) * (n + 1);
+                memset(p, 0, (n + 1) * 8);
+                memcpy(p, hs.data() + r * REENC_SLOTS, 64 * 8);
+                memcpy(p + n - 32, hs.data() + r * REENC_SLOTS + 64, 32 * 8);
+            }
+        }
+        if (er == cudaSuccess && host_values) {
+            er = cudaMemcpyAsync(host_values + c0, vals, (size_t)cnt * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (er == cudaSuccess) er = cudaStreamSynchronize(ctx->stream);
+        }
+        if (er != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, std::string("re-encryption: ") + cudaGetErrorString(er));
+    }
+    if (host_noise && !rc) { cudaError_t er = cudaStreamSynchronize(ctx->stream); if (er != cudaSuccess) rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(er)); }
+    dev_free(ctx, scratch); dev_free(ctx, plain); dev_free(ctx, slots); dev_free(ctx, e); dev_free(ctx, given); dev_free(ctx, vals);
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
+    *out = o;
     return CRCNN_OK;
 }
 

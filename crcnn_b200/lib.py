@@ -90,6 +90,10 @@ SYMBOLS = [
     ("crcnn_comm_create", _I, [_vp, _vp, _I, _I, _vpp]),
     ("crcnn_comm_destroy", _I, [_vp, _vp]),
     ("crcnn_comm_all_gather", _I, [_vp, _vp, _vp, _I, C.POINTER(C.c_long), _I, _vpp]),
+    ("crcnn_keys_upload", _I, [_vp, _vp, _vp, _vpp]),
+    ("crcnn_keys_free", _I, [_vp, _vp]),
+    ("crcnn_decrypt", _I, [_vp, _vp, _vp, _vp]),
+    ("crcnn_reencrypt", _I, [_vp, _vp, _vp, C.c_uint64, C.c_double, _vp, _vpp, _vp, _vp]),
     ("crcnn_probe_pipe", _I, [_vp, _I, _I, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 ]
 
@@ -303,6 +307,36 @@ class Engine:
         a = np.ascontiguousarray(words, dtype=np.uint64)
         s = np.ascontiguousarray(sizes, dtype=np.int32)
         return self._new(self.lib.crcnn_evk_upload, "evk", a.ctypes.data_as(_u64p), dbc, s.ctypes.data_as(_i32p))
+
+    # ---- re-encryption on the device (opt-in: the key holder's keys next to the activations)
+    def keys_upload(self, secret_key_ntt, public_key_ntt):
+        sk = np.ascontiguousarray(secret_key_ntt, dtype=np.uint64)
+        pk = np.ascontiguousarray(public_key_ntt, dtype=np.uint64)
+        assert sk.size == self.K * self.stride and pk.size == 2 * self.K * self.stride
+        return self._new(self.lib.crcnn_keys_upload, "keys", sk.ctypes.data, pk.ctypes.data)
+
+    def decrypt(self, keys, t):
+        """Decryptor::decrypt of every ciphertext of t -> [count][n+1] plaintext words."""
+        out = np.zeros((self.count(t), self.stride), dtype=np.uint64)
+        self._chk(self.lib.crcnn_decrypt(self.h, keys.ptr, t.ptr, out.ctypes.data))
+        return out
+
+    def reencrypt(self, keys, t, seed=0, sigma=0.0, noise=None, want_plain=False):
+        """decrypt -> decode -> float -> encode -> encrypt on the device; noise: optional int8 [count][3][n] (u, e0, e1).
+        Returns the fresh tensor (and, with want_plain, the re-encoded plaintexts [count][n+1] and the decoded float values)."""
+        cnt = self.count(t)
+        nz = None
+        if noise is not None:
+            nz = np.ascontiguousarray(noise, dtype=np.int8)
+            assert nz.size == cnt * 3 * self.n
+        plain = np.zeros((cnt, self.stride), dtype=np.uint64) if want_plain else None
+        vals = np.zeros(cnt, dtype=np.float32) if want_plain else None
+        out = C.c_void_p()
+        self._chk(self.lib.crcnn_reencrypt(self.h, keys.ptr, t.ptr, C.c_uint64(seed), C.c_double(sigma),
+                                           nz.ctypes.data if nz is not None else None, C.byref(out),
+                                           plain.ctypes.data if want_plain else None, vals.ctypes.data if want_plain else None))
+        h = Handle(self, out, "tensor")
+        return (h, plain, vals) if want_plain else h
 
     # ---- layers
     def conv(self, x, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, shard=None):

@@ -34,6 +34,7 @@ typedef struct crcnn_ctx crcnn_ctx;
 typedef struct crcnn_tensor crcnn_tensor; /* device tensor of ciphertexts */
 typedef struct crcnn_plain crcnn_plain;   /* device pack of plaintexts (weights, biases, scale factors) */
 typedef struct crcnn_evk crcnn_evk;       /* device copy of evaluation (relinearisation) keys */
+typedef struct crcnn_keys crcnn_keys;     /* device copy of the key holder's secret and public key (opt-in: GPU re-encryption) */
 typedef struct crcnn_comm crcnn_comm;     /* NCCL communicator of a group of contexts, one per GPU (output-neuron sharding) */
 
 typedef enum {
@@ -239,6 +240,27 @@ int crcnn_comm_destroy(crcnn_ctx *ctx, crcnn_comm *comm);
  * they are (all ranks of a sharded layer produce one domain: kernels are chosen from the layer's total output count). */
 int crcnn_comm_all_gather(crcnn_ctx *ctx, crcnn_comm *comm, crcnn_tensor *local, int batch, const long *counts,
                           int want_ntt_form, crcnn_tensor **out);
+
+/* ---- re-encryption on the device (opt-in) -----------------------------------------------------------
+ * Replaces: the noise reset inside Network::forward (CrCNN/src/network.cpp:30-33): decryptImage -> encryptImage
+ * (CrCNN/src/globals.cpp:127-142, 207-226), i.e. Decryptor::decrypt (SEAL/seal/decryptor.cpp:107-234), FractionalEncoder::decode,
+ * the float the reference stores in its floatCube, FractionalEncoder::encode and Encryptor::encrypt
+ * (SEAL/seal/encryptor.cpp:95-200) for every ciphertext of the tensor.  The reference runs it in-process with the SECRET key;
+ * so does this, on the GPU -- uploading keys is the caller's decision and nothing else in the library touches key material.
+ * secret_key_ntt: SecretKey::data() as SEAL keeps it, NTT form, uint64[K][n+1];  public_key_ntt: PublicKey::data(),
+ * uint64[2][K][n+1], NTT form. */
+int crcnn_keys_upload(crcnn_ctx *ctx, const uint64_t *secret_key_ntt, const uint64_t *public_key_ntt, crcnn_keys **out);
+int crcnn_keys_free(crcnn_ctx *ctx, crcnn_keys *keys);   /* the device copy of the secret key is zeroed first */
+/* Decryptor::decrypt of every (size-2) ciphertext of t: host_plain gets count plaintexts of n+1 words (values < t, pad word 0),
+ * bit-identical to SEAL's. */
+int crcnn_decrypt(crcnn_ctx *ctx, crcnn_keys *keys, crcnn_tensor *t, uint64_t *host_plain);
+/* decrypt -> decode -> (float) -> encode -> encrypt of every ciphertext of `in`, activations never leaving the device.  The three
+ * sampled polynomials of an encryption (u uniform in {-1,0,1}; e0, e1 clipped normal, standard deviation
+ * noise_standard_deviation (<= 0: SEAL's default 3.19), redrawn beyond 6 sigma, truncated toward zero) come from a counter-based
+ * generator keyed by `seed` -- or, for byte-exact checks, from host_noise: int8[count][3][n] = u, e0, e1.  Optional outputs:
+ * host_reencoded (count x (n+1) words: the plaintexts that were encrypted), host_values (count floats: the decoded values). */
+int crcnn_reencrypt(crcnn_ctx *ctx, crcnn_keys *keys, crcnn_tensor *in, uint64_t seed, double noise_standard_deviation,
+                    const int8_t *host_noise, crcnn_tensor **out, uint64_t *host_reencoded, float *host_values);
 
 /* ---- measurement ------------------------------------------------------------------------------
  * Kernel classes are timed with CUDA events on the context's stream while profiling is on. */

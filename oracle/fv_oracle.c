@@ -700,3 +700,115 @@ void orc_square_forward(const orc_ctx *c, const uint64_t *in, int count, const u
     }
     free(tmp);
 }
+
+/* ================================================================ client-side steps of the re-encryption
+ * Network::forward decrypts and re-encrypts the whole tensor before layer 6 (C/network.cpp:30-33: decryptImage -> encryptImage,
+ * C/globals.cpp:127-142, 207-226).  These restate Decryptor::decrypt, FractionalEncoder::decode and Encryptor::encrypt for that step. */
+#define GAMMA 0x1fffffffffc80001ULL   /* SU/globals.cpp:330 (internal_mods::gamma) */
+
+/* Decryptor::decrypt for size-2 ciphertexts, S/decryptor.cpp:107-234.  sk_ntt: the secret key in NTT form [K][n+1] as the
+ * Decryptor keeps it (secret_key_array_, power 1); plain_out: n+1 words per ciphertext (values < t, pad word 0). */
+void orc_decrypt(const orc_ctx *c, const uint64_t *cts, int count, const uint64_t *sk_ntt, uint64_t *plain_out) {
+    const int n = c->n, K = c->K;
+    const size_t st = STRIDE(c), ctw = (size_t)2 * K * st;
+    smod tm = smod_make(c->t), gm = smod_make(GAMMA);
+    uint64_t primes[MAXK];
+    for (int i = 0; i < K; i++) primes[i] = c->qt[i].m.q;
+    /* BaseConverter constants, SU/baseconverter.cpp:315-349 */
+    uint64_t qhat_t[MAXK], qhat_g[MAXK], tg_mod_q[MAXK];
+    for (int i = 0; i < K; i++) {
+        qhat_t[i] = prod_mod_except(primes, K, i, &tm);
+        qhat_g[i] = prod_mod_except(primes, K, i, &gm);
+        tg_mod_q[i] = mulmod(c->t % c->qt[i].m.q, GAMMA % c->qt[i].m.q, &c->qt[i].m);   /* plain_gamma_product_mod_coeff_array_ :345-349 */
+    }
+    const uint64_t neg_inv_q_t = invmod(negmod(prod_mod_except(primes, K, -1, &tm), &tm), c->t);   /* :325-335 */
+    const uint64_t neg_inv_q_g = invmod(negmod(prod_mod_except(primes, K, -1, &gm), &gm), GAMMA);
+    const uint64_t inv_gamma_t = invmod(GAMMA % c->t, c->t);                                      /* :337-343 */
+    uint64_t *y = malloc((size_t)K * st * 8), *tmp = malloc(st * 8);
+    for (int ct = 0; ct < count; ct++) {
+        const uint64_t *c0 = cts + (size_t)ct * ctw, *c1 = c0 + (size_t)K * st;
+        for (int i = 0; i < K; i++) {
+            const smod *m = &c->qt[i].m;
+            memcpy(tmp, c1 + (size_t)i * st, st * 8);
+            ntt_lazy(tmp, &c->qt[i]);                                       /* :158 */
+            for (int k = 0; k < n; k++) tmp[k] = mulmod(tmp[k], sk_ntt[(size_t)i * st + k], m);   /* dyadic_product_coeffmod :160 */
+            intt_full(tmp, &c->qt[i]);                                      /* :169 */
+            for (int k = 0; k < n; k++)                                     /* lazy "+ c0" then x |gamma t|_qi, :179-187 */
+                y[(size_t)i * st + k] = mulmod(tmp[k] + c0[(size_t)i * st + k], tg_mod_q[i], m);
+        }
+        uint64_t *out = plain_out + (size_t)ct * st;
+        for (int k = 0; k < n; k++) {
+            u128 st_ = 0, sg = 0;
+            for (int i = 0; i < K; i++) {                                   /* fastbconv_plain_gamma, SU/baseconverter.cpp:744-795 */
+                uint64_t v = mulmod(y[(size_t)i * st + k], c->inv_qhat[i], &c->qt[i].m);
+                st_ += (u128)v * qhat_t[i];
+                sg += (u128)v * qhat_g[i];
+            }
+            uint64_t at = mulmod(barrett_u128(st_, &tm), neg_inv_q_t, &tm);   /* S/decryptor.cpp:196-201 */
+            uint64_t ag = mulmod(barrett_u128(sg, &gm), neg_inv_q_g, &gm);
+            uint64_t w;
+            if (ag > (GAMMA >> 1)) w = addmod(at, (GAMMA - ag) % c->t, &tm);  /* :207-224 */
+            else w = submod(at, ag % c->t, &tm);
+            out[k] = mulmod(w, inv_gamma_t, &tm);                             /* :233-234 */
+        }
+        out[n] = 0;
+    }
+    free(y); free(tmp);
+}
+
+/* BalancedFractionalEncoder::decode with (64, 32, base 3), S/encoder.cpp (BalancedFractionalEncoder::decode,
+ * BalancedEncoder::decode_int64): plain has n+1 words. */
+double orc_decode_fractional(const orc_ctx *c, const uint64_t *plain) {
+    const uint64_t t = c->t, neg = (t + 1) >> 1;   /* coeff_neg_threshold_ = (plain_modulus + 1) >> 1, S/encoder.cpp (BalancedEncoder ctor) */
+    int64_t ip = 0;
+    int top = 63;
+    while (top >= 0 && plain[top] == 0) top--;
+    for (int i = top; i >= 0; i--) {
+        int64_t v = plain[i] >= neg ? -(int64_t)(t - plain[i]) : (int64_t)plain[i];
+        ip = (int64_t)((uint64_t)ip * 3u) + v;
+    }
+    double frac = 0;
+    const uint64_t *f = plain + c->n - 32;        /* plain_copy + coeff_count - 1 - fraction_coeff_count_, coeff_count = n+1 */
+    for (int i = 0; i < 32; i++) {
+        int64_t v = f[i] >= neg ? -(int64_t)(t - f[i]) : (int64_t)f[i];
+        frac += (double)v;
+        frac /= 3.0;
+    }
+    return (double)ip - frac;
+}
+
+/* Encryptor::encrypt, S/encryptor.cpp:95-166, with the three sampled polynomials given explicitly (u in {-1,0,1}; e0, e1 the
+ * rounded clipped-normal noise, as signed small integers, n entries each): c0 = pk0*u + e0 + Delta*m (preencrypt :168-200),
+ * c1 = pk1*u + e1.  pk: the public key as SEAL stores it, [2][K][n+1] in NTT form. */
+void orc_encrypt(const orc_ctx *c, const uint64_t *plain, int coeff_count, const uint64_t *pk, const int8_t *u, const int8_t *e0,
+                 const int8_t *e1, uint64_t *out) {
+    const int n = c->n, K = c->K;
+    const size_t st = STRIDE(c);
+    uint64_t *un = malloc(st * 8), *tmp = malloc(st * 8);
+    memset(out, 0, (size_t)2 * K * st * 8);
+    for (int i = 0; i < K; i++) {
+        const smod *m = &c->qt[i].m;
+        for (int k = 0; k < n; k++) un[k] = u[k] > 0 ? 1 : (u[k] < 0 ? m->q - 1 : 0);
+        un[n] = 0;
+        ntt_full(un, &c->qt[i]);    /* ntt_double_multiply_poly_nttpoly, SU/polyarithsmallmod.h: NTT(u) once, two dyadic products, two inverse NTTs */
+        for (int p = 0; p < 2; p++) {
+            const int8_t *e = p ? e1 : e0;
+            for (int k = 0; k < n; k++) tmp[k] = mulmod(un[k], pk[((size_t)p * K + i) * st + k], m);
+            tmp[n] = 0;
+            intt_full(tmp, &c->qt[i]);
+            uint64_t *dst = out + ((size_t)p * K + i) * st;
+            for (int k = 0; k < n; k++) {
+                uint64_t v = tmp[k];
+                if (p == 0 && k < coeff_count) {                         /* preencrypt */
+                    uint64_t pm = plain[k];
+                    u128 z = (u128)c->delta[i] * pm;
+                    if (pm >= c->half) z += c->rho[i];
+                    v = addmod(v, barrett_u128(z, m), m);
+                }
+                uint64_t en = e[k] > 0 ? (uint64_t)e[k] : (e[k] < 0 ? m->q - (uint64_t)(-(int)e[k]) : 0);
+                dst[k] = addmod(en, v, m);
+            }
+        }
+    }
+    free(un); free(tmp);
+}

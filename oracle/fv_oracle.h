@@ -73,6 +73,14 @@ void orc_bn_forward(const orc_ctx *c, const uint64_t *in, int zd, int xd, int yd
 void orc_square_forward(const orc_ctx *c, const uint64_t *in, int count, const uint64_t *evk, const int *sizes,
                         int dbc, uint64_t *out);
 
+/* Client-side steps of the reference's re-encryption inside Network::forward (CrCNN/src/network.cpp:30-33), SURVEY 8(f) N4:
+ * Decryptor::decrypt (SEAL/seal/decryptor.cpp:107-234), FractionalEncoder::decode, Encryptor::encrypt (encryptor.cpp:95-166)
+ * with the sampled polynomials u, e0, e1 supplied by the caller (signed small integers, n entries each). */
+void orc_decrypt(const orc_ctx *c, const uint64_t *cts, int count, const uint64_t *sk_ntt, uint64_t *plain_out);
+double orc_decode_fractional(const orc_ctx *c, const uint64_t *plain);
+void orc_encrypt(const orc_ctx *c, const uint64_t *plain, int coeff_count, const uint64_t *pk, const int8_t *u, const int8_t *e0,
+                 const int8_t *e1, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

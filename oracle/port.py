@@ -69,6 +69,11 @@ def load():
     L.orc_pool_forward.argtypes = [C.c_void_p, _u64p] + [C.c_int] * 7 + [_u64p, C.c_int, _u64p]
     L.orc_bn_forward.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, C.c_int, _u64p, _u64p, _u64p]
     L.orc_square_forward.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p, _i32p, C.c_int, _u64p]
+    L.orc_decrypt.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p, _u64p]
+    L.orc_decode_fractional.restype = C.c_double
+    L.orc_decode_fractional.argtypes = [C.c_void_p, _u64p]
+    _i8p = C.POINTER(C.c_int8)
+    L.orc_encrypt.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p, _i8p, _i8p, _i8p, _u64p]
     return L
 
 
@@ -163,6 +168,30 @@ class Oracle:
         count = a.size // self.ct_words(3)
         out = np.zeros((count, 2, self.K, self.stride), dtype=np.uint64)
         self.lib.orc_relinearize(self.h, _p(a), count, _p(e), _p(s, _i32p), dbc, _p(out))
+        return out
+
+    # ---- client-side steps of the re-encryption ----
+    def decrypt(self, cts, sk_ntt):
+        a = np.ascontiguousarray(cts, dtype=np.uint64)
+        sk = np.ascontiguousarray(sk_ntt, dtype=np.uint64)
+        count = a.size // self.ct_words(2)
+        out = np.zeros((count, self.stride), dtype=np.uint64)
+        self.lib.orc_decrypt(self.h, _p(a), count, _p(sk), _p(out))
+        return out
+
+    def decode(self, plain):
+        p = np.zeros(self.stride, dtype=np.uint64)
+        p[:len(plain)] = plain
+        return float(self.lib.orc_decode_fractional(self.h, _p(p)))
+
+    def encrypt(self, plain, pk, u, e0, e1, coeff_count=None):
+        p = np.ascontiguousarray(plain, dtype=np.uint64)
+        k = np.ascontiguousarray(pk, dtype=np.uint64)
+        i8 = C.POINTER(C.c_int8)
+        uu, a0, a1 = (np.ascontiguousarray(v, dtype=np.int8) for v in (u, e0, e1))
+        out = np.zeros((2, self.K, self.stride), dtype=np.uint64)
+        self.lib.orc_encrypt(self.h, _p(p), len(p) if coeff_count is None else coeff_count, _p(k), uu.ctypes.data_as(i8),
+                             a0.ctypes.data_as(i8), a1.ctypes.data_as(i8), _p(out))
         return out
 
     # ---- layers (plaintext parameters as [...][n+1] coefficient-form words) ----

@@ -106,6 +106,21 @@ class Ref:
                                               _p(plain, _u64p) if want_plain else None))
         return (vals, budgets, plain) if want_plain else (vals, budgets)
 
+    def keys(self):
+        """(secret key in NTT form [K][n+1], public key [2][K][n+1] in NTT form) of the reference's key generator."""
+        sk = np.zeros((self.K, self.stride), dtype=np.uint64)
+        pk = np.zeros((2, self.K, self.stride), dtype=np.uint64)
+        self._chk(self.lib.ref_keys(_p(sk, _u64p), _p(pk, _u64p)))
+        return sk, pk
+
+    def reencode(self, ct):
+        """decrypt -> decode to float -> encode: the plaintext Network::forward re-encrypts (network.cpp:30-33). -> (plain n+1 words, value)"""
+        c = np.ascontiguousarray(ct, dtype=np.uint64)
+        out = np.zeros(self.stride, dtype=np.uint64)
+        v = C.c_double()
+        self._chk(self.lib.ref_reencode(_p(c, _u64p), _p(out, _u64p), C.byref(v)))
+        return out, v.value
+
     # ---- evaluator-level ----
     def ct_transform(self, cts, size=2, inverse=False):
         a = np.array(cts, dtype=np.uint64, copy=True, order="C")

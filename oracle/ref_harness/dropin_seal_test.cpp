@@ -7,6 +7,7 @@
 //
 // Built by oracle/Makefile.ref into oracle/_ref/dropin_seal_test (needs /root/reference at build
 // time; the binary travels to the GPU box).  Run:  dropin_seal_test [n] [t]
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <random>
@@ -141,6 +142,24 @@ int main(int argc, char **argv) {
         int nb_d = decryptor->invariant_noise_budget(d[0][0][0]);
         std::cout << "re-encryption callback calls " << calls << ", budget after re-encrypted tail " << nb_d << " bits\n";
         net.reencrypt = nullptr;
+        // the same noise reset ON THE DEVICE: keys uploaded by the key holder, decrypt -> decode -> float -> encode ->
+        // encrypt on the GPU.  Ciphertexts are randomised, plaintexts are not: the decrypted scores must equal, coefficient by
+        // coefficient, those of the REFERENCE's own Network::forward (which re-encrypts before layer 6 with SEAL on the host).
+        net.use_device_reencryption(keygen->secret_key(), keygen->public_key(), 2024);
+        ciphertext3D g = net.forward(x);
+        ciphertext3D h = ref.forward(x);            // CrCNN/src/network.cpp:22-47, unmodified
+        bool plain_equal = true;
+        for (int i = 0; i < 10; i++) {
+            Plaintext pg, ph;
+            decryptor->decrypt(g[0][i][0], pg);
+            decryptor->decrypt(h[0][i][0], ph);
+            plain_equal = plain_equal && pg == ph;
+        }
+        int nb_g = decryptor->invariant_noise_budget(g[0][0][0]), nb_h = decryptor->invariant_noise_budget(h[0][0][0]);
+        std::cout << "device re-encryption: decrypted plaintexts equal to the reference's Network::forward: " << plain_equal
+                  << ", noise budget " << nb_g << " vs " << nb_h << " bits\n";
+        ok = ok && plain_equal && nb_g > 0 && std::abs(nb_g - nb_h) <= 1;
+        net.reencrypt_dev = nullptr;
         net.skip_reencryption = true;
 
         floatCube sa = decryptImage(a), sc = decryptImage(c);  // SEAL decryption, client side

@@ -466,4 +466,30 @@ int ref_fc_forward_timed(const uint64_t *in, int in_dim, int out_dim, int th_cou
     });
 }
 
+// The key holder's material for the re-encryption step: the secret key as the Decryptor keeps it (NTT form,
+// [K][n+1] words, SEAL/seal/decryptor.cpp:60-70) and the public key ([2][K][n+1], NTT form, SEAL/seal/encryptor.cpp:60-75).
+int ref_keys(uint64_t *sk_out, uint64_t *pk_out) {
+    return guarded([&] {
+        const size_t w = size_t(g_K) * (g_n + 1);
+        if (sk_out) memcpy(sk_out, keygen->secret_key().data().data(), w * 8);
+        if (pk_out) memcpy(pk_out, keygen->public_key().data().data(), 2 * w * 8);
+    });
+}
+
+// What Network::forward does to ONE ciphertext before layer 6 (CrCNN/src/network.cpp:30-33 through decryptImage / encryptImage,
+// CrCNN/src/globals.cpp:127-142, 207-226): decrypt, decode to a float (floatCube), encode again -- the plaintext the fresh
+// ciphertext is made of.  plain_out: n+1 words.
+int ref_reencode(const uint64_t *ct, uint64_t *plain_out, double *value) {
+    return guarded([&] {
+        Ciphertext c = make_ct(ct, 2);
+        Plaintext p;
+        decryptor->decrypt(c, p);
+        float f = (float)fraencoder->decode(p);
+        Plaintext q = fraencoder->encode(f);
+        memset(plain_out, 0, size_t(g_n + 1) * 8);
+        memcpy(plain_out, q.data(), size_t(q.coeff_count()) * 8);
+        if (value) *value = f;
+    });
+}
+
 } // extern "C"

@@ -82,3 +82,4 @@ def test_seal_mode_dropin_against_reference_classes(n, t):
     assert res.returncode == 0 and "DROPIN OK" in res.stdout, res.stdout[-2000:] + res.stderr[-500:]
     assert res.stdout.count("bit-identical") == 9   # 7 layers + Network::forward skipped / with the re-encryption callback
     assert "forward without re-encryption policy refused: 1" in res.stdout and "re-encryption callback calls 1" in res.stdout
+    assert "device re-encryption: decrypted plaintexts equal to the reference's Network::forward: 1" in res.stdout, res.stdout[-1500:]

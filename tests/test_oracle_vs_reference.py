@@ -90,3 +90,33 @@ def test_layers(pair):
                           o.bn(xi, 2, 3, 3, o.encode_many([0.3, -0.2]), o.encode_many([1.7, 0.9])))
     ev, sizes, dbc = r.evk()
     assert np.array_equal(r.square_layer(xi[:4], 1, 2, 2).ravel(), o.square_layer(xi[:4], ev, sizes, dbc).ravel())
+
+
+@pytest.mark.parametrize("n,t", [(2048, 1 << 16), (4096, 1 << 20), (8192, 1 << 30)])
+def test_reencryption_steps_against_seal(n, t):
+    """SURVEY 8(f) N4: the oracle's Decryptor::decrypt, FractionalEncoder::decode and Encryptor::encrypt restatements against
+    SEAL's own objects -- decrypt bit for bit (fresh and used ciphertexts), decode -> float -> encode bit for bit, and an
+    encryption with explicit sampled polynomials that SEAL's Decryptor opens to the same plaintext with a fresh noise budget."""
+    r = ref.Ref(n, t, seed=5)
+    o = port.Oracle(n, r.primes, t)
+    sk, pk = r.keys()
+    rng = np.random.default_rng(n)
+    vals = rng.uniform(-3, 3, 6).astype(np.float32)
+    cts = r.encrypt(vals)
+    _, fresh_budget, plain = r.decrypt(cts, want_plain=True)
+    assert np.array_equal(o.decrypt(cts, sk), plain)
+    w = rng.uniform(-1, 1, 12).astype(np.float32); b = rng.uniform(-1, 1, 2).astype(np.float32)
+    y = r.fc(cts, 6, 2, w, b, th=2).reshape(2, 2, r.K, r.stride)
+    dec_vals, _, plain2 = r.decrypt(y, want_plain=True)
+    assert np.array_equal(o.decrypt(y, sk), plain2)
+    for i in range(2):
+        assert o.decode(plain2[i]) == dec_vals[i]
+        want_plain, want_val = r.reencode(y[i])
+        enc, _ = o.encode(float(np.float32(o.decode(plain2[i]))))
+        assert np.array_equal(enc, want_plain) and np.float32(o.decode(plain2[i])) == np.float32(want_val)
+        u = rng.integers(-1, 2, n).astype(np.int8)
+        e0 = np.clip(np.trunc(rng.normal(0, 3.19, n)), -19, 19).astype(np.int8)
+        e1 = np.clip(np.trunc(rng.normal(0, 3.19, n)), -19, 19).astype(np.int8)
+        ct = o.encrypt(want_plain, pk, u, e0, e1)
+        _, budget, back = r.decrypt(ct[None], want_plain=True)
+        assert np.array_equal(back[0], want_plain) and abs(int(budget[0]) - int(fresh_budget[0])) <= 1
