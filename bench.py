@@ -29,13 +29,21 @@ import numpy as np
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 # ... and so does anything a native library writes to file descriptor 1 directly: fd 1 points at stderr for the whole run, the JSON line
 # goes to a duplicate of the original stdout (emit()).
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """main() only (tools import this module for its constants and helpers and keep their stdout)."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
 
 
 def emit(line):
     sys.stdout.flush()
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -647,6 +655,7 @@ def port_baseline(budget_s):
 def main():
     global MODEL, N_POLY, PRIMES, T_PLAIN
     args = parse()
+    _claim_stdout()
     if args.model:
         MODEL = args.model
     if args.mode == "crt" and not args.model:

@@ -1277,19 +1277,20 @@ int crcnn_plain_op(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_plain *p, long index, 
     REQUIRE(t && p && index >= 0 && index < p->count && op >= 0 && op <= 2, "bad plain_op arguments");
     CU(cudaSetDevice(ctx->device));
     int rc;
-    const uint64_t *pl;
+    const uint64_t *pl, *pl_sh = nullptr;
     if (op == 0) {
         rc = ensure_domain(ctx, t, 1);
-        if (!rc) rc = ensure_form(ctx, p, PF_NTT_MUL);
+        if (!rc) rc = ensure_shoup(ctx, p);
         if (rc) return rc;
         pl = p->ntt_mul + index * poly_words(ctx);
+        pl_sh = p->ntt_mul_sh + index * poly_words(ctx);
     } else {
         rc = ensure_form(ctx, p, t->ntt ? PF_NTT_ADD : PF_COEF_ADD);
         if (rc) return rc;
         pl = (t->ntt ? p->ntt_add : p->coef_add) + index * poly_words(ctx);
     }
     ProfScope ps(ctx, KC_PLAIN_OP, lp_bytes(ctx, (double)t->count * (op == 0 ? t->size : 1) * 2 * ctx->K), (double)t->count * (op == 0 ? t->size : 1) * ctx->K * ctx->n);
-    CU(launch_plain_op(ctx->dP, ctx->n, ctx->K, t->d, t->count, t->size, pl, op, ctx->stream));
+    CU(launch_plain_op(ctx->dP, ctx->n, ctx->K, t->d, t->count, t->size, pl, pl_sh, op, ctx->stream));
     return CRCNN_OK;
 }
 
@@ -1299,23 +1300,41 @@ int crcnn_add_many(crcnn_ctx *ctx, crcnn_tensor *t, crcnn_tensor **out) {
     REQUIRE(t->count >= 1, "encrypteds cannot be empty");  // evaluator.cpp:298-301
     REQUIRE(t->size == 2, "add_many is implemented for size-2 ciphertexts");
     CU(cudaSetDevice(ctx->device));
-    std::vector<int> key = {4, (int)t->count};
-    const int *d_index = nullptr;
-    if (ctx->index_cache.find(key) == ctx->index_cache.end()) {
-        std::vector<int> table(t->count);
-        for (long i = 0; i < t->count; i++) table[i] = (int)i;
-        int rc = get_index_table(ctx, key, table, &d_index);
-        if (rc) return rc;
-    } else {
-        d_index = ctx->index_cache[key];
-    }
+    // sum of ciphertexts [first, first + count) of `src` in groups of `g` -> `nout` ciphertexts at dst (identity index table, cached)
+    auto pass = [&](const uint64_t *src, long first, int nout, int g, uint64_t *dst) -> int {
+        std::vector<int> key = {4, (int)first, nout, g};
+        const int *d_index = nullptr;
+        auto it = ctx->index_cache.find(key);
+        if (it == ctx->index_cache.end()) {
+            std::vector<int> table((size_t)nout * g);
+            for (size_t i = 0; i < table.size(); i++) table[i] = (int)(first + (long)i);
+            int rc = get_index_table(ctx, key, table, &d_index);
+            if (rc) return rc;
+        } else d_index = it->second;
+        ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)nout * g + nout) * 2 * ctx->K), (double)nout * g * 2 * ctx->K * ctx->n);
+        CU(launch_pool(ctx->dP, ctx->n, ctx->K, src, d_index, nout, g, nullptr, nullptr, sum_fits_64(ctx, g), dst, ctx->stream));
+        return CRCNN_OK;
+    };
     crcnn_tensor *o = nullptr;
     int rc = new_tensor(ctx, 1, 2, t->ntt, &o);
     if (rc) return rc;
-    ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)t->count + 1) * 2 * ctx->K), (double)t->count * 2 * ctx->K * ctx->n);
-    cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, t->d, d_index, 1, (int)t->count, nullptr, nullptr,
-                                sum_fits_64(ctx, t->count), o->d, ctx->stream);
-    if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    if (t->count <= 128) {
+        rc = pass(t->d, 0, 1, (int)t->count, o->d);
+    } else {
+        // ONE output ciphertext keeps 2K CTAs busy: reduce in two levels -- groups of ~sqrt(count) summed in parallel (every input read
+        // once, in full coalesced rows), then the canonical partial sums.  Modular addition is associative: same residues as the
+        // reference's serial add_many (evaluator.cpp:296-308).
+        int g = 1;
+        while ((long)g * g < t->count) g++;
+        const long full = t->count / g, tail = t->count % g, groups = full + (tail ? 1 : 0);
+        crcnn_tensor *part = nullptr;
+        rc = new_tensor(ctx, groups, 2, t->ntt, &part);
+        if (!rc) rc = pass(t->d, 0, (int)full, g, part->d);
+        if (!rc && tail) rc = pass(t->d, full * g, 1, (int)tail, part->d + full * 2 * poly_words(ctx));
+        if (!rc) rc = pass(part->d, 0, 1, (int)groups, o->d);
+        crcnn_tensor_free(ctx, part);
+    }
+    if (rc) { crcnn_tensor_free(ctx, o); return rc; }
     *out = o;
     return CRCNN_OK;
 }

@@ -603,20 +603,38 @@ cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, 
     return cudaGetLastError();
 }
 
+// Four consecutive residues per thread (two 128-bit loads and stores); additive ops touch polynomial 0 only, and only those words
+// are launched.  HBM-bound: 2 x 8 bytes per residue of the ciphertext, the plaintext operand (K*n words, shared by every
+// ciphertext of the launch) comes from L2.
 __global__ void __launch_bounds__(256)
-plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data, int size, const uint64_t *__restrict__ pl, int op) {
+plain_op_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data, int size, const uint64_t *__restrict__ pl,
+                const uint64_t *__restrict__ pl_sh, int op) {
     const int n = P->n, K = P->K;
-    const long pw = (long)K * n, ctw = size * pw;
+    const long pw = (long)K * n, ctw = size * pw, active = op == 0 ? ctw : pw;
     const long ct = blockIdx.x;
-    const long word = (long)blockIdx.y * 256 + threadIdx.x;
-    if (word >= ctw) return;
-    const int poly = (int)(word / pw);
-    const long lw = word - poly * pw;
+    const long word = ((long)blockIdx.y * 256 + threadIdx.x) * 4;
+    if (word >= active) return;
+    const long lw = word % pw;
     const int j = (int)(lw / n);
     const Mod mod = P->tab[j].mod;
-    uint64_t *x = data + ct * ctw + word;
-    if (op == 0) *x = mulmod(*x, __ldg(pl + lw), mod);
-    else if (poly == 0) *x = (op == 1) ? addmod(*x, __ldg(pl + lw), mod.q) : submod(*x, __ldg(pl + lw), mod.q);
+    ulonglong2 *x = reinterpret_cast<ulonglong2 *>(data + ct * ctw + word);
+    const ulonglong2 *w = reinterpret_cast<const ulonglong2 *>(pl + lw);
+    ulonglong2 a = x[0], b = x[1];
+    const ulonglong2 wa = __ldg(w), wb = __ldg(w + 1);
+    if (op == 0) {
+        // the plaintext is a constant of the launch: Shoup companions (floor(w 2^64 / q)) make each product 1 mulhi + 2 mullo and one
+        // conditional subtraction instead of a 128-bit Barrett step -- the same canonical residue
+        const ulonglong2 *ws = reinterpret_cast<const ulonglong2 *>(pl_sh + lw);
+        const ulonglong2 sa = __ldg(ws), sb = __ldg(ws + 1);
+        uint64_t r;
+        r = mulshoup_lazy(a.x, wa.x, sa.x, mod.q); a.x = r >= mod.q ? r - mod.q : r;
+        r = mulshoup_lazy(a.y, wa.y, sa.y, mod.q); a.y = r >= mod.q ? r - mod.q : r;
+        r = mulshoup_lazy(b.x, wb.x, sb.x, mod.q); b.x = r >= mod.q ? r - mod.q : r;
+        r = mulshoup_lazy(b.y, wb.y, sb.y, mod.q); b.y = r >= mod.q ? r - mod.q : r;
+    }
+    else if (op == 1) { a.x = addmod(a.x, wa.x, mod.q); a.y = addmod(a.y, wa.y, mod.q); b.x = addmod(b.x, wb.x, mod.q); b.y = addmod(b.y, wb.y, mod.q); }
+    else { a.x = submod(a.x, wa.x, mod.q); a.y = submod(a.y, wa.y, mod.q); b.x = submod(b.x, wb.x, mod.q); b.y = submod(b.y, wb.y, mod.q); }
+    x[0] = a; x[1] = b;
 }
 
 // Reductions of the BEHZ kernels.  FOLD: the three-fold reduction through the 2^k - delta shape every SEAL modulus on this path has
@@ -901,10 +919,11 @@ cudaError_t launch_bn(const DeviceParams *P, int n, int K, const uint64_t *in, l
 }
 
 cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data, long count, int size,
-                               const uint64_t *pl, int op, cudaStream_t stream) {
+                               const uint64_t *pl, const uint64_t *pl_sh, int op, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
-    dim3 grid((unsigned)count, (unsigned)(((long)size * K * n + 255) / 256));
-    plain_op_kernel<<<grid, 256, 0, stream>>>(P, data, size, pl, op);
+    const long active = (long)(op == 0 ? size : 1) * K * n;     // additive ops: polynomial 0 only
+    dim3 grid((unsigned)count, (unsigned)((active / 4 + 255) / 256));
+    plain_op_kernel<<<grid, 256, 0, stream>>>(P, data, size, pl, pl_sh, op);
     return cudaGetLastError();
 }
 

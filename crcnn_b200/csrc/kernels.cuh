@@ -73,7 +73,7 @@ cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, 
 // ---- generic plaintext ops on `count` ciphertexts of `size` polys (evaluator-level API)
 // op 0: every poly *= pl (pl in NTT lifted form, data in NTT form); op 1/2: poly0 +=/-= pl (scaled form,
 // same domain as data)
-cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data, long count, int size, const uint64_t *pl, int op,
+cudaError_t launch_plain_op(const DeviceParams *P, int n, int K, uint64_t *data, long count, int size, const uint64_t *pl, const uint64_t *pl_sh, int op,
                             cudaStream_t stream);
 
 // ---- FV square (BEHZ), staged exactly as evaluator.cpp:742-883

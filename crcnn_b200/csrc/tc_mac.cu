@@ -21,19 +21,16 @@ using namespace tcptx;
 
 // ------------------------------------------------------------------------------------ the GEMM kernel
 // SUB = K blocks of 128 bytes per ring stage (one barrier flip and one tcgen05.commit per stage): 1 -> 4 stages of 44 KB, 2 -> 2 stages of 88 KB
-// DUO: two CTAs per SM, each with half the shared memory (two 44 KB stages, diagonal sum by warp shuffles instead of the 32 KB
-// scratch) and half the tensor memory (ONE accumulator of 256 columns): the two CTAs' pipelines are independent, so one CTA's MMAs
-// run while the other waits for its loads or drains its accumulator.
-template <int PLANES, int SUB = 1, bool DUO = false>
-__global__ void __launch_bounds__(TC_THREADS, DUO ? 2 : 1)
+template <int PLANES, int SUB = 1>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
               const DeviceParams *__restrict__ P, TcMacArgs a) {
     constexpr int N = PLANES * TC_CB;               // UMMA N: 224 or 256
     constexpr int B_BLK = N * TC_BK;                // 28 / 32 KB
-    constexpr int TC_STAGES = DUO ? 2 : 4 / SUB;
-    constexpr int NACC = DUO ? 1 : 2;                       // accumulators in tensor memory
-    constexpr uint32_t TMEM_COLS = DUO ? 256 : 512;
-    constexpr int SCRATCH = DUO ? 0 : 4 * TC_SCRATCH_WARP;
+    constexpr int TC_STAGES = 4 / SUB;
+    constexpr int NACC = 2;                                 // accumulators in tensor memory
+    constexpr uint32_t TMEM_COLS = 512;
+    constexpr int SCRATCH = 4 * TC_SCRATCH_WARP;
     constexpr int A_STAGE = SUB * TC_A_STAGE, B_STAGE = SUB * B_BLK;
     constexpr uint32_t IDESC = (2u << 4)            // accumulator format S32
                                | (1u << 7)          // A = signed 8 bit
@@ -124,7 +121,7 @@ tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     } else {
         // ===================================================================== epilogue
         const int lg = warp & 3;  // TMEM lane group this warp may read = output (mt*4 + lg), lane = tap-1
-        int *S = reinterpret_cast<int *>(base_ptr + off_scratch + (DUO ? 0 : (warp - 2) * TC_SCRATCH_WARP));
+        int *S = reinterpret_cast<int *>(base_ptr + off_scratch + (warp - 2) * TC_SCRATCH_WARP);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (long item = blockIdx.x; item < items; item += gridDim.x) {
@@ -153,29 +150,21 @@ tc_mac_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * TC_ACC_STRIDE + l * TC_CB, v);
                     // D[(m,tap), cc] belongs to output coefficient cc - tap of this block (tap = lane+1):
                     // skew into S[cc - tap + 32][lane]; rows < 32 finish the previous block, rows >= 32 start this one
+                    // D[(m,tap), cc] belongs to output coefficient cc - tap of this block (tap = lane+1):
+                    // skew into S[cc - tap + 32][lane]; rows < 32 finish the previous block, rows >= 32 start this one
+#pragma unroll
+                    for (int cc = 0; cc < 32; cc++) S[(cc - lane + 31) * 32 + lane] = v[cc];
+                    __syncwarp();
                     int slo = 0, shi = 0;
-                    if (!DUO) {
 #pragma unroll
-                        for (int cc = 0; cc < 32; cc++) S[(cc - lane + 31) * 32 + lane] = v[cc];
-                        __syncwarp();
-#pragma unroll
-                        for (int st = 0; st < 32; st++) {
-                            const int i = (st + lane) & 31;
-                            const bool is_lo = i >= 31 - lane;
-                            const int val = S[(lane + (is_lo ? 0 : 32)) * 32 + i];
-                            slo += is_lo ? val : 0;
-                            shi += is_lo ? 0 : val;
-                        }
-                        __syncwarp();
-                    } else {
-                        // the same diagonal sum by warp shuffles: entry (tap lane L, column cc) belongs to row cc - L + 31 of the skewed
-                        // array; lane l collects rows l (cc <= l) and l + 32 (cc > l); for a given cc exactly one source lane qualifies
-#pragma unroll
-                        for (int cc = 0; cc < 32; cc++) {
-                            const int x = __shfl_sync(0xffffffffu, v[cc], (cc + 31 - lane) & 31);
-                            if (cc > lane) shi += x; else slo += x;
-                        }
+                    for (int st = 0; st < 32; st++) {
+                        const int i = (st + lane) & 31;
+                        const bool is_lo = i >= 31 - lane;
+                        const int val = S[(lane + (is_lo ? 0 : 32)) * 32 + i];
+                        slo += is_lo ? val : 0;
+                        shi += is_lo ? 0 : val;
                     }
+                    __syncwarp();
                     lo[l] = slo;
                     hi[l] = shi;
                 }
@@ -526,19 +515,16 @@ cudaError_t launch_tc_mac_t(const DeviceParams *P, const TcMacArgs &a, int sm_co
     }
     // two 128-byte K blocks per ring stage (2 stages of 88 KB, half as many barrier flips and commits): fc3 of the bench 64.8 -> 62.1 ms on B200; CRCNN_TC_SUB=1 = four 44 KB stages
     static const int sub_env = [] { const char *e = getenv("CRCNN_TC_SUB"); return e ? atoi(e) : 2; }();
-    static const int duo_env = [] { const char *e = getenv("CRCNN_TC_DUO"); return e ? atoi(e) : 0; }();
-    auto k = duo_env ? tc_mac_kernel<PLANES, 1, true> : (sub_env == 2 ? tc_mac_kernel<PLANES, 2, false> : tc_mac_kernel<PLANES, 1, false>);
-    const size_t smem = duo_env ? 1024 + (size_t)2 * (TC_A_STAGE + PLANES * TC_CB * TC_BK) + 16 * 2 + 32 + 16 : tc_smem_bytes<PLANES>();
+    auto k = sub_env == 2 ? tc_mac_kernel<PLANES, 2> : tc_mac_kernel<PLANES, 1>;
+    const size_t smem = tc_smem_bytes<PLANES>();
     static DeviceOnce once;
     if (once.first()) {
-        cudaError_t e = cudaFuncSetAttribute(tc_mac_kernel<PLANES, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<PLANES>());
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mac_kernel<PLANES, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes<PLANES>());
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mac_kernel<PLANES, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 + 2 * (TC_A_STAGE + PLANES * TC_CB * TC_BK) + 16 * 2 + 32 + 16);
+        cudaError_t e = cudaFuncSetAttribute(tc_mac_kernel<PLANES, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mac_kernel<PLANES, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     const long items = (long)a.npos * 2 * a.K * (a.Mpad / TC_BM);
-    const long ctas = (long)sm_count * (duo_env ? 2 : 1);
-    const unsigned grid = (unsigned)(items < ctas ? items : ctas);
+    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
     k<<<grid, TC_THREADS, smem, stream>>>(tmA, tmB, P, a);
     return cudaGetLastError();
 }

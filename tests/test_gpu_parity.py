@@ -95,9 +95,14 @@ def test_multiply_plain_ntt_semantics(env):
 
 def test_add_many(env):
     n, primes, t, eng, orc, rng = env
-    x = random_cts(rng, n, primes, 9)
+    x = random_cts(rng, n, primes, 7)
     got = eng.download(eng.add_many(eng.upload(x)))
     assert np.array_equal(got[0], orc.add_many(x))
+    # more than 128 ciphertexts take the two-level reduction (groups of ~sqrt(count) + a shorter tail group)
+    for count in (129, 300):
+        x = random_cts(rng, n, primes, count)
+        got = eng.download(eng.add_many(eng.upload(x)))
+        assert np.array_equal(got[0], orc.add_many(x)), count
 
 
 def test_square_and_relinearize(env):
