@@ -83,6 +83,28 @@ def test_approx_n8192_batch2_tail_sampled():
     eng.close()
 
 
+def test_tiny_n2048_reference_parameters_every_layer_sampled():
+    """The parameters the reference itself ran the Tiny network with (n = 2048, one 54-bit prime, t = 2^16: Doc/Tesi.lyx:14789-14913)."""
+    eng, orc, net, x, evk_host = _setup("PlainModelTiny", 2048, 2, 47)
+    checked, _ = sampled.check_network(eng, orc, net, x, 2, evk_host=evk_host, samples=4, seed=5, log=print)
+    assert len(checked) == 6
+    eng.close()
+
+
+def test_approx_n16384_batch1_tail_sampled():
+    """The largest degree of the kernel sweep (n = 16384, K = 8, 9 Bsk primes, four 30-bit relinearisation primes): conv2 -> square ->
+    pool -> bn -> fc -> fc of the Approx network at full layer shapes."""
+    from crcnn_b200 import nets
+    eng, orc, net, x, evk_host = _setup("ApproxPlainModel", 16384, 1, 48)
+    x.free()
+    rng = np.random.default_rng(8)
+    nin = nets.layer_io_counts(net.layers[3])[0]
+    x = eng.upload(util.random_cts(rng, 16384, util.PRIMES[16384], nin))
+    checked, _ = sampled.check_network(eng, orc, net, x, 1, evk_host=evk_host, samples=3, seed=6, first=3, log=print)
+    assert len(checked) == 6
+    eng.close()
+
+
 def test_checker_detects_a_wrong_ciphertext():
     """The sampled check is not vacuous: one flipped word in one sampled output fails it."""
     eng, orc, net, x, evk_host = _setup("PlainModel", 8192, 1, 46)
