@@ -343,6 +343,7 @@ def run_sharded(dist, rank, world, local_rank, batch, steps, warmup, rng_seed=10
     per_image = net.zd * net.xd * net.yd
     pin, own = host.pinned_array(batch * per_image * net.ct_words())
     synth_residues(rng, (batch * per_image, 2), PRIMES, n, out=pin.reshape(batch * per_image, 2, K, n + 1))
+    _barrier(dist)
     net.resident_begin(own.ptr, batch)
     net.resident_run(max(1, warmup))
     _barrier(dist)
@@ -441,6 +442,7 @@ def main_b200(args, rank, world, local_rank):
     layers = nets.TOPOLOGIES[MODEL]["layers"]
 
     # ---- warm-up (also builds the resident weight forms once), then the timed device-resident steps
+    _barrier(dist)                                       # NCCL sets its channels up lazily in the first collective: not inside the timed region
     net.resident_begin(own_in.ptr, B)
     net.resident_run(max(3, args.warmup))
     _barrier(dist)
