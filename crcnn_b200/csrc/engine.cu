@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -98,6 +99,13 @@ struct crcnn_ctx {
     size_t tc_scratch_bytes = 12ull << 30;
     std::string err;
     std::map<std::vector<int>, int *> index_cache;
+    // Large device blocks (activations, GEMM staging, transform scratch) are recycled by exact size: a forward pass asks for the same
+    // sizes step after step, and the stream-ordered allocator, although it never releases memory here, occasionally has to re-map
+    // physical memory when its free list is fragmented -- a 100+ ms stall in the middle of a step (seen in pool1 of the bench network).
+    // All work of a context runs on one stream, so a block freed after its last consumer was enqueued may be handed out again at once.
+    std::unordered_map<void *, size_t> big_size;   // live and cached blocks >= kBigBlock
+    std::multimap<size_t, void *> big_free;        // cached, by size
+    size_t big_cached = 0, big_cache_cap = 64ull << 30;
     uint64_t *stage = nullptr;       // persistent H2D staging buffer of crcnn_tensor_upload_into (host layout, pad words included)
     size_t stage_bytes = 0;
     // profiling
@@ -165,13 +173,47 @@ inline size_t poly_words(const crcnn_ctx *c) { return (size_t)c->K * c->n; }
 inline double lp_bytes(const crcnn_ctx *c, double polys) { return polys * c->n * 8.0; }
 inline double lp_bfly(const crcnn_ctx *c, double polys) { return polys * (c->n / 2) * c->logn; }
 
+constexpr size_t kBigBlock = 32ull << 20;
+void big_cache_flush(crcnn_ctx *ctx) {
+    for (auto &kv : ctx->big_free) { ctx->big_size.erase(kv.second); cudaFreeAsync(kv.second, ctx->stream); }
+    ctx->big_free.clear();
+    ctx->big_cached = 0;
+}
 int dev_alloc(crcnn_ctx *ctx, size_t bytes, void **out) {
     *out = nullptr;
     if (bytes == 0) return CRCNN_OK;
-    CU(cudaMallocAsync(out, bytes, ctx->stream));
+    if (bytes >= kBigBlock) {
+        auto it = ctx->big_free.find(bytes);
+        if (it != ctx->big_free.end()) {
+            *out = it->second;
+            ctx->big_cached -= bytes;
+            ctx->big_free.erase(it);
+            return CRCNN_OK;
+        }
+    }
+    cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+    if (e == cudaErrorMemoryAllocation && !ctx->big_free.empty()) {   // the cache holds what the allocator needs: give it back and retry
+        cudaGetLastError();
+        big_cache_flush(ctx);
+        e = cudaMallocAsync(out, bytes, ctx->stream);
+    }
+    CU(e);
+    if (bytes >= kBigBlock) ctx->big_size[*out] = bytes;
     return CRCNN_OK;
 }
-void dev_free(crcnn_ctx *ctx, void *p) { if (p) cudaFreeAsync(p, ctx->stream); }
+void dev_free(crcnn_ctx *ctx, void *p) {
+    if (!p) return;
+    auto it = ctx->big_size.find(p);
+    if (it != ctx->big_size.end()) {
+        if (ctx->big_cached + it->second <= ctx->big_cache_cap) {
+            ctx->big_free.insert({it->second, p});
+            ctx->big_cached += it->second;
+            return;
+        }
+        ctx->big_size.erase(it);
+    }
+    cudaFreeAsync(p, ctx->stream);
+}
 
 int new_tensor(crcnn_ctx *ctx, long count, int size, int ntt, crcnn_tensor **out) {
     auto *t = new crcnn_tensor{count, size, ntt, nullptr};
@@ -594,6 +636,7 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
 int crcnn_ctx_destroy(crcnn_ctx *ctx) {
     if (!ctx) return CRCNN_OK;
     cudaSetDevice(ctx->device);
+    big_cache_flush(ctx);
     cudaStreamSynchronize(ctx->stream);
     prof_collect(ctx);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
