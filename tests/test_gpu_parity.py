@@ -343,3 +343,23 @@ def test_end_to_end_with_real_seal_client():
                 plain[k, i, j] = (im[i:i + 2, j:j + 2].ravel() * wv[k * 4:(k + 1) * 4]).sum() + bv[k]
     assert np.allclose(vals.reshape(2, 3, 3), plain ** 2, atol=1e-3)
     eng.close()
+
+
+def test_empty_shards_are_legal(env):
+    """More ranks than outputs (fc4 has 10 rows, a box has up to 16 GPUs): a rank's range may be empty; the shard calls then return
+    an empty tensor instead of an error, and the layer's kernel choice does not depend on the shard width."""
+    n, primes, t, eng, orc, rng = env
+    x = eng.upload(random_cts(rng, n, primes, 2 * 3 * 3))
+    wv = rng.uniform(-1, 1, size=2 * 2 * 2 * 2).astype(np.float32)
+    bv = rng.uniform(-1, 1, size=2).astype(np.float32)
+    e = eng.conv(x, eng.plain_encode(wv), eng.plain_encode(bv), 1, 3, 3, 2, 1, 1, 2, 2, 2, shard=(2, 0))
+    assert eng.count(e) == 0 and eng.download(e).shape[0] == 0
+    fw = rng.uniform(-1, 1, size=18 * 3).astype(np.float32)
+    fb = rng.uniform(-1, 1, size=3).astype(np.float32)
+    e = eng.fc(x, eng.plain_encode(fw), eng.plain_encode(fb), 1, 18, 3, shard=(1, 0))
+    assert eng.count(e) == 0
+    # the non-empty shards of the same layer still give the layer's bytes
+    want = orc.fc(eng.download(x), 18, 3, orc.encode_many(fw), orc.encode_many(fb)).reshape(3, 2, len(primes), n + 1)
+    got = np.concatenate([eng.download(eng.fc(x, eng.plain_encode(fw), eng.plain_encode(fb), 1, 18, 3, shard=s))
+                          for s in ((0, 1), (1, 0), (1, 2))])
+    assert np.array_equal(got, want)
