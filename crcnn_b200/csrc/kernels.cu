@@ -488,9 +488,9 @@ bn_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, i
 // =====================================================================================
 constexpr int TAP_CT = 1024;   // coefficients per CTA (4 consecutive ones per thread)
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 tapmul_kernel(const DeviceParams *__restrict__ P, TapMulArgs a) {
-    __shared__ uint64_t sm[64 + TAP_CT + 32];
+    __shared__ __align__(16) uint64_t sm[64 + TAP_CT + 32];
     __shared__ short t_delta[96];          // positive terms first, then the negative ones
     __shared__ int t_count[2];
     const int n = P->n, K = P->K;
@@ -543,20 +543,69 @@ tapmul_kernel(const DeviceParams *__restrict__ P, TapMulArgs a) {
         if (threadIdx.x == 0) { t_count[0] = npos; t_count[1] = nneg; }
     }
     const uint64_t *subp = (a.sub && poly == 0) ? a.sub + (long)z * pw + (long)j * n : nullptr;
-    for (int i = threadIdx.x; i < 64 + TAP_CT + 32; i += 256) {
-        int cc = c0 - 64 + i;
+    // Load phase: the limb-polynomial of every window input is resolved ONCE per CTA (s_src), then every thread moves pairs of
+    // residues with 128-bit loads -- the per-element index load and 64-bit address product of the first version were a third of the
+    // kernel's instructions (ncu r02E: 10.6 k warp instructions per CTA, 70 % issue-active).
+    __shared__ const uint64_t *s_src[16];
+    const int R = a.in_index ? a.R : 1;
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + (R < 16 ? R : 16)) {
+        const int r = threadIdx.x - 32;
+        const long ct = a.in_index ? (long)__ldg(a.in_index + o * a.R + r) : o;
+        s_src[r] = a.in + ct * ctw + (long)poly * pw + (long)j * n;
+    }
+    __syncthreads();
+    constexpr int PAIRS = (64 + TAP_CT + 32) / 2, ITER = (PAIRS + 255) / 256;
+    auto finish = [&](int i2, ulonglong2 v, bool summed) {
+        int cc = c0 - 64 + 2 * i2;
         const bool wrapped = cc < 0 || cc >= n;
         cc = cc < 0 ? cc + n : (cc >= n ? cc - n : cc);
-        uint64_t v = 0;
-        const long word = (long)poly * pw + (long)j * n + cc;
-        if (a.in_index) {
-            for (int r = 0; r < a.R; r++) v += __ldg(a.in + (long)__ldg(a.in_index + o * a.R + r) * ctw + word);
-            v = reduce64(v, mod);
-        } else {
-            v = __ldg(a.in + o * ctw + word);
+        if (summed) { v.x = reduce64(v.x, mod); v.y = reduce64(v.y, mod); }
+        if (subp) {
+            const ulonglong2 m2 = __ldg(reinterpret_cast<const ulonglong2 *>(subp + cc));
+            v.x = submod(v.x, m2.x, mod.q); v.y = submod(v.y, m2.y, mod.q);
         }
-        if (subp) v = submod(v, __ldg(subp + cc), mod.q);
-        sm[i] = wrapped ? negmod(v, mod.q) : v;
+        if (wrapped) { v.x = negmod(v.x, mod.q); v.y = negmod(v.y, mod.q); }
+        *reinterpret_cast<ulonglong2 *>(sm + 2 * i2) = v;
+    };
+    auto wrap_cc = [&](int i2) { int cc = c0 - 64 + 2 * i2; return cc < 0 ? cc + n : (cc >= n ? cc - n : cc); };   // even: a pair wraps together
+    if (R == 4 || R == 1) {
+        // all loads of a thread (ITER pairs x R inputs) are issued before the first use: the kernel waits on DRAM latency otherwise
+        // (in batches of two pairs per thread: 32 registers of loads in flight keep the kernel at five CTAs per SM)
+#pragma unroll
+        for (int it0 = 0; it0 < ITER; it0 += 2) {
+            ulonglong2 w[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i2 = threadIdx.x + (it0 + u) * 256;
+                if (it0 + u < ITER && i2 < PAIRS) {
+                    const int cc = wrap_cc(i2);
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (r < R) w[u][r] = __ldg(reinterpret_cast<const ulonglong2 *>(s_src[r] + cc));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i2 = threadIdx.x + (it0 + u) * 256;
+                if (it0 + u < ITER && i2 < PAIRS) {
+                    ulonglong2 v = w[u][0];
+                    if (R == 4) { v.x += w[u][1].x + w[u][2].x + w[u][3].x; v.y += w[u][1].y + w[u][2].y + w[u][3].y; }
+                    finish(i2, v, R > 1);
+                }
+            }
+        }
+    } else {
+        for (int i2 = threadIdx.x; i2 < PAIRS; i2 += 256) {
+            const int cc = wrap_cc(i2);
+            ulonglong2 v = make_ulonglong2(0, 0);
+            for (int r = 0; r < R; r++) {
+                const uint64_t *src = R <= 16 ? s_src[r] + cc
+                                              : a.in + (long)__ldg(a.in_index + o * a.R + r) * ctw + (long)poly * pw + (long)j * n + cc;
+                const ulonglong2 x2 = __ldg(reinterpret_cast<const ulonglong2 *>(src));
+                v.x += x2.x; v.y += x2.y;
+            }
+            finish(i2, v, true);
+        }
     }
     __syncthreads();
     const int npos = t_count[0], nneg = t_count[1];
