@@ -301,7 +301,12 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = a.n;
     const int m_tiles = (a.M + TCN2_MT - 1) / TCN2_MT;
-    const long items = (long)(a.nslots / NS) * m_tiles;   // item = (group of NS consecutive slots, output tile)
+    // item = (group of NS consecutive slots, output tile).  A CTA takes slot groups round robin and runs ALL output tiles of a group back to
+    // back: the second tile streams the group's input planes again, now from L2 (conv2: 4.3 MB per slot) instead of from DRAM -- with the
+    // tiles of a group on neighbouring CTAs the kernel read 26.8 GB for 12.5 GB of staged planes (ncu r01g).
+    const long groups = a.nslots / NS;
+    const long items = (groups > blockIdx.x ? (groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0) * m_tiles;   // items of THIS CTA
+    auto item_group = [&](long it) { return (long)blockIdx.x + (it / m_tiles) * gridDim.x; };
     const int chunks = (a.ncols + TCN2_CB - 1) / TCN2_CB;
     const int ksteps = (a.R + 31) / 32;
     const int KB = (ksteps * 32 + BK - 1) / BK;   // <= TCN2_KBMAX (checked by the launcher)
@@ -330,8 +335,8 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, wphase = 0;
-            for (long item = blockIdx.x; item < items; item += gridDim.x) {
-                const int sl = (int)(item / m_tiles) * NS, mt = (int)(item % m_tiles);
+            for (long item = 0; item < items; item++) {
+                const int sl = (int)item_group(item) * NS, mt = (int)(item % m_tiles);
                 mbar_wait(bar_wempty, wphase ^ 1);
                 mbar_expect_tx(bar_wfull, NS * KB * W_BLOCK);
                 for (int s = 0; s < NS; s++)
@@ -356,7 +361,7 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, acc_phase = 0, wphase = 0;
-            for (long item = blockIdx.x; item < items; item += gridDim.x) {
+            for (long item = 0; item < items; item++) {
                 mbar_wait(bar_wfull, wphase);
                 wphase ^= 1;
                 tc_fence_after();
@@ -408,8 +413,8 @@ tcn2_mac_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
         const long pw = (long)a.K * n;
         const long m_stride = 2L * a.Pimg * pw;      // words between consecutive outputs of one column
         uint32_t acc_phase = 0;
-        for (long item = blockIdx.x; item < items; item += gridDim.x) {
-            const int sl = (int)(item / m_tiles) * NS, mt = (int)(item % m_tiles);
+        for (long item = 0; item < items; item++) {
+            const int sl = (int)item_group(item) * NS, mt = (int)(item % m_tiles);
             const int slot = a.slot0 + sl, j = slot / n, c = slot - j * n;   // first slot of the item; its NS slots share the limb j (n and slot0 are multiples of NS)
             const Mod mod = P->tab[j].mod;
             const TcnFold fold = a.fold[FOLD ? j : 0];
@@ -611,8 +616,8 @@ cudaError_t launch_tcn2_mac_t(const DeviceParams *P, const TcnMacArgs &a, int sm
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const long items = (long)(a.nslots / NS) * ((a.M + TCN2_MT - 1) / TCN2_MT);
-    const unsigned grid = (unsigned)(items < sm_count ? items : sm_count);
+    const long groups = a.nslots / NS;      // a CTA runs every output tile of its slot groups
+    const unsigned grid = (unsigned)(groups < sm_count ? groups : sm_count);
     k<<<grid, TCN2_THREADS, smem, stream>>>(tmW, tmX, P, a);
     return cudaGetLastError();
 }
