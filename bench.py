@@ -584,6 +584,7 @@ def main_b200(args, rank, world, local_rank):
                    "weights": "conv1/conv2/fc4: byte planes of the NTT-form plaintexts resident (limb-split tcgen05 kind::i8 weighted sum in the NTT domain); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
+                "link_bound_below_ms_per_step": h2d / h2d_gbs / 1e6,   # the upload of a step at this rank's measured pinned H2D rate: a forward faster than this is link-bound end to end
                 "device_mem_free_gb": {"after_resident_loop": round(mem_free[0], 1), "after_e2e_loop": round(mem_free[1], 1)},
                 "note": "crcnn_b200::BatchServer: pinned H2D + re-stride of request i+1 on a copy stream while request i runs; scores come back "
                         "through an asynchronous pinned download; the timed region starts before the first upload (not overlapped) and ends when the last scores have landed"},

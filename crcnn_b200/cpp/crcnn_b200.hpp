@@ -963,10 +963,17 @@ public:
                 channels = c->nf; sharded = true; rows = false;
             } else if (auto *f = dynamic_cast<FullyConnectedLayer *>(l)) {
                 if (sharded) x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);
-                int o0, oc; shard_range(f->out_dim, world_, rank_, &o0, &oc);
-                x = f->forward_shard(x, o0, oc);
-                x.zd = oc; x.xd = 1;            // rows play the part of channels for the next gather
-                channels = f->out_dim; sharded = true; rows = true;
+                if (f->out_dim < min_sharded_outputs) {
+                    // a handful of output rows (fc4: 10): the layer's cost is transforming and staging its INPUT, which every rank has in
+                    // full after the gather -- splitting the rows saves nothing and costs another exchange; every rank computes them all
+                    x = f->forward_dev(std::move(x));
+                    channels = 1; sharded = false; rows = false;
+                } else {
+                    int o0, oc; shard_range(f->out_dim, world_, rank_, &o0, &oc);
+                    x = f->forward_shard(x, o0, oc);
+                    x.zd = oc; x.xd = 1;            // rows play the part of channels for the next gather
+                    channels = f->out_dim; sharded = true; rows = true;
+                }
             } else if (auto *bn = dynamic_cast<BatchNormLayer *>(l)) {
                 if (sharded) { int k0, kc; shard_range(channels, world_, rank_, &k0, &kc); x = bn->forward_shard(x, k0, kc); }
                 else x = bn->forward_dev(std::move(x));
@@ -981,6 +988,7 @@ public:
         }
         return x;
     }
+    int min_sharded_outputs = 32;   // fully connected layers with fewer output rows run replicated (no split, no exchange)
     int gather_ntt_form = -1;  // domain the activations are exchanged in: -1 as produced (no transform), 0 coefficient form, 1 NTT form
 
 private:
