@@ -459,8 +459,13 @@ def main_b200(args, rank, world, local_rank):
     mem_free = [torch.cuda.mem_get_info()[0] / 1e9]
     net.serve(own_in.ptr, own_out.ptr, B, 2)             # untimed: staging buffer and the two input tensors exist before the clock starts
     _barrier(dist)
+    alloc0 = eng.alloc_stats()
     ms_e2e = net.serve(own_in.ptr, own_out.ptr, B, args.steps)
     _barrier(dist)
+    alloc1 = eng.alloc_stats()
+    alloc_e2e = {k: alloc1[k] - alloc0[k] for k in ("pool_mallocs", "cache_hits", "cache_bypass", "flushes", "small_mallocs")}
+    serve_done = net.serve_times()
+    request_ms = [round(b - a, 1) for a, b in zip([0.0] + serve_done[:-1], serve_done)]
     mem_free.append(torch.cuda.mem_get_info()[0] / 1e9)
     # the host link by itself: one plain pinned H2D copy of a step's input (explains e2e when the link is the limit)
     host_t = torch.empty(in_words, dtype=torch.int64, pin_memory=True)
@@ -586,6 +591,7 @@ def main_b200(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
                 "link_bound_below_ms_per_step": h2d / h2d_gbs / 1e6,   # the upload of a step at this rank's measured pinned H2D rate: a forward faster than this is link-bound end to end
                 "device_mem_free_gb": {"after_resident_loop": round(mem_free[0], 1), "after_e2e_loop": round(mem_free[1], 1)},
+                "request_ms": request_ms, "allocator": alloc_e2e,
                 "note": "crcnn_b200::BatchServer: pinned H2D + re-stride of request i+1 on a copy stream while request i runs; scores come back "
                         "through an asynchronous pinned download; the timed region starts before the first upload (not overlapped) and ends when the last scores have landed"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,

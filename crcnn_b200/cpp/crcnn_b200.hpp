@@ -17,7 +17,9 @@
 //   poolingLayer.h:12-21, avgPoolingLayer.h:7-14, batchNormLayer.h:13-30, squareLayer.h:9-20,
 //   network.h:11-39.
 #pragma once
+#include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -588,6 +590,7 @@ public:
         div_factor = Plaintext(rt.n() + 1);
         rt.check(crcnn_plain_get(rt.ctx(), pack_.p, 0, div_factor.data()));
     }
+    crcnn_plain *scale_pack() { return pack_.p; }
 protected:
     crcnn_plain *scale() override { return pack_.p; }
 private:
@@ -638,14 +641,19 @@ public:
         mean.resize(num_channels); var.resize(num_channels);
         for (int i = 0; i < num_channels; i++) { mean[i] = m_.fetch(i); var[i] = v_.fetch(i); }
     }
+    void ensure_packs() {
+        if (m_.p) return;
+        std::vector<const Plaintext *> ms, vs;
+        for (auto &p : mean) ms.push_back(&p);
+        for (auto &p : var) vs.push_back(&p);
+        m_.assign(ms); v_.assign(vs);
+    }
+    // avg-pool + this batch-norm in one pass over NTT-form activations (crcnn_pool_bn_forward): what Network::forward_dev calls when an
+    // AvgPoolingLayer is directly followed by a BatchNormLayer (layers 1+2 and 5+6 of the reference's nine-layer blocks, cnnBuilder.cpp:115-134)
+    DeviceTensor forward_after_avgpool(DeviceTensor in, class AvgPoolingLayer &pool);
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
-        if (!m_.p) {
-            std::vector<const Plaintext *> ms, vs;
-            for (auto &p : mean) ms.push_back(&p);
-            for (auto &p : var) vs.push_back(&p);
-            m_.assign(ms); v_.assign(vs);
-        }
+        ensure_packs();
         crcnn_tensor *o = nullptr;
         rt.check(crcnn_bn_forward(rt.ctx(), in.t, in.batch, in.zd, in.xd, in.yd, m_.p, v_.p, &o));
         return DeviceTensor(o, in.zd, in.xd, in.yd, in.batch);
@@ -669,6 +677,15 @@ private:
     std::vector<float> mean_f_, invstd_f_;
     int s0_ = -1, sc_ = -1;
 };
+
+inline DeviceTensor BatchNormLayer::forward_after_avgpool(DeviceTensor in, AvgPoolingLayer &pool) {
+    Runtime &rt = Runtime::get();
+    ensure_packs();
+    if (in.zd != num_channels) throw std::invalid_argument("channel count of the pooled tensor does not match the batch-norm layer");
+    crcnn_tensor *o = nullptr;
+    rt.check(crcnn_pool_bn_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(), m_.p, v_.p, &o));
+    return DeviceTensor(o, in.zd, pool.xo, pool.yo, in.batch);
+}
 
 // ------------------------------------------------------------------------------------------------
 // SquareLayer (CrCNN/src/squareLayer.h:6-28)
@@ -803,11 +820,23 @@ public:
     virtual DeviceTensor forward_dev(DeviceTensor x, int first, int last) {
         if (first < 0 || last > (int)layers.size() || first > last) throw std::invalid_argument("bad layer range");
         for (int i = first; i < last; i++) {
+            // AvgPoolingLayer directly followed by BatchNormLayer: one pass instead of two (same bytes; crcnn_pool_bn_forward)
+            if (fuse_pool_bn && i + 1 < last) {
+                auto *pool = dynamic_cast<AvgPoolingLayer *>(layers[i].get());
+                auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 1].get()) : nullptr;
+                if (bn) {
+                    x = bn->forward_after_avgpool(std::move(x), *pool);
+                    if (after_layer) { after_layer(i); after_layer(i + 1); }
+                    i++;
+                    continue;
+                }
+            }
             x = layers[i]->forward_dev(std::move(x));
             if (after_layer) after_layer(i);
         }
         return x;
     }
+    bool fuse_pool_bn = !(std::getenv("CRCNN_POOL_BN") && std::atoi(std::getenv("CRCNN_POOL_BN")) == 0);   // A/B switch, same bytes
     // Called after layer i has been ENQUEUED (nothing has necessarily run yet): the place to record a CUDA event for per-layer timing,
     // the counterpart of the reference's commented-out chrono timers around layers[i]->forward (network.cpp:39-43).
     std::function<void(int)> after_layer;
@@ -900,14 +929,19 @@ public:
     // The whole loop for `requests` requests reading in(i) and writing out(i): upload of i+1 overlaps forward of i.
     void serve(long requests, const std::function<const std::uint64_t *(long)> &in, const std::function<std::uint64_t *(long)> &out) {
         if (requests <= 0) return;
+        const auto t0 = std::chrono::steady_clock::now();
+        auto stamp = [&] { completed_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count()); };
+        completed_ms.clear();
         stage(0, in(0));
         for (long i = 0; i < requests; i++) {
             run(i, out(i));                       // waits (on the device) for upload i, then forward + async score download
             if (i + 1 < requests) stage(i + 1, in(i + 1));
-            if (i >= 1) wait(i - 1);              // scores of the previous request are complete: the caller may decrypt them
+            if (i >= 1) { wait(i - 1); stamp(); } // scores of the previous request are complete: the caller may decrypt them
         }
         wait(requests - 1);
+        stamp();
     }
+    std::vector<double> completed_ms;   // host clock, from the start of the last serve(), at which each request's scores had landed
     void *copy_stream() { return copy_; }
 
 private:

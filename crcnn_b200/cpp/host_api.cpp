@@ -151,6 +151,14 @@ int crcnn_host_serve(const uint64_t *pinned_in, uint64_t *pinned_out, int batch,
     });
 }
 
+// Host-clock completion time (ms since the start of the last crcnn_host_serve) of each of its requests; returns how many there are.
+int crcnn_host_serve_times(double *out, int cap) {
+    if (!g_srv) return 0;
+    const int n = (int)g_srv->completed_ms.size();
+    for (int i = 0; i < n && i < cap; i++) out[i] = g_srv->completed_ms[i];
+    return n;
+}
+
 void crcnn_host_shutdown() { g_x0.reset(); g_srv.reset(); g_net.reset(); Runtime::get().reset(); }
 
 }  // extern "C"

@@ -43,7 +43,10 @@ struct crcnn_tensor {
     uint64_t *d;
 };
 
+static long next_plain_serial() { static long s = 0; return ++s; }   // contexts are driven by one thread each; ids only need to differ within a process
+
 struct crcnn_plain {
+    long serial = next_plain_serial();   // identity that survives address reuse (the fused constants below are keyed on it)
     long count;
     bool sparse_shape = false;       // every plaintext supported in [0,64) U [n-32,n) (FractionalEncoder output)
     std::vector<uint32_t> off, idx;  // host copy of the sparse form
@@ -62,6 +65,10 @@ struct crcnn_plain {
     // limb-split tensor-core form (tcn_mac.cuh): byte planes of the NTT-form weights [K*n][7][count/R][Kpad]
     uint8_t *tcn_W = nullptr;
     int tcn_R = 0;
+    // fused average pooling + batch-norm (this pack = the batch-norm factors): C[z] = scale (.) invstd[z] with Shoup companions and
+    // D[z] = mean[z] (.) invstd[z] in NTT form, valid for the (scale, mean) packs they were made from
+    uint64_t *fused_C = nullptr, *fused_Csh = nullptr, *fused_D = nullptr;
+    long fused_scale = 0, fused_mean = 0;   // serials of the packs the constants were made from
 };
 
 struct crcnn_evk {
@@ -106,6 +113,7 @@ struct crcnn_ctx {
     std::unordered_map<void *, size_t> big_size;   // live and cached blocks >= kBigBlock
     std::multimap<size_t, void *> big_free;        // cached, by size
     size_t big_cached = 0, big_cache_cap = 64ull << 30;
+    long long st_big_malloc = 0, st_big_hit = 0, st_big_bypass = 0, st_flush = 0, st_small_malloc = 0;   // crcnn_ctx_alloc_stats
     uint64_t *stage = nullptr;       // persistent H2D staging buffer of crcnn_tensor_upload_into (host layout, pad words included)
     size_t stage_bytes = 0;
     // profiling
@@ -188,12 +196,17 @@ int dev_alloc(crcnn_ctx *ctx, size_t bytes, void **out) {
             *out = it->second;
             ctx->big_cached -= bytes;
             ctx->big_free.erase(it);
+            ctx->st_big_hit++;
             return CRCNN_OK;
         }
+        ctx->st_big_malloc++;
+    } else {
+        ctx->st_small_malloc++;
     }
     cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
     if (e == cudaErrorMemoryAllocation && !ctx->big_free.empty()) {   // the cache holds what the allocator needs: give it back and retry
         cudaGetLastError();
+        ctx->st_flush++;
         big_cache_flush(ctx);
         e = cudaMallocAsync(out, bytes, ctx->stream);
     }
@@ -211,6 +224,7 @@ void dev_free(crcnn_ctx *ctx, void *p) {
             return;
         }
         ctx->big_size.erase(it);
+        ctx->st_big_bypass++;
     }
     cudaFreeAsync(p, ctx->stream);
 }
@@ -578,6 +592,11 @@ int crcnn_ctx_create(int n, int K, const uint64_t *q, uint64_t t, int device, cr
         uint64_t thr = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    {   // the exact-size cache may hold up to 3/4 of the device: the CUDA pool would keep those pages anyway (release threshold above); a
+        // request that does not fit flushes the cache and retries (dev_alloc), so the cap only bounds what shape changes can strand
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && tot) c->big_cache_cap = tot / 4 * 3;
+    }
     // upload tables
     int slots = K + hp.d.S;
     auto up = [&](const std::vector<uint64_t> &v, const uint64_t **dst) -> cudaError_t {
@@ -659,6 +678,13 @@ int crcnn_ctx_sync(crcnn_ctx *ctx) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     CU(cudaStreamSynchronize(ctx->stream));
     prof_collect(ctx);
+    return CRCNN_OK;
+}
+
+int crcnn_ctx_alloc_stats(crcnn_ctx *ctx, long long out[6]) {
+    if (!ctx || !out) return CRCNN_ERR_INVALID_ARGUMENT;
+    out[0] = ctx->st_big_malloc; out[1] = ctx->st_big_hit; out[2] = ctx->st_big_bypass; out[3] = ctx->st_flush;
+    out[4] = ctx->st_small_malloc; out[5] = (long long)ctx->big_cached;
     return CRCNN_OK;
 }
 
@@ -928,6 +954,7 @@ int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p) {
     if (!p) return CRCNN_OK;
     dev_free(ctx, p->d_off); dev_free(ctx, p->d_idx); dev_free(ctx, p->d_val);
     dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_mul_sh); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A); dev_free(ctx, p->tcn_W);
+    dev_free(ctx, p->fused_C); dev_free(ctx, p->fused_Csh); dev_free(ctx, p->fused_D);
     delete p;
     return CRCNN_OK;
 }
@@ -1117,6 +1144,78 @@ int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int 
         ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)in->count + Nout) * 2 * ctx->K), (double)Nout * R * 2 * ctx->K * ctx->n);
         cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nout, R, scale ? scale->ntt_mul : nullptr,
                                     scale ? scale->ntt_mul_sh : nullptr, sum_fits_64(ctx, R), o->d, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    *out = o;
+    return CRCNN_OK;
+}
+
+/* Replaces AvgPoolingLayer::forward immediately followed by BatchNormLayer::forward (CrCNN/src/avgPoolingLayer.cpp:16-45,
+ * batchNormLayer.cpp:29-40) in ONE pass when the activations are in NTT form: out = (window sum) * (scale (.) invstd_z) - mean_z (.) invstd_z.
+ * Same canonical residues (ring arithmetic mod q_j), one read of the inputs and one write instead of two of each.  Coefficient-form
+ * activations (after the square layer) take the two coefficient-domain kernels in sequence. */
+int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
+                          crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && scale && mean && invstd && out, "null argument");
+    REQUIRE(scale->count >= 1 && mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
+    const int xo = (xd - xf) / xs + 1, yo = (yd - yf) / ys + 1;
+    const int R = xf * yf;
+    if (!in->ntt || !sum_fits_64(ctx, R)) {      // not the fused kernel's case: the two layers one after the other
+        crcnn_tensor *mid = nullptr;
+        int rc = crcnn_pool_forward(ctx, in, batch, xd, yd, zd, xs, ys, xf, yf, scale, &mid);
+        if (rc) return rc;
+        rc = crcnn_bn_forward(ctx, mid, batch, zd, xo, yo, mean, invstd, out);
+        crcnn_tensor_free(ctx, mid);
+        return rc;
+    }
+    // geometry checks and the window index table are those of the pooling layer: run it on an empty batch? no -- build the table here
+    REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && xf <= xd && yf <= yd, "bad pooling geometry");
+    REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
+    CU(cudaSetDevice(ctx->device));
+    int xl, yl;
+    boundaries(xd, yd, xs, ys, xf, yf, &xl, &yl);
+    if ((xl + xs - 1) / xs != xo || (yl + ys - 1) / ys != yo)
+        return fail(ctx, CRCNN_ERR_UNSUPPORTED, "stride larger than the window leaves outputs the reference never computes");
+    const int Nout = batch * zd * xo * yo;
+    std::vector<int> key = {3, batch, xd, yd, zd, xs, ys, xf, yf};
+    const int *d_index = nullptr;
+    if (ctx->index_cache.find(key) == ctx->index_cache.end()) {
+        std::vector<int> table((size_t)Nout * R);
+        size_t o = 0;
+        for (int bz = 0; bz < batch * zd; bz++)
+            for (int i = 0; i < xo; i++)
+                for (int j = 0; j < yo; j++)
+                    for (int kx = 0; kx < xf; kx++)
+                        for (int ky = 0; ky < yf; ky++) table[o++] = (bz * xd + i * xs + kx) * yd + j * ys + ky;
+        int rc = get_index_table(ctx, key, table, &d_index);
+        if (rc) return rc;
+    } else {
+        d_index = ctx->index_cache[key];
+    }
+    int rc = ensure_form(ctx, scale, PF_NTT_MUL);
+    if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
+    if (!rc) rc = ensure_form(ctx, invstd, PF_NTT_MUL);
+    if (rc) return rc;
+    const size_t words = (size_t)zd * poly_words(ctx);
+    if (!invstd->fused_C || invstd->fused_scale != scale->serial || invstd->fused_mean != mean->serial) {
+        dev_free(ctx, invstd->fused_C); dev_free(ctx, invstd->fused_Csh); dev_free(ctx, invstd->fused_D);
+        invstd->fused_C = invstd->fused_Csh = invstd->fused_D = nullptr;
+        rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_C);
+        if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_Csh);
+        if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_D);
+        if (rc) return rc;
+        CU(launch_pool_bn_consts(ctx->dP, scale->ntt_mul, invstd->ntt_mul, mean->ntt_add, (long)words, invstd->fused_C, invstd->fused_D, ctx->stream));
+        CU(launch_shoup_companion(ctx->dP, invstd->fused_C, (long)words, invstd->fused_Csh, ctx->stream));
+        invstd->fused_scale = scale->serial; invstd->fused_mean = mean->serial;
+    }
+    crcnn_tensor *o = nullptr;
+    rc = new_tensor(ctx, Nout, 2, 1, &o);
+    if (rc) return rc;
+    {
+        ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)in->count + Nout) * 2 * ctx->K), (double)Nout * (R + 1) * 2 * ctx->K * ctx->n);
+        cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nout, R, invstd->fused_C, invstd->fused_Csh, true, o->d, ctx->stream,
+                                    xo * yo, zd, invstd->fused_D);
         if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
     }
     *out = o;

@@ -377,10 +377,19 @@ template <bool SMALL>
 __global__ void __launch_bounds__(256)
 pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in, const int *__restrict__ in_index,
             int R, const uint64_t *__restrict__ scale, const uint64_t *__restrict__ scale_sh, uint64_t *__restrict__ out,
-            int chunks, int per) {
+            int chunks, int per, int per_channel, int channels, const uint64_t *__restrict__ sub) {
     const int n = P->n, K = P->K;
     const long ctw = 2L * K * n;
     const long o = blockIdx.x / chunks;
+    if (channels > 0) {
+        // fused average pooling + batch-norm (NTT form): out = (sum of the window) * C_z - D_z, C_z = scale (.) invstd_z, D_z = mean_z (.)
+        // invstd_z precomputed per channel z -- ((sum * s) - m) * v = sum * (s v) - m v mod q, the same canonical residues as
+        // AvgPoolingLayer::forward followed by BatchNormLayer::forward (avgPoolingLayer.cpp:16-45, batchNormLayer.cpp:29-40)
+        const long z = (o / per_channel) % channels;
+        scale += z * (long)K * n;
+        scale_sh += z * (long)K * n;
+        sub += z * (long)K * n;
+    }
     const long word0 = (long)(blockIdx.x % chunks) * (512L * per) + 2 * threadIdx.x;  // within the ciphertext
     const int j = (int)((word0 / n) % K);
     const Mod mod = P->tab[j].mod;
@@ -424,6 +433,11 @@ pool_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ in,
             v.y = mulshoup_lazy(v.y, sc.y, sh.y, mod.q);
             v.x = v.x >= mod.q ? v.x - mod.q : v.x;
             v.y = v.y >= mod.q ? v.y - mod.q : v.y;
+            if (channels > 0 && word0 < (long)K * n) {     // polynomial 0 only: sub_plain touches c0 (evaluator.cpp:1218-1240)
+                const ulonglong2 d = __ldg(reinterpret_cast<const ulonglong2 *>(sub + lw0 + 512 * k));
+                v.x = submod(v.x, d.x, mod.q);
+                v.y = submod(v.y, d.y, mod.q);
+            }
         } else if (SMALL) {
             v.x = reduce64(v.x, mod);
             v.y = reduce64(v.y, mod);
@@ -948,12 +962,31 @@ static int ew_per(int n) { return n % (512 * 4) == 0 ? 4 : (n % (512 * 2) == 0 ?
 
 cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout,
                            int R, const uint64_t *scale_ntt, const uint64_t *scale_shoup, bool sum_fits_64, uint64_t *out,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int per_channel, int channels, const uint64_t *sub) {
     if (Nout <= 0) return cudaSuccess;
     const int per = ew_per(n), chunks = (int)(2L * K * n / (512 * per));
     const unsigned grid = (unsigned)((long)Nout * chunks);
-    if (sum_fits_64) pool_kernel<true><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out, chunks, per);
-    else pool_kernel<false><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out, chunks, per);
+    if (sum_fits_64) pool_kernel<true><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out, chunks, per, per_channel, channels, sub);
+    else pool_kernel<false><<<grid, 256, 0, stream>>>(P, in, in_index, R, scale_ntt, scale_shoup, out, chunks, per, per_channel, channels, sub);
+    return cudaGetLastError();
+}
+
+// C[z] = S (.) V[z], D[z] = M[z] (.) V[z] (pointwise mod q_j): the per-channel constants of the fused pooling + batch-norm
+__global__ void __launch_bounds__(256)
+pool_bn_consts_kernel(const DeviceParams *__restrict__ P, const uint64_t *__restrict__ S, const uint64_t *__restrict__ V,
+                      const uint64_t *__restrict__ M, long words, uint64_t *__restrict__ C, uint64_t *__restrict__ D) {
+    const long w = (long)blockIdx.x * 256 + threadIdx.x;
+    if (w >= words) return;
+    const long pw = (long)P->K * P->n, lw = w % pw;
+    const Mod mod = P->tab[lw / P->n].mod;
+    const uint64_t v = __ldg(V + w);
+    C[w] = mulmod(__ldg(S + lw), v, mod);
+    D[w] = mulmod(__ldg(M + w), v, mod);
+}
+cudaError_t launch_pool_bn_consts(const DeviceParams *P, const uint64_t *S, const uint64_t *V, const uint64_t *M, long words,
+                                  uint64_t *C, uint64_t *D, cudaStream_t stream) {
+    if (words <= 0) return cudaSuccess;
+    pool_bn_consts_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(P, S, V, M, words, C, D);
     return cudaGetLastError();
 }
 

@@ -44,7 +44,9 @@ cudaError_t launch_mac(const DeviceParams *P, const MacArgs &a, cudaStream_t str
 // scale_shoup = Shoup companions of scale_ntt (launch_shoup_companion); sum_fits_64: R * max(q) < 2^64
 cudaError_t launch_pool(const DeviceParams *P, int n, int K, const uint64_t *in, const int *in_index, int Nout, int R,
                         const uint64_t *scale_ntt, const uint64_t *scale_shoup, bool sum_fits_64, uint64_t *out,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int per_channel = 1, int channels = 0, const uint64_t *sub = nullptr);
+cudaError_t launch_pool_bn_consts(const DeviceParams *P, const uint64_t *S, const uint64_t *V, const uint64_t *M, long words,
+                                  uint64_t *C, uint64_t *D, cudaStream_t stream);
 
 // ---- batch-norm, NTT domain: c0' = (c0 - mean_ntt[z]) * invstd_ntt[z], c1' = c1 * invstd_ntt[z]
 // ciphertext i belongs to channel (i / per_channel) % channels.

@@ -38,6 +38,8 @@ def load():
     h.crcnn_host_resident_begin.argtypes = [_vp, _I]
     h.crcnn_host_resident_run.argtypes = [_I, _dp, _dp]
     h.crcnn_host_serve.argtypes = [_vp, _vp, _I, C.c_long, _dp]
+    h.crcnn_host_serve_times.argtypes = [_dp, _I]
+    h.crcnn_host_serve_times.restype = _I
     _h = h
     return h
 
@@ -137,6 +139,12 @@ class HostNetwork:
         ms = C.c_double()
         self._chk(self.h.crcnn_host_serve(pinned_in_ptr, pinned_out_ptr, batch, requests, C.byref(ms)))
         return ms.value
+
+    def serve_times(self):
+        """ms (host clock, from the start of the last serve()) at which each request's scores had landed."""
+        buf = (C.c_double * 4096)()
+        k = self.h.crcnn_host_serve_times(buf, 4096)
+        return list(buf[:min(k, 4096)])
 
     def close(self):
         self.h.crcnn_host_shutdown()

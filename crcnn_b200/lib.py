@@ -27,6 +27,7 @@ SYMBOLS = [
     ("crcnn_ctx_destroy", _I, [_vp]),
     ("crcnn_ctx_set_stream", _I, [_vp, _vp]),
     ("crcnn_ctx_sync", _I, [_vp]),
+    ("crcnn_ctx_alloc_stats", _I, [_vp, C.POINTER(C.c_longlong)]),
     ("crcnn_ctx_set_weight_cache_bytes", _I, [_vp, C.c_size_t]),
     ("crcnn_ctx_set_tensor_core_mode", _I, [_vp, C.c_int, C.c_int, C.c_size_t]),
     ("crcnn_ctx_set_limb_split_mode", _I, [_vp, C.c_int]),
@@ -63,6 +64,7 @@ SYMBOLS = [
     ("crcnn_fc_forward_shard", _I, [_vp, _vp, _vp, _vp, _I, _I, _I, _I, _I, _vpp]),
     ("crcnn_pool_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp, _vpp]),
     ("crcnn_bn_forward", _I, [_vp, _vp, _I, _I, _I, _I, _vp, _vp, _vpp]),
+    ("crcnn_pool_bn_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp, _vp, _vp, _vpp]),
     ("crcnn_square_forward", _I, [_vp, _vp, _vp, _vpp]),
     ("crcnn_transform_to_ntt", _I, [_vp, _vp]),
     ("crcnn_transform_from_ntt", _I, [_vp, _vp]),
@@ -357,6 +359,16 @@ class Engine:
 
     def bn(self, x, batch, zd, xd, yd, mean, invstd):
         return self._new(self.lib.crcnn_bn_forward, "tensor", x.ptr, batch, zd, xd, yd, mean.ptr, invstd.ptr)
+
+    def alloc_stats(self):
+        """Allocator counters (crcnn_ctx_alloc_stats): dict of pool_mallocs, cache_hits, cache_bypass, flushes, small_mallocs, cached_bytes."""
+        v = (C.c_longlong * 6)()
+        self._chk(self.lib.crcnn_ctx_alloc_stats(self.h, v))
+        return dict(zip(("pool_mallocs", "cache_hits", "cache_bypass", "flushes", "small_mallocs", "cached_bytes"), list(v)))
+
+    def pool_bn(self, x, batch, xd, yd, zd, xs, ys, xf, yf, scale, mean, invstd):
+        """Average pooling + batch-norm in one pass (crcnn_pool_bn_forward)."""
+        return self._new(self.lib.crcnn_pool_bn_forward, "tensor", x.ptr, batch, xd, yd, zd, xs, ys, xf, yf, scale.ptr, mean.ptr, invstd.ptr)
 
     def square_layer(self, x, evk):
         return self._new(self.lib.crcnn_square_forward, "tensor", x.ptr, evk.ptr)

@@ -61,6 +61,11 @@ int crcnn_ctx_destroy(crcnn_ctx *ctx);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream); NULL selects the legacy default stream. */
 int crcnn_ctx_set_stream(crcnn_ctx *ctx, void *cuda_stream);
 int crcnn_ctx_sync(crcnn_ctx *ctx);
+/* Device-memory allocator counters since the context was created: out[0] blocks >= 32 MB taken from the
+ * CUDA pool, out[1] taken from the context's exact-size cache, out[2] returned to the CUDA pool because the cache was full,
+ * out[3] cache flushes after an out-of-memory answer, out[4] small allocations, out[5] bytes the cache holds now.  A steady-state
+ * step should only move out[1] and out[4]. */
+int crcnn_ctx_alloc_stats(crcnn_ctx *ctx, long long out[6]);
 /* Upper bound (bytes) for NTT-form weights kept resident per plaintext pack; larger packs are
  * expanded chunk by chunk into a scratch buffer during forward.  Default 24 GiB. */
 int crcnn_ctx_set_weight_cache_bytes(crcnn_ctx *ctx, size_t bytes);
@@ -186,6 +191,12 @@ int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int 
  * multiply_plain(invstd[z]). */
 int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd, int yd, crcnn_plain *mean,
                      crcnn_plain *invstd, crcnn_tensor **out);
+/* AvgPoolingLayer::forward immediately followed by BatchNormLayer::forward (CrCNN/src/avgPoolingLayer.cpp:16-45,
+ * batchNormLayer.cpp:29-40 -- layers 1+2 and 5+6 of the reference's nine-layer networks, cnnBuilder.cpp:115-134) in one pass over
+ * NTT-form activations: out = (window sum) * (scale (.) invstd_z) - mean_z (.) invstd_z, the same canonical residues as the two
+ * calls.  Coefficient-form activations run the two layers one after the other.  The result has the batch-norm layer's shape. */
+int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
+                          crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out);
 /* Replaces SquareLayer::forward (CrCNN/src/squareLayer.cpp:22-71): Evaluator::square + relinearize. */
 int crcnn_square_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_evk *evk, crcnn_tensor **out);
 

@@ -287,6 +287,35 @@ def test_bn_layer(env):
     assert np.array_equal(got2.reshape(want2.shape), want2)
 
 
+def test_pool_bn_fused(env):
+    """crcnn_pool_bn_forward == AvgPoolingLayer::forward then BatchNormLayer::forward (avgPoolingLayer.cpp:16-45, batchNormLayer.cpp:29-40),
+    for NTT-form activations (the one-pass kernel) and coefficient-form ones (the two layers in turn), batch 1 and 3, 2x2 and 3x3 windows."""
+    n, primes, t, eng, orc, rng = env
+    for (xd, yd, zd, xs, ys, xf, yf, batch) in [(4, 4, 3, 2, 2, 2, 2, 1), (6, 6, 2, 3, 3, 3, 3, 3), (5, 4, 5, 1, 1, 2, 2, 2)]:
+        xo, yo = (xd - xf) // xs + 1, (yd - yf) // ys + 1
+        mv, mp = _layer_params(orc, rng, zd)
+        vv = rng.uniform(-3, 3, size=zd).astype(np.float32)
+        vp = orc.encode_many(vv)
+        d, cc = orc.encode(1.0 / (xf * yf))
+        x = random_cts(rng, n, primes, batch * zd * xd * yd)
+        per = zd * xd * yd
+        want = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, d, cc), zd, xo, yo, mp, vp) for b in range(batch)])
+        packs = (eng.plain_encode_f64([1.0 / (xf * yf)]), eng.plain_encode(mv), eng.plain_encode(vv))
+        tn = eng.upload(x)
+        eng.to_ntt(tn)
+        got_n = eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, *packs))
+        assert np.array_equal(got_n.reshape(want.shape), want)
+        again = eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, *packs))     # cached per-channel constants
+        assert np.array_equal(again.reshape(want.shape), want)
+        got_c = eng.download(eng.pool_bn(eng.upload(x), batch, xd, yd, zd, xs, ys, xf, yf, *packs))
+        assert np.array_equal(got_c.reshape(want.shape), want)
+        # the same scale pack with another batch-norm layer: the cache must not hand back the first layer's constants
+        mv2, mp2 = _layer_params(orc, rng, zd)
+        want2 = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, d, cc), zd, xo, yo, mp2, vp) for b in range(batch)])
+        got2 = eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, packs[0], eng.plain_encode(mv2), packs[2]))
+        assert np.array_equal(got2.reshape(want2.shape), want2)
+
+
 def test_layer_chain_stays_exact(env):
     """conv -> avgpool -> bn -> square -> fc without leaving the device (lazy NTT domain inside)."""
     n, primes, t, eng, orc, rng = env
