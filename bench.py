@@ -606,10 +606,15 @@ def main_b200(args, rank, world, local_rank):
             from oracle.port import Oracle
             pnet = nets.Network(eng, MODEL, evk=eng.evk_upload(*evk_host))       # the same C ABI calls on the same context
             x = eng.upload_ptr(own_in.ptr, B * per_image)
-            checked, _ = sampled.check_network(eng, Oracle(n, PRIMES, t_plain), pnet, x, B, evk_host=evk_host, samples=2, seed=7)
+            checked, y_checked = sampled.check_network(eng, Oracle(n, PRIMES, t_plain), pnet, x, B, evk_host=evk_host, samples=2, seed=7, keep_last=True)
             x.free()
+            # the layer-by-layer path the checker walked and the C++ host path the bench timed (fused layers, serving loop) must agree on
+            # every byte of the scores: own_out still holds the last timed request's download of the same input
+            scores_checked = eng.download(y_checked)
+            y_checked.free()
+            assert np.array_equal(scores_checked.ravel(), np.asarray(pin_out).ravel()), "scores of the timed C++ host path differ from the layer-by-layer path the oracle checked"
             line["parity_sample"] = "ok"
-            line["parity_sample_detail"] = {"ciphertexts_checked_per_layer": checked,
+            line["parity_sample_detail"] = {"ciphertexts_checked_per_layer": checked, "timed_host_path_scores_equal_checked_path": True,
                                             "how": "oracle/sampled.py: random + first/last output ciphertexts of every layer of this run's network at batch %d, "
                                                    "bit-compared with the CPU oracle evaluated on their input windows" % B}
         except AssertionError as e:

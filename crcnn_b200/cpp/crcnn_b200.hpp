@@ -413,6 +413,8 @@ public:
         rt.check(crcnn_conv_forward_shard(rt.ctx(), in.t, w_.p, b_.p, in.batch, xd, yd, zd, xs, ys, xf, yf, nf, k0, kc, &o));
         return DeviceTensor(o, kc, xo, yo, in.batch);
     }
+    crcnn_plain *weight_pack() { ensure_packs(); return w_.p; }
+    crcnn_plain *bias_pack() { ensure_packs(); return b_.p; }
     plaintext3D getKernel(int kernel_index) { materializeHostParameters(); return filters[kernel_index]; }
     Plaintext getBias(int bias_index) { materializeHostParameters(); return biases[bias_index]; }
 
@@ -651,6 +653,9 @@ public:
     // avg-pool + this batch-norm in one pass over NTT-form activations (crcnn_pool_bn_forward): what Network::forward_dev calls when an
     // AvgPoolingLayer is directly followed by a BatchNormLayer (layers 1+2 and 5+6 of the reference's nine-layer blocks, cnnBuilder.cpp:115-134)
     DeviceTensor forward_after_avgpool(DeviceTensor in, class AvgPoolingLayer &pool);
+    // convolution + avg-pool + this batch-norm (crcnn_conv_pool_bn_forward): layers 0-2 of those blocks; a stride-1 convolution is then
+    // evaluated on the pooled grid (window sums of its input, convolution at the pooling stride) -- same bytes, a quarter of the columns
+    DeviceTensor forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, class AvgPoolingLayer &pool);
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
         ensure_packs();
@@ -685,6 +690,17 @@ inline DeviceTensor BatchNormLayer::forward_after_avgpool(DeviceTensor in, AvgPo
     crcnn_tensor *o = nullptr;
     rt.check(crcnn_pool_bn_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(), m_.p, v_.p, &o));
     return DeviceTensor(o, in.zd, pool.xo, pool.yo, in.batch);
+}
+
+inline DeviceTensor BatchNormLayer::forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, AvgPoolingLayer &pool) {
+    Runtime &rt = Runtime::get();
+    ensure_packs();
+    if (conv.nf != num_channels || pool.xd != conv.xo || pool.yd != conv.yo)
+        throw std::invalid_argument("convolution / pooling / batch-norm shapes do not chain");
+    crcnn_tensor *o = nullptr;
+    rt.check(crcnn_conv_pool_bn_forward(rt.ctx(), in.t, conv.weight_pack(), conv.bias_pack(), in.batch, conv.xd, conv.yd, conv.zd, conv.xs, conv.ys,
+                                        conv.xf, conv.yf, conv.nf, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(), m_.p, v_.p, &o));
+    return DeviceTensor(o, conv.nf, pool.xo, pool.yo, in.batch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -820,6 +836,18 @@ public:
     virtual DeviceTensor forward_dev(DeviceTensor x, int first, int last) {
         if (first < 0 || last > (int)layers.size() || first > last) throw std::invalid_argument("bad layer range");
         for (int i = first; i < last; i++) {
+            // ConvolutionalLayer + AvgPoolingLayer + BatchNormLayer: the convolution on the pooled grid (same bytes; crcnn_conv_pool_bn_forward)
+            if (fuse_conv_pool_bn && i + 2 < last) {
+                auto *conv = dynamic_cast<ConvolutionalLayer *>(layers[i].get());
+                auto *pool = conv ? dynamic_cast<AvgPoolingLayer *>(layers[i + 1].get()) : nullptr;
+                auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 2].get()) : nullptr;
+                if (bn) {
+                    x = bn->forward_after_conv_avgpool(std::move(x), *conv, *pool);
+                    if (after_layer) { after_layer(i); after_layer(i + 1); after_layer(i + 2); }
+                    i += 2;
+                    continue;
+                }
+            }
             // AvgPoolingLayer directly followed by BatchNormLayer: one pass instead of two (same bytes; crcnn_pool_bn_forward)
             if (fuse_pool_bn && i + 1 < last) {
                 auto *pool = dynamic_cast<AvgPoolingLayer *>(layers[i].get());
@@ -836,6 +864,7 @@ public:
         }
         return x;
     }
+    bool fuse_conv_pool_bn = !(std::getenv("CRCNN_CONV_POOL_BN") && std::atoi(std::getenv("CRCNN_CONV_POOL_BN")) == 0);   // A/B switch, same bytes
     bool fuse_pool_bn = !(std::getenv("CRCNN_POOL_BN") && std::atoi(std::getenv("CRCNN_POOL_BN")) == 0);   // A/B switch, same bytes
     // Called after layer i has been ENQUEUED (nothing has necessarily run yet): the place to record a CUDA event for per-layer timing,
     // the counterpart of the reference's commented-out chrono timers around layers[i]->forward (network.cpp:39-43).

@@ -69,6 +69,13 @@ struct crcnn_plain {
     // D[z] = mean[z] (.) invstd[z] in NTT form, valid for the (scale, mean) packs they were made from
     uint64_t *fused_C = nullptr, *fused_Csh = nullptr, *fused_D = nullptr;
     long fused_scale = 0, fused_mean = 0;   // serials of the packs the constants were made from
+    // "this plaintext added add_mult times": the additive forms hold add_mult * (Delta-scaled plaintext) mod q.  A bias pack keeps the
+    // derived pack the fused convolution + pooling path adds (one bias per pooled convolution output = window-size biases per sum).
+    int add_mult = 1;
+    // a convolution's weight pack keeps the packs of the pooled-grid path (crcnn_conv_pool_bn_forward): weights and bias with the pooling
+    // scale and the batch-norm folded in, valid for the packs whose serials are in folded_key
+    crcnn_plain *folded_w = nullptr, *folded_b = nullptr;
+    long folded_key[5] = {0, 0, 0, 0, 0};
 };
 
 struct crcnn_evk {
@@ -266,7 +273,10 @@ int ensure_form(crcnn_ctx *ctx, crcnn_plain *p, PlainForm f) {
     if (*slot) return CRCNN_OK;
     int rc = dev_alloc(ctx, (size_t)p->count * poly_words(ctx) * 8, (void **)slot);
     if (rc) return rc;
-    return expand_range(ctx, p, 0, p->count, f, *slot);
+    rc = expand_range(ctx, p, 0, p->count, f, *slot);
+    if (!rc && f != PF_NTT_MUL && p->add_mult != 1)
+        CU(launch_scale_small(ctx->dP, *slot, (long)((size_t)p->count * poly_words(ctx)), p->add_mult, ctx->stream));
+    return rc;
 }
 
 int make_plain(crcnn_ctx *ctx, std::vector<uint32_t> &&off, std::vector<uint32_t> &&idx, std::vector<uint64_t> &&val,
@@ -300,6 +310,27 @@ int ensure_shoup(crcnn_ctx *ctx, crcnn_plain *p) {
     rc = dev_alloc(ctx, words * 8, (void **)&p->ntt_mul_sh);
     if (rc) return rc;
     CU(launch_shoup_companion(ctx->dP, p->ntt_mul, (long)words, p->ntt_mul_sh, ctx->stream));
+    return CRCNN_OK;
+}
+
+// Per-channel constants of "pooling scale, then batch-norm" in NTT form, kept in the batch-norm factor pack:
+// C[z] = scale (.) invstd[z] (with Shoup companions), D[z] = mean[z] (.) invstd[z];  x -> x (.) C[z] - D[z] (D on polynomial 0 only).
+int ensure_pool_bn_consts(crcnn_ctx *ctx, crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd) {
+    int rc = ensure_form(ctx, scale, PF_NTT_MUL);
+    if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
+    if (!rc) rc = ensure_form(ctx, invstd, PF_NTT_MUL);
+    if (rc) return rc;
+    if (invstd->fused_C && invstd->fused_scale == scale->serial && invstd->fused_mean == mean->serial) return CRCNN_OK;
+    const size_t words = (size_t)invstd->count * poly_words(ctx);
+    dev_free(ctx, invstd->fused_C); dev_free(ctx, invstd->fused_Csh); dev_free(ctx, invstd->fused_D);
+    invstd->fused_C = invstd->fused_Csh = invstd->fused_D = nullptr;
+    rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_C);
+    if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_Csh);
+    if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_D);
+    if (rc) return rc;
+    CU(launch_pool_bn_consts(ctx->dP, scale->ntt_mul, invstd->ntt_mul, mean->ntt_add, (long)words, invstd->fused_C, invstd->fused_D, ctx->stream));
+    CU(launch_shoup_companion(ctx->dP, invstd->fused_C, (long)words, invstd->fused_Csh, ctx->stream));
+    invstd->fused_scale = scale->serial; invstd->fused_mean = mean->serial;
     return CRCNN_OK;
 }
 
@@ -955,6 +986,8 @@ int crcnn_plain_free(crcnn_ctx *ctx, crcnn_plain *p) {
     dev_free(ctx, p->d_off); dev_free(ctx, p->d_idx); dev_free(ctx, p->d_val);
     dev_free(ctx, p->ntt_mul); dev_free(ctx, p->ntt_mul_sh); dev_free(ctx, p->ntt_add); dev_free(ctx, p->coef_add); dev_free(ctx, p->tc_A); dev_free(ctx, p->tcn_W);
     dev_free(ctx, p->fused_C); dev_free(ctx, p->fused_Csh); dev_free(ctx, p->fused_D);
+    if (p->folded_w) crcnn_plain_free(ctx, p->folded_w);
+    if (p->folded_b) crcnn_plain_free(ctx, p->folded_b);
     delete p;
     return CRCNN_OK;
 }
@@ -1193,22 +1226,8 @@ int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, i
     } else {
         d_index = ctx->index_cache[key];
     }
-    int rc = ensure_form(ctx, scale, PF_NTT_MUL);
-    if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
-    if (!rc) rc = ensure_form(ctx, invstd, PF_NTT_MUL);
+    int rc = ensure_pool_bn_consts(ctx, scale, mean, invstd);
     if (rc) return rc;
-    const size_t words = (size_t)zd * poly_words(ctx);
-    if (!invstd->fused_C || invstd->fused_scale != scale->serial || invstd->fused_mean != mean->serial) {
-        dev_free(ctx, invstd->fused_C); dev_free(ctx, invstd->fused_Csh); dev_free(ctx, invstd->fused_D);
-        invstd->fused_C = invstd->fused_Csh = invstd->fused_D = nullptr;
-        rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_C);
-        if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_Csh);
-        if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_D);
-        if (rc) return rc;
-        CU(launch_pool_bn_consts(ctx->dP, scale->ntt_mul, invstd->ntt_mul, mean->ntt_add, (long)words, invstd->fused_C, invstd->fused_D, ctx->stream));
-        CU(launch_shoup_companion(ctx->dP, invstd->fused_C, (long)words, invstd->fused_Csh, ctx->stream));
-        invstd->fused_scale = scale->serial; invstd->fused_mean = mean->serial;
-    }
     crcnn_tensor *o = nullptr;
     rc = new_tensor(ctx, Nout, 2, 1, &o);
     if (rc) return rc;
@@ -1219,6 +1238,106 @@ int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, i
         if (e != cudaSuccess) { crcnn_tensor_free(ctx, o); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
     }
     *out = o;
+    return CRCNN_OK;
+}
+
+// Convolution -> average pooling -> batch-norm as the reference's nine-layer blocks chain them (cnnBuilder.cpp:109-134), computed on
+// the POOLED grid.  Every one of these layers is linear (affine) over Z_q[x]/(x^n+1), so with cs / ps the convolution / pooling strides
+//     sum_{(a,b) in window} conv(X)[k, i*ps+a, j*ps+b]  =  sum_r W[k,r] * S[z_r, i*ps*cs + kx_r, j*ps*cs + ky_r]  +  |window| * B_k,
+//     S[z,u,v] = sum_{(a,b) in window} X[z, u + a*cs, v + b*cs]             (one dilated window sum of the layer's INPUT),
+// i.e. the convolution at stride ps*cs over the window sums of its input with the bias added |window| times, and the pooling scale and
+// batch-norm  y -> y (.) C_k - D_k  (ensure_pool_bn_consts) go into the convolution's own constants:
+//     W'[k,r] = W[k,r] (.) C_k,      B'_k = |window| * B_k (.) C_k - D_k        (NTT domain, computed once per network).
+// One weighted sum with (pooled positions / convolution positions) of the columns replaces three layers and two full-size
+// intermediates; the residues are the canonical ones of the same ring elements, hence the reference's bytes.
+int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
+                               int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
+                               crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && w && b && scale && mean && invstd && out, "null argument");
+    REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && nf > 0 && xf <= xd && yf <= yd,
+            "bad convolution geometry");
+    const int cxo = (xd - xf) / xs + 1, cyo = (yd - yf) / ys + 1;          // convolution output (convolutionalLayer.cpp:24)
+    REQUIRE(pxs > 0 && pys > 0 && pxf > 0 && pyf > 0 && pxf <= cxo && pyf <= cyo, "bad pooling geometry");
+    const int pxo = (cxo - pxf) / pxs + 1, pyo = (cyo - pyf) / pys + 1;    // pooled output (poolingLayer.cpp:18)
+    const int Rp = pxf * pyf, R = zd * xf * yf;
+    REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
+    REQUIRE(w->count == (long)nf * R && b->count == nf, "kernel/bias count does not match the layer geometry");
+    REQUIRE(scale->count >= 1 && mean->count == nf && invstd->count == nf, "mean/var count does not match the channel count");
+    CU(cudaSetDevice(ctx->device));
+    // the pooled grid needs: strides that leave no output the reference skips (computeBoundaries), window sums below 2^64, and the
+    // limb-split weighted sum (any NTT-form weights) with the folded weight planes resident
+    const bool pooled_grid = pxs <= pxf && pys <= pyf && xs <= xf && ys <= yf && pxs * xs <= xf && pys * ys <= yf && Rp <= 64 && sum_fits_64(ctx, Rp) &&
+                             ctx->tcn_mode && tcn_planes_for(ctx->hp.d) == 7 && R <= TCN_MAX_R && tc_mac_available() == cudaSuccess &&
+                             tcn_w_bytes(7, nf, tcn_kpad(R), ctx->K, ctx->n) <= ctx->weight_cache_bytes && !getenv("CRCNN_NO_POOLED_CONV");
+    if (!pooled_grid) {   // the three layers one after the other (the last two in one pass when the activations are in NTT form)
+        crcnn_tensor *mid = nullptr;
+        int rc = crcnn_conv_forward(ctx, in, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, &mid);
+        if (rc) return rc;
+        rc = crcnn_pool_bn_forward(ctx, mid, batch, cxo, cyo, nf, pxs, pys, pxf, pyf, scale, mean, invstd, out);
+        crcnn_tensor_free(ctx, mid);
+        return rc;
+    }
+    int rc = ensure_pool_bn_consts(ctx, scale, mean, invstd);
+    if (rc) return rc;
+    const long key[5] = {b->serial, scale->serial, mean->serial, invstd->serial, (long)Rp};
+    if (!w->folded_w || memcmp(key, w->folded_key, sizeof(key)) != 0) {
+        if (w->folded_w) { crcnn_plain_free(ctx, w->folded_w); w->folded_w = nullptr; }
+        if (w->folded_b) { crcnn_plain_free(ctx, w->folded_b); w->folded_b = nullptr; }
+        const size_t pw = poly_words(ctx);
+        // W' : the NTT form of W, row m*R + r times C[m]; staged as byte planes right away (the dense form is released by the staging)
+        rc = make_plain(ctx, std::vector<uint32_t>(w->off), std::vector<uint32_t>(w->idx), std::vector<uint64_t>(w->val), &w->folded_w);
+        if (rc) return rc;
+        w->folded_w->sparse_shape = false;   // never the ternary-tap path: these weights are general residues
+        w->folded_w->tc_state = -1; w->folded_w->tap_state = -1;
+        rc = ensure_form(ctx, w->folded_w, PF_NTT_MUL);
+        if (rc) return rc;
+        CU(launch_fold_affine(ctx->dP, w->folded_w->ntt_mul, (long)nf * R, (long)pw, R, invstd->fused_C, nullptr, ctx->stream));
+        rc = ensure_tcn_weights(ctx, w->folded_w, R);
+        if (rc) return rc;
+        // B' : |window| * (Delta-scaled bias) in NTT form, times C[m], minus D[m]
+        rc = make_plain(ctx, std::vector<uint32_t>(b->off), std::vector<uint32_t>(b->idx), std::vector<uint64_t>(b->val), &w->folded_b);
+        if (rc) return rc;
+        w->folded_b->add_mult = Rp;
+        rc = ensure_form(ctx, w->folded_b, PF_NTT_ADD);
+        if (rc) return rc;
+        CU(launch_fold_affine(ctx->dP, w->folded_b->ntt_add, (long)nf, (long)pw, 1, invstd->fused_C, invstd->fused_D, ctx->stream));
+        memcpy(w->folded_key, key, sizeof(key));
+    }
+    // S: dilated window sums of the input, (zd, sxd, syd) per image, in the input's domain
+    const int sxd = xd - (pxf - 1) * xs, syd = yd - (pyf - 1) * ys;
+    const int Nsum = batch * zd * sxd * syd;
+    std::vector<int> skey = {4, batch, xd, yd, zd, xs, ys, pxf, pyf};
+    const int *d_index = nullptr;
+    if (ctx->index_cache.find(skey) == ctx->index_cache.end()) {
+        std::vector<int> table((size_t)Nsum * Rp);
+        size_t o = 0;
+        for (int bz = 0; bz < batch * zd; bz++)
+            for (int u = 0; u < sxd; u++)
+                for (int v = 0; v < syd; v++)
+                    for (int a = 0; a < pxf; a++)
+                        for (int c = 0; c < pyf; c++) table[o++] = (bz * xd + u + a * xs) * yd + v + c * ys;
+        rc = get_index_table(ctx, skey, table, &d_index);
+        if (rc) return rc;
+    } else {
+        d_index = ctx->index_cache[skey];
+    }
+    crcnn_tensor *sums = nullptr, *pooled = nullptr;
+    rc = new_tensor(ctx, Nsum, 2, in->ntt, &sums);
+    if (rc) return rc;
+    {
+        ProfScope ps(ctx, KC_POOL, lp_bytes(ctx, ((double)in->count + Nsum) * 2 * ctx->K), (double)Nsum * Rp * 2 * ctx->K * ctx->n);
+        cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nsum, Rp, nullptr, nullptr, true, sums->d, ctx->stream);
+        if (e != cudaSuccess) { crcnn_tensor_free(ctx, sums); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    rc = crcnn_conv_forward(ctx, sums, w->folded_w, w->folded_b, batch, sxd, syd, zd, pxs * xs, pys * ys, xf, yf, nf, &pooled);
+    crcnn_tensor_free(ctx, sums);
+    if (rc) return rc;
+    if (pooled->count != (long)batch * nf * pxo * pyo || !pooled->ntt) {
+        crcnn_tensor_free(ctx, pooled);
+        return fail(ctx, CRCNN_ERR_UNSUPPORTED, "pooled-grid convolution produced an unexpected shape");
+    }
+    *out = pooled;
     return CRCNN_OK;
 }
 

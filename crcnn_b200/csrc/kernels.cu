@@ -666,6 +666,47 @@ cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, 
     return cudaGetLastError();
 }
 
+// data[w] = times * data[w] mod q (times small): the additive form of a plaintext that is added `times` times.  Once per pack.
+__global__ void __launch_bounds__(256)
+scale_small_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data, long words, int times) {
+    const long w = (long)blockIdx.x * 256 + threadIdx.x;
+    if (w >= words) return;
+    const uint64_t q = P->tab[(w / P->n) % P->K].mod.q;
+    const uint64_t v = data[w];
+    uint64_t acc = 0;
+    for (int i = 0; i < times; i++) acc = addmod(acc, v, q);
+    data[w] = acc;
+}
+
+// data[row][K][n] = data[row] (.) C[row / group] - D[row / group] (D may be null; pointwise mod q_j): folds per-channel constants into
+// the NTT forms of a convolution's weights (group = fan-in) and bias (group = 1).  Once per network.
+__global__ void __launch_bounds__(256)
+fold_affine_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ data, long rows, int group, const uint64_t *__restrict__ C,
+                   const uint64_t *__restrict__ D) {
+    const long pw = (long)P->K * P->n;
+    const long w = (long)blockIdx.x * 256 + threadIdx.x;
+    if (w >= rows * pw) return;
+    const long row = w / pw, lw = w - row * pw;
+    const Mod mod = P->tab[lw / P->n].mod;
+    const long cw = (row / group) * pw + lw;
+    uint64_t v = mulmod(data[w], __ldg(C + cw), mod);
+    if (D) v = submod(v, __ldg(D + cw), mod.q);
+    data[w] = v;
+}
+
+cudaError_t launch_fold_affine(const DeviceParams *P, uint64_t *data, long rows, long poly_words, int group, const uint64_t *C,
+                               const uint64_t *D, cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    fold_affine_kernel<<<(unsigned)((rows * poly_words + 255) / 256), 256, 0, stream>>>(P, data, rows, group, C, D);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scale_small(const DeviceParams *P, uint64_t *data, long words, int times, cudaStream_t stream) {
+    if (words <= 0) return cudaSuccess;
+    scale_small_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(P, data, words, times);
+    return cudaGetLastError();
+}
+
 // Four consecutive residues per thread (two 128-bit loads and stores); additive ops touch polynomial 0 only, and only those words
 // are launched.  HBM-bound: 2 x 8 bytes per residue of the ciphertext, the plaintext operand (K*n words, shared by every
 // ciphertext of the launch) comes from L2.

@@ -70,6 +70,10 @@ struct TapMulArgs {
 cudaError_t launch_tapmul(const DeviceParams *P, int n, int K, const TapMulArgs &a, cudaStream_t stream);
 
 // ---- Shoup companions floor(v * 2^64 / q_j) of `words` canonical residues laid out [..][K][n]
+// data[row] = data[row] (.) C[row / group] - D[row / group] over rows of poly_words residues (D may be null)
+cudaError_t launch_fold_affine(const DeviceParams *P, uint64_t *data, long rows, long poly_words, int group, const uint64_t *C,
+                               const uint64_t *D, cudaStream_t stream);
+cudaError_t launch_scale_small(const DeviceParams *P, uint64_t *data, long words, int times, cudaStream_t stream);   // data *= times (mod q), times small
 cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, long words, uint64_t *out, cudaStream_t stream);
 
 // ---- generic plaintext ops on `count` ciphertexts of `size` polys (evaluator-level API)

@@ -65,6 +65,7 @@ SYMBOLS = [
     ("crcnn_pool_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp, _vpp]),
     ("crcnn_bn_forward", _I, [_vp, _vp, _I, _I, _I, _I, _vp, _vp, _vpp]),
     ("crcnn_pool_bn_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp, _vp, _vp, _vpp]),
+    ("crcnn_conv_pool_bn_forward", _I, [_vp, _vp, _vp, _vp] + [_I] * 13 + [_vp, _vp, _vp, _vpp]),
     ("crcnn_square_forward", _I, [_vp, _vp, _vp, _vpp]),
     ("crcnn_transform_to_ntt", _I, [_vp, _vp]),
     ("crcnn_transform_from_ntt", _I, [_vp, _vp]),
@@ -359,6 +360,11 @@ class Engine:
 
     def bn(self, x, batch, zd, xd, yd, mean, invstd):
         return self._new(self.lib.crcnn_bn_forward, "tensor", x.ptr, batch, zd, xd, yd, mean.ptr, invstd.ptr)
+
+    def conv_pool_bn(self, x, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf, scale, mean, invstd):
+        """Convolution + average pooling + batch-norm on the pooled grid (crcnn_conv_pool_bn_forward)."""
+        return self._new(self.lib.crcnn_conv_pool_bn_forward, "tensor", x.ptr, w.ptr, b.ptr, batch, xd, yd, zd, xs, ys, xf, yf, nf,
+                         pxs, pys, pxf, pyf, scale.ptr, mean.ptr, invstd.ptr)
 
     def alloc_stats(self):
         """Allocator counters (crcnn_ctx_alloc_stats): dict of pool_mallocs, cache_hits, cache_bypass, flushes, small_mallocs, cached_bytes."""

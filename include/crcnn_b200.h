@@ -197,6 +197,20 @@ int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd
  * calls.  Coefficient-form activations run the two layers one after the other.  The result has the batch-norm layer's shape. */
 int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
                           crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out);
+/* ConvolutionalLayer::forward, AvgPoolingLayer::forward and BatchNormLayer::forward in a row (layers 0-2 of the reference's
+ * nine-layer networks, CrCNN/src/cnnBuilder.cpp:109-134; convolutionalLayer.cpp:136-196, avgPoolingLayer.cpp:16-45,
+ * batchNormLayer.cpp:29-40), producing the batch-norm layer's output ciphertexts -- the same bytes as the three calls.  The work
+ * is done on the pooled grid: the pooling windows are summed over the layer's INPUT (dilated by the convolution stride), the
+ * convolution runs at stride (pool stride x conv stride) over those sums, and the pooling scale and the batch-norm are folded into
+ * the convolution's weights and bias once (W' = W (.) scale (.) invstd_k, B' = |window| B (.) scale (.) invstd_k - mean_k (.) invstd_k,
+ * NTT domain).  All three layers are affine over Z_q[x]/(x^n+1), so the canonical residues are identical while one weighted sum over
+ * the pooled positions replaces three layers and two full-size intermediates.  Geometries where the combined stride exceeds the
+ * filter, or contexts without the limb-split tensor-core GEMM, run crcnn_conv_forward + crcnn_pool_bn_forward.  conv: (xd,yd,zd)
+ * input, stride (xs,ys), filter (xf,yf), nf kernels; pool: stride (pxs,pys), window (pxf,pyf).  Environment CRCNN_NO_POOLED_CONV=1
+ * forces the layer-by-layer path (A/B timing, tests). */
+int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
+                               int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
+                               crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out);
 /* Replaces SquareLayer::forward (CrCNN/src/squareLayer.cpp:22-71): Evaluator::square + relinearize. */
 int crcnn_square_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_evk *evk, crcnn_tensor **out);
 

@@ -5,6 +5,8 @@ to the golden fixtures by the CPU tests).  Where oracle/_ref/libcrcnn_ref.so is 
 reference (SEAL 2.3.1 + CrCNN layers) encrypts the inputs and decrypts the outputs as well.
 Bar: bit-exact (integer residues) -- np.array_equal, no tolerance.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -314,6 +316,69 @@ def test_pool_bn_fused(env):
         want2 = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, d, cc), zd, xo, yo, mp2, vp) for b in range(batch)])
         got2 = eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, packs[0], eng.plain_encode(mv2), packs[2]))
         assert np.array_equal(got2.reshape(want2.shape), want2)
+
+
+def test_conv_pool_bn_on_the_pooled_grid(env):
+    """crcnn_conv_pool_bn_forward == ConvolutionalLayer, AvgPoolingLayer, BatchNormLayer::forward in a row (convolutionalLayer.cpp:136-196,
+    avgPoolingLayer.cpp:16-45, batchNormLayer.cpp:29-40).  Stride-1 convolutions are evaluated on the pooled grid (window sums of the input,
+    convolution at the pooling stride, bias once per window element); the rest take the layer-by-layer path.  Cases: the headline block's
+    shape in small (5x5 filter, 2x2/2 pooling), 3x3/3 and overlapping 3x3/2 windows, several input channels, batch > 1, a strided convolution."""
+    n, primes, t, eng, orc, rng = env
+    cases = [  # xd yd zd  xs ys xf yf nf  pxs pys pxf pyf  batch  pooled grid?
+        (8, 8, 1, 1, 1, 5, 5, 3, 2, 2, 2, 2, 2, True),
+        (7, 8, 2, 1, 1, 2, 3, 2, 3, 3, 3, 3, 1, False),     # pooling stride 3 > filter 2: outputs the strided convolution would skip
+        (8, 7, 2, 1, 1, 2, 2, 3, 2, 2, 3, 3, 2, True),      # overlapping windows
+        (9, 9, 1, 2, 2, 5, 5, 2, 1, 1, 2, 2, 2, True),      # the headline block: 5x5 stride 2, then 2x2 stride 1 (cnnBuilder.cpp:115-117)
+        (8, 9, 2, 2, 1, 3, 2, 2, 1, 2, 2, 2, 1, True),      # different strides per axis
+        (9, 9, 1, 2, 2, 3, 3, 2, 2, 2, 2, 2, 1, False),     # combined stride 4 > filter 3
+    ]
+    for (xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf, batch, pooled_grid) in cases:
+        cxo, cyo = (xd - xf) // xs + 1, (yd - yf) // ys + 1
+        pxo, pyo = (cxo - pxf) // pxs + 1, (cyo - pyf) // pys + 1
+        wv, wp = _layer_params(orc, rng, nf * zd * xf * yf)
+        bv, bp = _layer_params(orc, rng, nf)
+        mv, mp = _layer_params(orc, rng, nf)
+        vv = rng.uniform(-3, 3, size=nf).astype(np.float32)
+        vp = orc.encode_many(vv)
+        d, cc = orc.encode(1.0 / (pxf * pyf))
+        per = zd * xd * yd
+        x = random_cts(rng, n, primes, batch * per)
+        want = np.concatenate([
+            orc.bn(orc.pool(orc.conv(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, nf, wp, bp).reshape(nf * cxo * cyo, *x.shape[1:]),
+                            cxo, cyo, nf, pxs, pys, pxf, pyf, d, cc), nf, pxo, pyo, mp, vp) for b in range(batch)])
+        w, bias = eng.plain_encode(wv), eng.plain_encode(bv)
+        packs = (eng.plain_encode_f64([1.0 / (pxf * pyf)]), eng.plain_encode(mv), eng.plain_encode(vv))
+        geo = (batch, xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf)
+        def run():
+            eng.prof_reset(); eng.prof_enable(True)
+            y = eng.download(eng.conv_pool_bn(eng.upload(x), w, bias, *geo, *packs))
+            work = eng.prof_work()
+            eng.prof_enable(False)
+            return y, work
+        got, work = run()
+        assert np.array_equal(got.reshape(want.shape), want), geo
+        # which path ran: CRCNN_NO_POOLED_CONV forces the layer-by-layer path, whose weighted sum has more columns (other algorithmic work)
+        # (ternary-tap GEMM off for the comparison, so that both paths count their work in the same kernel family)
+        eng.set_tensor_core_mode(0)
+        os.environ["CRCNN_NO_POOLED_CONV"] = "1"
+        try:
+            got_l, work_l = run()
+            del os.environ["CRCNN_NO_POOLED_CONV"]
+            got, work = run()
+        finally:
+            os.environ.pop("CRCNN_NO_POOLED_CONV", None)
+            eng.set_tensor_core_mode(1)
+        assert np.array_equal(got_l.reshape(want.shape), want) and np.array_equal(got.reshape(want.shape), want), geo
+        macs = lambda wk: sum(v[1] for k, v in wk.items() if k.startswith("weighted_sum"))
+        assert (macs(work) < macs(work_l)) == pooled_grid, (geo, work, work_l)
+        tn = eng.upload(x)
+        eng.to_ntt(tn)      # NTT-form input
+        got_n = eng.download(eng.conv_pool_bn(tn, w, bias, *geo, *packs))
+        assert np.array_equal(got_n.reshape(want.shape), want), geo
+        # the bias pack still adds ONE bias in a plain convolution afterwards (the repeated form lives in a derived pack)
+        want_c = np.concatenate([orc.conv(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, nf, wp, bp).reshape(nf * cxo * cyo, *x.shape[1:]) for b in range(batch)])
+        got_c = eng.download(eng.conv(eng.upload(x), w, bias, batch, xd, yd, zd, xs, ys, xf, yf, nf))
+        assert np.array_equal(got_c.reshape(want_c.shape), want_c), geo
 
 
 def test_layer_chain_stays_exact(env):
