@@ -479,7 +479,22 @@ def main_b200(args, rank, world, local_rank):
     h2d_gbs = h2d / ev3[0].elapsed_time(ev3[1]) / 1e6
     del dev_buf, host_t
 
-    ms_total, ms_e2e = _max_over_ranks(dist, [ms_total, ms_e2e])
+    # ---- the same steps with every reference layer as its own call (layer fusion off): what the algebraic folds are worth, and the
+    # ternary-tap GEMM of fc3 (which the composed fc3*fc4 layer replaces) measured at the headline shape
+    lbl_steps = max(1, min(args.steps, 5))
+    net.set_fusion(False)
+    net.resident_begin(own_in.ptr, B)
+    net.resident_run(3)
+    _barrier(dist)
+    eng.prof_reset(); eng.prof_enable(True)
+    ms_lbl, per_layer_lbl = net.resident_run(lbl_steps)
+    _barrier(dist)
+    net.resident_end()
+    prof_lbl, work_lbl = eng.prof(), eng.prof_work()
+    eng.prof_enable(False)
+    net.set_fusion(True)
+
+    ms_total, ms_e2e, ms_lbl = _max_over_ranks(dist, [ms_total, ms_e2e, ms_lbl])
     images = B * args.steps * (1 if crt else world)
     value = images / (ms_total / 1000.0)
     e2e_value = images / (ms_e2e / 1000.0)
@@ -571,6 +586,14 @@ def main_b200(args, rank, world, local_rank):
                      "int_pipe_probe_gmac_s": probe_rate / 1e9, "imad_wide_probe_ginstr_s": wide_rate / 1e9,
                      "umma_i8_probe_tops": 2 * umma_rate / 1e12, "classes": classes})
     launches = int(sum(v[0] for v in prof.values()))
+    layer_by_layer = {"value": B * lbl_steps * (1 if crt else world) / (ms_lbl / 1000.0), "unit": "images/s", "ms_per_step": ms_lbl / lbl_steps,
+                      "steps": lbl_steps, "per_layer_ms": dict(zip(layer_names, per_layer_lbl)),
+                      "note": "layer fusion off (crcnn_b200::Network::fuse_* = false): one C-ABI call per reference layer, same output bytes"}
+    if prof_lbl.get("weighted_sum_tc_i8", (0, 0.0))[0]:
+        l_c, ms_c = prof_lbl["weighted_sum_tc_i8"]
+        ops = work_lbl.get("weighted_sum_tc_i8", (0.0, 0.0))[1]
+        layer_by_layer["weighted_sum_tc_i8"] = {"ms_per_step": ms_c / lbl_steps, "int8_tops": 2 * ops / (ms_c / 1000.0) / 1e12,
+                                                "tensor_frac": ops / (ms_c / 1000.0) / umma_rate, "ncu": counters.get("weighted_sum_tc_i8")}
 
     workload = ("PlainModel.h5 encoded net (conv-avgpool-bn-conv-square-avgpool-bn-fc-fc), n=8192, K=4, t=2^30, 32x32 zero-bordered input"
                 if (MODEL, N_POLY) == ("PlainModel", 8192) else "%s encoded net, n=%d, K=%d, t=2^%d" % (MODEL, N_POLY, K, T_PLAIN.bit_length() - 1))
@@ -586,6 +609,9 @@ def main_b200(args, rank, world, local_rank):
         "config": {"workload": workload, "images_per_step_per_gpu": B, "parallelism": parallelism,
                    "host": "C++17: crcnn_b200::CnnBuilder + Network::forward_dev (value) and BatchServer (e2e) behind libcrcnn_b200_host.so",
                    "l2": "inputs (%.1f GB per step) and weights exceed the 126 MB L2; no flush needed" % (h2d / 1e9),
+                   "fusion": "default engine behaviour, same output bytes as layer by layer (checked in parity_sample): conv1+avgpool1+bn1 as one weighted sum "
+                             "on the pooled grid with the scale and batch-norm folded into its weights; avgpool2+bn2 back to back; fc3+fc4 as one composed "
+                             "layer W4*W3 (built on the device at the first forward); `layer_by_layer` repeats the measurement with all of it off",
                    "weights": "conv1/conv2/fc4: byte planes of the NTT-form plaintexts resident (limb-split tcgen05 kind::i8 weighted sum in the NTT domain); fc3: ternary tap matrix resident (tcgen05 kind::i8 weighted sum in the coefficient domain)"},
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "h2d_link_gbs": h2d_gbs,
@@ -595,6 +621,7 @@ def main_b200(args, rank, world, local_rank):
                 "note": "crcnn_b200::BatchServer: pinned H2D + re-stride of request i+1 on a copy stream while request i runs; scores come back "
                         "through an asynchronous pinned download; the timed region starts before the first upload (not overlapped) and ends when the last scores have landed"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_layer_ms": per_layer, "kernel_ms": kernel_ms,
+        "layer_by_layer": layer_by_layer,
     }
     if crt:
         line["crt"] = crt

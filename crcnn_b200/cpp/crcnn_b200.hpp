@@ -514,6 +514,16 @@ public:
         rt.check(crcnn_fc_forward(rt.ctx(), in.t, w_.p, b_.p, in.batch, in_dim, out_dim, &o));
         return DeviceTensor(o, 1, out_dim, 1, in.batch);
     }
+    // this layer and the fully connected layer that follows it directly, as one composed layer (crcnn_fc_fc_forward): what
+    // Network::forward_dev calls for fc3 -> fc4 (cnnBuilder.cpp:121-122); the composed weights are built at the first call
+    DeviceTensor forward_then(DeviceTensor in, FullyConnectedLayer &next) {
+        Runtime &rt = Runtime::get();
+        ensure_packs(); next.ensure_packs();
+        if (next.in_dim != out_dim) throw std::invalid_argument("fully connected layers do not chain");
+        crcnn_tensor *o = nullptr;
+        rt.check(crcnn_fc_fc_forward(rt.ctx(), in.t, w_.p, b_.p, next.w_.p, next.b_.p, in.batch, in_dim, out_dim, next.out_dim, &o));
+        return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
+    }
     // Output rows [o0, o0+oc) only: this GPU's share of the reference's row split (fullyConnectedLayer.cpp:148-158)
     DeviceTensor forward_shard(const DeviceTensor &in, int o0, int oc) {
         Runtime &rt = Runtime::get();
@@ -848,6 +858,17 @@ public:
                     continue;
                 }
             }
+            // FullyConnectedLayer directly followed by FullyConnectedLayer: one composed layer (same bytes; crcnn_fc_fc_forward)
+            if (fuse_fc_fc && i + 1 < last) {
+                auto *f1 = dynamic_cast<FullyConnectedLayer *>(layers[i].get());
+                auto *f2 = f1 ? dynamic_cast<FullyConnectedLayer *>(layers[i + 1].get()) : nullptr;
+                if (f2) {
+                    x = f1->forward_then(std::move(x), *f2);
+                    if (after_layer) { after_layer(i); after_layer(i + 1); }
+                    i++;
+                    continue;
+                }
+            }
             // AvgPoolingLayer directly followed by BatchNormLayer: one pass instead of two (same bytes; crcnn_pool_bn_forward)
             if (fuse_pool_bn && i + 1 < last) {
                 auto *pool = dynamic_cast<AvgPoolingLayer *>(layers[i].get());
@@ -864,6 +885,7 @@ public:
         }
         return x;
     }
+    bool fuse_fc_fc = !(std::getenv("CRCNN_FC_FC") && std::atoi(std::getenv("CRCNN_FC_FC")) == 0);   // A/B switch, same bytes
     bool fuse_conv_pool_bn = !(std::getenv("CRCNN_CONV_POOL_BN") && std::atoi(std::getenv("CRCNN_CONV_POOL_BN")) == 0);   // A/B switch, same bytes
     bool fuse_pool_bn = !(std::getenv("CRCNN_POOL_BN") && std::atoi(std::getenv("CRCNN_POOL_BN")) == 0);   // A/B switch, same bytes
     // Called after layer i has been ENQUEUED (nothing has necessarily run yet): the place to record a CUDA event for per-layer timing,

@@ -151,6 +151,14 @@ int crcnn_host_serve(const uint64_t *pinned_in, uint64_t *pinned_out, int batch,
     });
 }
 
+// Layer fusion of the built network on (default) / off: off runs every reference layer as its own call (A/B timing; same bytes).
+int crcnn_host_set_fusion(int on) {
+    return guarded([&] {
+        if (!g_net) throw std::invalid_argument("no network built");
+        g_net->fuse_fc_fc = g_net->fuse_conv_pool_bn = g_net->fuse_pool_bn = on != 0;
+    });
+}
+
 // Host-clock completion time (ms since the start of the last crcnn_host_serve) of each of its requests; returns how many there are.
 int crcnn_host_serve_times(double *out, int cap) {
     if (!g_srv) return 0;

@@ -72,6 +72,7 @@ struct crcnn_plain {
     // "this plaintext added add_mult times": the additive forms hold add_mult * (Delta-scaled plaintext) mod q.  A bias pack keeps the
     // derived pack the fused convolution + pooling path adds (one bias per pooled convolution output = window-size biases per sum).
     int add_mult = 1;
+    bool dense_only = false;       // a derived pack that exists only in its device forms (no sparse plaintexts to expand from)
     // a convolution's weight pack keeps the packs of the pooled-grid path (crcnn_conv_pool_bn_forward): weights and bias with the pooling
     // scale and the batch-norm folded in, valid for the packs whose serials are in folded_key
     crcnn_plain *folded_w = nullptr, *folded_b = nullptr;
@@ -271,6 +272,7 @@ int expand_range(crcnn_ctx *ctx, crcnn_plain *p, long first, long count, PlainFo
 int ensure_form(crcnn_ctx *ctx, crcnn_plain *p, PlainForm f) {
     uint64_t **slot = f == PF_NTT_MUL ? &p->ntt_mul : (f == PF_NTT_ADD ? &p->ntt_add : &p->coef_add);
     if (*slot) return CRCNN_OK;
+    if (p->dense_only) return fail(ctx, CRCNN_ERR_UNSUPPORTED, "this derived plaintext pack has no such form");
     int rc = dev_alloc(ctx, (size_t)p->count * poly_words(ctx) * 8, (void **)slot);
     if (rc) return rc;
     rc = expand_range(ctx, p, 0, p->count, f, *slot);
@@ -959,6 +961,7 @@ int crcnn_plain_encode_f64(crcnn_ctx *ctx, const double *values, long count, crc
 int crcnn_plain_get(crcnn_ctx *ctx, const crcnn_plain *p, long index, uint64_t *out_words) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(p && out_words && index >= 0 && index < p->count, "plaintext index out of range");
+    REQUIRE(!p->dense_only, "derived plaintext pack: no host form");
     memset(out_words, 0, (size_t)(ctx->n + 1) * 8);
     for (uint32_t e = p->off[index]; e < p->off[index + 1]; e++) out_words[p->idx[e]] = p->val[e];
     return CRCNN_OK;
@@ -967,6 +970,7 @@ int crcnn_plain_get(crcnn_ctx *ctx, const crcnn_plain *p, long index, uint64_t *
 int crcnn_plain_get_ntt(crcnn_ctx *ctx, crcnn_plain *p, long index, uint64_t *out_words) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
     REQUIRE(p && out_words && index >= 0 && index < p->count, "plaintext index out of range");
+    REQUIRE(!p->dense_only, "derived plaintext pack: no host form");
     uint64_t *tmp = nullptr;
     int rc = dev_alloc(ctx, poly_words(ctx) * 8, (void **)&tmp);
     if (rc) return rc;
@@ -1118,6 +1122,128 @@ int crcnn_fc_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crc
 int crcnn_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int in_dim, int out_dim,
                      crcnn_tensor **out) {
     return crcnn_fc_forward_shard(ctx, in, w, b, batch, in_dim, out_dim, 0, out_dim, out);
+}
+
+// Two FullyConnectedLayers with nothing between them (fc3 -> fc4 of every reference topology, cnnBuilder.cpp:121-122, 132-133, 153-154):
+//     fc2(fc1(x)) = W2 (W1 x + Delta b1) + Delta b2 = (W2 W1) x + (W2 Delta b1 + Delta b2)          over Z_q[x]/(x^n+1),
+// so the pair is ONE weighted sum with the composed weights W = W2 W1 (out_dim x in_dim ring elements) and bias B = W2 Delta b1 +
+// Delta b2.  Both are computed once per network, on the device, by this engine's own weighted-sum kernels: column pairs (r, r+1) of
+// W1's NTT form play the two polynomials of a "ciphertext", fc2 applied to them yields the matching columns of W.  The composed
+// layer has out_dim x in_dim terms instead of mid_dim x (in_dim + out_dim) -- 50x fewer for PlainModel -- and produces the canonical residues
+// of the same ring elements, hence the reference's bytes.  The composed weights are general residues: limb-split GEMM only.
+static int compose_fc(crcnn_ctx *ctx, crcnn_plain *w1, crcnn_plain *b1, crcnn_plain *w2, crcnn_plain *b2, int in_dim, int mid_dim, int out_dim) {
+    const size_t pw = poly_words(ctx);
+    const int saved_tc = ctx->tc_mode;
+    const bool saved_prof = ctx->prof_on;
+    ctx->tc_mode = 0;           // NTT-domain kernels only: the "ciphertexts" below are NTT-form plaintexts
+    ctx->prof_on = false;       // build-time work is not part of any step's profile
+    crcnn_plain *zero = nullptr, *W = nullptr, *B = nullptr;
+    crcnn_tensor *T = nullptr, *O = nullptr;
+    uint64_t *dense = nullptr;
+    int rc = CRCNN_OK;
+    auto done = [&](int code) {
+        if (T) crcnn_tensor_free(ctx, T);
+        if (O) crcnn_tensor_free(ctx, O);
+        if (zero) crcnn_plain_free(ctx, zero);
+        dev_free(ctx, dense);
+        if (code) { if (W) crcnn_plain_free(ctx, W); if (B) crcnn_plain_free(ctx, B); }
+        ctx->tc_mode = saved_tc; ctx->prof_on = saved_prof;
+        return code;
+    };
+    rc = make_plain(ctx, std::vector<uint32_t>((size_t)out_dim + 1, 0), {}, {}, &zero);
+    if (rc) return done(rc);
+    rc = dev_alloc(ctx, (size_t)out_dim * in_dim * pw * 8, (void **)&dense);
+    if (rc) return done(rc);
+    // column pairs per pass: the staged columns of W1 (mid_dim pseudo-ciphertexts per pair) stay below ~8 GB
+    const int pairs_all = (in_dim + 1) / 2;
+    int Bc = (int)std::max<size_t>(1, std::min<size_t>((size_t)pairs_all, (8ull << 30) / ((size_t)mid_dim * 2 * pw * 8)));
+    if (const char *e = getenv("CRCNN_FC_COMPOSE_PAIRS")) Bc = std::max(1, std::min(Bc, atoi(e)));   // tests: several passes on small layers
+    std::vector<int> table((size_t)Bc * mid_dim);
+    for (int bi = 0; bi < Bc; bi++)
+        for (int o = 0; o < mid_dim; o++) table[(size_t)bi * mid_dim + o] = o * Bc + bi;
+    const int *d_index = nullptr;
+    rc = get_index_table(ctx, {5, Bc, mid_dim}, table, &d_index);
+    if (rc) return done(rc);
+    rc = new_tensor(ctx, (long)mid_dim * Bc, 2, 1, &T);
+    if (!rc) rc = new_tensor(ctx, (long)Bc * out_dim, 2, 1, &O);
+    if (rc) return done(rc);
+    CU(cudaMemsetAsync(T->d, 0, (size_t)T->count * 2 * pw * 8, ctx->stream));
+    for (int r0 = 0; r0 < in_dim && !rc; r0 += 2 * Bc) {
+        const int cols = std::min(2 * Bc, in_dim - r0);
+        for (int o = 0; o < mid_dim && !rc; o++)
+            rc = expand_range(ctx, w1, (long)o * in_dim + r0, cols, PF_NTT_MUL, T->d + (size_t)o * Bc * 2 * pw);
+        if (rc) break;
+        rc = run_weighted_sum(ctx, T, w2, zero, d_index, mid_dim, Bc, 1, out_dim, 0, out_dim, O);
+        if (rc) break;
+        // O[b][k] = (W[k][r0+2b], W[k][r0+2b+1])  ->  dense[k][r]
+        for (int bi = 0; 2 * bi < cols; bi++) {
+            const int polys = std::min(2, cols - 2 * bi);
+            cudaError_t e = cudaMemcpy2DAsync(dense + ((size_t)r0 + 2 * bi) * pw, (size_t)in_dim * pw * 8, O->d + (size_t)bi * out_dim * 2 * pw,
+                                              2 * pw * 8, (size_t)polys * pw * 8, out_dim, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) { rc = fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); break; }
+        }
+    }
+    if (rc) return done(rc);
+    W = new crcnn_plain();
+    W->count = (long)out_dim * in_dim; W->dense_only = true; W->sparse_shape = false; W->tc_state = -1; W->tap_state = -1;
+    W->ntt_mul = dense; dense = nullptr;
+    rc = ensure_tcn_weights(ctx, W, in_dim);      // byte planes of the composed weights; releases the dense form
+    if (rc) return done(rc);
+    // bias: fc2 applied to the Delta-scaled b1 (polynomial 0 of one pseudo-ciphertext per middle neuron), plus Delta b2
+    rc = ensure_form(ctx, b1, PF_NTT_ADD);
+    if (rc) return done(rc);
+    crcnn_tensor_free(ctx, T); T = nullptr;
+    crcnn_tensor_free(ctx, O); O = nullptr;
+    rc = new_tensor(ctx, mid_dim, 2, 1, &T);
+    if (!rc) rc = new_tensor(ctx, out_dim, 2, 1, &O);
+    if (rc) return done(rc);
+    CU(cudaMemsetAsync(T->d, 0, (size_t)mid_dim * 2 * pw * 8, ctx->stream));
+    CU(cudaMemcpy2DAsync(T->d, 2 * pw * 8, b1->ntt_add, pw * 8, pw * 8, mid_dim, cudaMemcpyDeviceToDevice, ctx->stream));
+    std::vector<int> ident(mid_dim);
+    for (int o = 0; o < mid_dim; o++) ident[o] = o;
+    rc = get_index_table(ctx, {2, 1, mid_dim}, ident, &d_index);
+    if (!rc) rc = run_weighted_sum(ctx, T, w2, b2, d_index, mid_dim, 1, 1, out_dim, 0, out_dim, O);
+    if (rc) return done(rc);
+    B = new crcnn_plain();
+    B->count = out_dim; B->dense_only = true; B->sparse_shape = false; B->tc_state = -1; B->tap_state = -1;
+    rc = dev_alloc(ctx, (size_t)out_dim * pw * 8, (void **)&B->ntt_add);
+    if (rc) return done(rc);
+    CU(cudaMemcpy2DAsync(B->ntt_add, pw * 8, O->d, 2 * pw * 8, pw * 8, out_dim, cudaMemcpyDeviceToDevice, ctx->stream));
+    w1->folded_w = W; w1->folded_b = B;
+    return done(CRCNN_OK);
+}
+
+int crcnn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w1, crcnn_plain *b1, crcnn_plain *w2, crcnn_plain *b2, int batch,
+                        int in_dim, int mid_dim, int out_dim, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && w1 && b1 && w2 && b2 && out, "null argument");
+    REQUIRE(batch > 0 && in_dim > 0 && mid_dim > 0 && out_dim > 0, "bad fully-connected geometry");
+    REQUIRE(in->size == 2 && in->count == (long)batch * in_dim, "input tensor does not match the layer geometry");
+    REQUIRE(w1->count == (long)mid_dim * in_dim && b1->count == mid_dim && w2->count == (long)out_dim * mid_dim && b2->count == out_dim,
+            "weight/bias count does not match the layer geometry");
+    CU(cudaSetDevice(ctx->device));
+    // worth it when the composed layer is the smaller one, and possible when its byte planes fit the weight cache
+    const bool composed = (double)out_dim * in_dim < (double)mid_dim * (in_dim + out_dim) && !w1->dense_only && !w2->dense_only &&
+                          ctx->tcn_mode && tcn_planes_for(ctx->hp.d) == 7 && in_dim <= TCN_MAX_R && mid_dim <= TCN_MAX_R &&
+                          tc_mac_available() == cudaSuccess && tcn_w_bytes(7, out_dim, tcn_kpad(in_dim), ctx->K, ctx->n) <= ctx->weight_cache_bytes &&
+                          !getenv("CRCNN_NO_FC_COMPOSE");
+    if (!composed) {
+        crcnn_tensor *mid = nullptr;
+        int rc = crcnn_fc_forward(ctx, in, w1, b1, batch, in_dim, mid_dim, &mid);
+        if (rc) return rc;
+        rc = crcnn_fc_forward(ctx, mid, w2, b2, batch, mid_dim, out_dim, out);
+        crcnn_tensor_free(ctx, mid);
+        return rc;
+    }
+    const long key[5] = {b1->serial, w2->serial, b2->serial, (long)mid_dim, (long)out_dim};
+    if (!w1->folded_w || memcmp(key, w1->folded_key, sizeof(key)) != 0) {
+        if (w1->folded_w) { crcnn_plain_free(ctx, w1->folded_w); w1->folded_w = nullptr; }
+        if (w1->folded_b) { crcnn_plain_free(ctx, w1->folded_b); w1->folded_b = nullptr; }
+        int rc = compose_fc(ctx, w1, b1, w2, b2, in_dim, mid_dim, out_dim);
+        if (rc) return rc;
+        memcpy(w1->folded_key, key, sizeof(key));
+    }
+    return crcnn_fc_forward(ctx, in, w1->folded_w, w1->folded_b, batch, in_dim, out_dim, out);
 }
 
 int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,

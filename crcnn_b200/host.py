@@ -38,6 +38,7 @@ def load():
     h.crcnn_host_resident_begin.argtypes = [_vp, _I]
     h.crcnn_host_resident_run.argtypes = [_I, _dp, _dp]
     h.crcnn_host_serve.argtypes = [_vp, _vp, _I, C.c_long, _dp]
+    h.crcnn_host_set_fusion.argtypes = [_I]
     h.crcnn_host_serve_times.argtypes = [_dp, _I]
     h.crcnn_host_serve_times.restype = _I
     _h = h
@@ -139,6 +140,10 @@ class HostNetwork:
         ms = C.c_double()
         self._chk(self.h.crcnn_host_serve(pinned_in_ptr, pinned_out_ptr, batch, requests, C.byref(ms)))
         return ms.value
+
+    def set_fusion(self, on):
+        """Layer fusion (conv+pool+bn on the pooled grid, pool+bn, fc+fc composed) on / off; off = one call per reference layer."""
+        self._chk(self.h.crcnn_host_set_fusion(int(bool(on))))
 
     def serve_times(self):
         """ms (host clock, from the start of the last serve()) at which each request's scores had landed."""

@@ -211,6 +211,15 @@ int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, i
 int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
                                int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
                                crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out);
+/* Two FullyConnectedLayer::forward calls in a row with no layer between them (fc3 -> fc4, the tail of every reference topology:
+ * CrCNN/src/cnnBuilder.cpp:121-122, 132-133, 153-154; fullyConnectedLayer.cpp:96-166), producing the second layer's output
+ * ciphertexts -- the same bytes as the two calls.  fc2(fc1(x)) = (W2 W1) x + (W2 Delta b1 + Delta b2) over Z_q[x]/(x^n+1): the composed
+ * weights (out_dim x in_dim ring elements, NTT form, staged as byte planes for the limb-split GEMM) and bias are computed on the device
+ * at the first call and kept in w1; every later call is ONE weighted sum with out_dim x in_dim terms instead of
+ * mid_dim x (in_dim + out_dim).  Falls back to the two calls when that is not smaller, when the composed planes do not fit the weight
+ * cache, or without the limb-split GEMM.  Environment CRCNN_NO_FC_COMPOSE=1 forces the two-call path (A/B timing, tests). */
+int crcnn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w1, crcnn_plain *b1, crcnn_plain *w2, crcnn_plain *b2, int batch,
+                        int in_dim, int mid_dim, int out_dim, crcnn_tensor **out);
 /* Replaces SquareLayer::forward (CrCNN/src/squareLayer.cpp:22-71): Evaluator::square + relinearize. */
 int crcnn_square_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_evk *evk, crcnn_tensor **out);
 

@@ -381,6 +381,56 @@ def test_conv_pool_bn_on_the_pooled_grid(env):
         assert np.array_equal(got_c.reshape(want_c.shape), want_c), geo
 
 
+def test_two_fc_layers_as_one_composed_layer(env):
+    """crcnn_fc_fc_forward == FullyConnectedLayer::forward twice (fullyConnectedLayer.cpp:96-166; fc3 -> fc4, cnnBuilder.cpp:121-122): the
+    composed weights W2 W1 and bias W2 Delta b1 + Delta b2 are built on the device; odd fan-in (a last column without a partner), several
+    build passes with a partial last one, batch > 1, and a shape where composing does not pay (falls back to the two layers)."""
+    n, primes, t, eng, orc, rng = env
+    cases = [  # in mid out batch  build pairs per pass  composed?
+        (21, 12, 3, 2, 4, True),
+        (16, 9, 2, 1, None, True),
+        (6, 4, 40, 1, None, False),      # 40 x 6 terms composed vs 4 x 46 layer by layer: not smaller
+    ]
+    for (in_dim, mid, out, batch, pairs, composed) in cases:
+        w1v, w1p = _layer_params(orc, rng, mid * in_dim)
+        b1v, b1p = _layer_params(orc, rng, mid)
+        w2v, w2p = _layer_params(orc, rng, out * mid)
+        b2v, b2p = _layer_params(orc, rng, out)
+        x = random_cts(rng, n, primes, batch * in_dim)
+        want = np.concatenate([orc.fc(orc.fc(x[b * in_dim:(b + 1) * in_dim], in_dim, mid, w1p, b1p).reshape(mid, *x.shape[1:]), mid, out, w2p, b2p).reshape(out, *x.shape[1:])
+                               for b in range(batch)])
+        packs = [eng.plain_encode(v) for v in (w1v, b1v, w2v, b2v)]
+
+        def run():
+            eng.prof_reset(); eng.prof_enable(True)
+            y = eng.download(eng.fc_fc(eng.upload(x), *packs, batch, in_dim, mid, out))
+            work = eng.prof_work()
+            eng.prof_enable(False)
+            return y, work
+        eng.set_tensor_core_mode(0)      # both paths count their work in the same kernel family
+        if pairs:
+            os.environ["CRCNN_FC_COMPOSE_PAIRS"] = str(pairs)
+        try:
+            got, _ = run()               # builds the composed layer
+            got2, work = run()           # steady state: the composed layer alone
+            os.environ["CRCNN_NO_FC_COMPOSE"] = "1"
+            got_l, work_l = run()
+        finally:
+            os.environ.pop("CRCNN_NO_FC_COMPOSE", None)
+            os.environ.pop("CRCNN_FC_COMPOSE_PAIRS", None)
+            eng.set_tensor_core_mode(1)
+        for y in (got, got2, got_l):
+            assert np.array_equal(y.reshape(want.shape), want), (in_dim, mid, out, batch)
+        macs = lambda wk: sum(v[1] for k, v in wk.items() if k.startswith("weighted_sum"))
+        assert (macs(work) < macs(work_l)) == composed, (work, work_l)
+        # NTT-form input, and the first layer on its own still gives its own output afterwards
+        tn = eng.upload(x)
+        eng.to_ntt(tn)
+        assert np.array_equal(eng.download(eng.fc_fc(tn, *packs, batch, in_dim, mid, out)).reshape(want.shape), want)
+        want1 = np.concatenate([orc.fc(x[b * in_dim:(b + 1) * in_dim], in_dim, mid, w1p, b1p).reshape(mid, *x.shape[1:]) for b in range(batch)])
+        assert np.array_equal(eng.download(eng.fc(eng.upload(x), packs[0], packs[1], batch, in_dim, mid)).reshape(want1.shape), want1)
+
+
 def test_layer_chain_stays_exact(env):
     """conv -> avgpool -> bn -> square -> fc without leaving the device (lazy NTT domain inside)."""
     n, primes, t, eng, orc, rng = env

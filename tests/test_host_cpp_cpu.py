@@ -45,7 +45,7 @@ def test_host_library_exports():
     h = host.load()
     for name in ("crcnn_host_init", "crcnn_host_set_evk", "crcnn_host_build", "crcnn_host_shape", "crcnn_host_layer_name",
                  "crcnn_host_forward_range", "crcnn_host_resident_begin", "crcnn_host_resident_run", "crcnn_host_resident_end",
-                 "crcnn_host_serve", "crcnn_host_serve_times", "crcnn_host_ctx", "crcnn_host_shutdown", "crcnn_host_last_error"):
+                 "crcnn_host_serve", "crcnn_host_serve_times", "crcnn_host_set_fusion", "crcnn_host_ctx", "crcnn_host_shutdown", "crcnn_host_last_error"):
         assert hasattr(h, name), name
     # without a network the calls fail with a message instead of crashing
     v = [ctypes.c_int() for _ in range(5)]
