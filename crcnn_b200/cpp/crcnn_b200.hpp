@@ -524,6 +524,8 @@ public:
         rt.check(crcnn_fc_fc_forward(rt.ctx(), in.t, w_.p, b_.p, next.w_.p, next.b_.p, in.batch, in_dim, out_dim, next.out_dim, &o));
         return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
     }
+    // avg-pool + batch-norm + this layer + the next one (crcnn_pool_bn_fc_fc_forward): layers 5-8 of the nine-layer networks
+    DeviceTensor forward_after_avgpool_bn_then(DeviceTensor in, class AvgPoolingLayer &pool, class BatchNormLayer &bn, FullyConnectedLayer &next);
     // Output rows [o0, o0+oc) only: this GPU's share of the reference's row split (fullyConnectedLayer.cpp:148-158)
     DeviceTensor forward_shard(const DeviceTensor &in, int o0, int oc) {
         Runtime &rt = Runtime::get();
@@ -653,6 +655,8 @@ public:
         mean.resize(num_channels); var.resize(num_channels);
         for (int i = 0; i < num_channels; i++) { mean[i] = m_.fetch(i); var[i] = v_.fetch(i); }
     }
+    crcnn_plain *mean_pack() { ensure_packs(); return m_.p; }
+    crcnn_plain *invstd_pack() { ensure_packs(); return v_.p; }
     void ensure_packs() {
         if (m_.p) return;
         std::vector<const Plaintext *> ms, vs;
@@ -711,6 +715,17 @@ inline DeviceTensor BatchNormLayer::forward_after_conv_avgpool(DeviceTensor in, 
     rt.check(crcnn_conv_pool_bn_forward(rt.ctx(), in.t, conv.weight_pack(), conv.bias_pack(), in.batch, conv.xd, conv.yd, conv.zd, conv.xs, conv.ys,
                                         conv.xf, conv.yf, conv.nf, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(), m_.p, v_.p, &o));
     return DeviceTensor(o, conv.nf, pool.xo, pool.yo, in.batch);
+}
+
+inline DeviceTensor FullyConnectedLayer::forward_after_avgpool_bn_then(DeviceTensor in, AvgPoolingLayer &pool, BatchNormLayer &bn, FullyConnectedLayer &next) {
+    Runtime &rt = Runtime::get();
+    ensure_packs(); next.ensure_packs();
+    if (next.in_dim != out_dim || bn.num_channels != in.zd || in.zd * pool.xo * pool.yo != in_dim)
+        throw std::invalid_argument("pooling / batch-norm / fully connected shapes do not chain");
+    crcnn_tensor *o = nullptr;
+    rt.check(crcnn_pool_bn_fc_fc_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(),
+                                         bn.mean_pack(), bn.invstd_pack(), w_.p, b_.p, next.w_.p, next.b_.p, out_dim, next.out_dim, &o));
+    return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -855,6 +870,19 @@ public:
                     x = bn->forward_after_conv_avgpool(std::move(x), *conv, *pool);
                     if (after_layer) { after_layer(i); after_layer(i + 1); after_layer(i + 2); }
                     i += 2;
+                    continue;
+                }
+            }
+            // AvgPoolingLayer + BatchNormLayer + two FullyConnectedLayers: window sums + one composed layer (same bytes; crcnn_pool_bn_fc_fc_forward)
+            if (fuse_fc_fc && fuse_pool_bn && i + 3 < last) {
+                auto *pool = dynamic_cast<AvgPoolingLayer *>(layers[i].get());
+                auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 1].get()) : nullptr;
+                auto *f1 = bn ? dynamic_cast<FullyConnectedLayer *>(layers[i + 2].get()) : nullptr;
+                auto *f2 = f1 ? dynamic_cast<FullyConnectedLayer *>(layers[i + 3].get()) : nullptr;
+                if (f2) {
+                    x = f1->forward_after_avgpool_bn_then(std::move(x), *pool, *bn, *f2);
+                    if (after_layer) for (int k = 0; k < 4; k++) after_layer(i + k);
+                    i += 3;
                     continue;
                 }
             }

@@ -76,7 +76,7 @@ struct crcnn_plain {
     // a convolution's weight pack keeps the packs of the pooled-grid path (crcnn_conv_pool_bn_forward): weights and bias with the pooling
     // scale and the batch-norm folded in, valid for the packs whose serials are in folded_key
     crcnn_plain *folded_w = nullptr, *folded_b = nullptr;
-    long folded_key[5] = {0, 0, 0, 0, 0};
+    long folded_key[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 struct crcnn_evk {
@@ -1131,7 +1131,10 @@ int crcnn_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_pla
 // W1's NTT form play the two polynomials of a "ciphertext", fc2 applied to them yields the matching columns of W.  The composed
 // layer has out_dim x in_dim terms instead of mid_dim x (in_dim + out_dim) -- 50x fewer for PlainModel -- and produces the canonical residues
 // of the same ring elements, hence the reference's bytes.  The composed weights are general residues: limb-split GEMM only.
-static int compose_fc(crcnn_ctx *ctx, crcnn_plain *w1, crcnn_plain *b1, crcnn_plain *w2, crcnn_plain *b2, int in_dim, int mid_dim, int out_dim) {
+// With C / D (per input channel, `per_channel` inputs each; ensure_pool_bn_consts) the layer in front of fc1 -- x = P (.) C_c - D_c, the pooling
+// scale and batch-norm applied to window sums P -- goes into the composed constants as well: W[k,r] (.)= C_c(r), B_k -= sum_r W[k,r] (.) D_c(r).
+static int compose_fc(crcnn_ctx *ctx, crcnn_plain *w1, crcnn_plain *b1, crcnn_plain *w2, crcnn_plain *b2, int in_dim, int mid_dim, int out_dim,
+                      const uint64_t *C = nullptr, const uint64_t *D = nullptr, int per_channel = 1) {
     const size_t pw = poly_words(ctx);
     const int saved_tc = ctx->tc_mode;
     const bool saved_prof = ctx->prof_on;
@@ -1187,8 +1190,6 @@ static int compose_fc(crcnn_ctx *ctx, crcnn_plain *w1, crcnn_plain *b1, crcnn_pl
     W = new crcnn_plain();
     W->count = (long)out_dim * in_dim; W->dense_only = true; W->sparse_shape = false; W->tc_state = -1; W->tap_state = -1;
     W->ntt_mul = dense; dense = nullptr;
-    rc = ensure_tcn_weights(ctx, W, in_dim);      // byte planes of the composed weights; releases the dense form
-    if (rc) return done(rc);
     // bias: fc2 applied to the Delta-scaled b1 (polynomial 0 of one pseudo-ciphertext per middle neuron), plus Delta b2
     rc = ensure_form(ctx, b1, PF_NTT_ADD);
     if (rc) return done(rc);
@@ -1209,6 +1210,9 @@ static int compose_fc(crcnn_ctx *ctx, crcnn_plain *w1, crcnn_plain *b1, crcnn_pl
     rc = dev_alloc(ctx, (size_t)out_dim * pw * 8, (void **)&B->ntt_add);
     if (rc) return done(rc);
     CU(cudaMemcpy2DAsync(B->ntt_add, pw * 8, O->d, 2 * pw * 8, pw * 8, out_dim, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (C) CU(launch_fold_fc_input_affine(ctx->dP, W->ntt_mul, out_dim, in_dim, (long)pw, per_channel, C, D, B->ntt_add, ctx->stream));
+    rc = ensure_tcn_weights(ctx, W, in_dim);      // byte planes of the composed weights; releases the dense form
+    if (rc) return done(rc);
     w1->folded_w = W; w1->folded_b = B;
     return done(CRCNN_OK);
 }
@@ -1235,7 +1239,7 @@ int crcnn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w1, crcnn
         crcnn_tensor_free(ctx, mid);
         return rc;
     }
-    const long key[5] = {b1->serial, w2->serial, b2->serial, (long)mid_dim, (long)out_dim};
+    const long key[9] = {b1->serial, w2->serial, b2->serial, (long)mid_dim, (long)out_dim, 0, 0, 0, 0};
     if (!w1->folded_w || memcmp(key, w1->folded_key, sizeof(key)) != 0) {
         if (w1->folded_w) { crcnn_plain_free(ctx, w1->folded_w); w1->folded_w = nullptr; }
         if (w1->folded_b) { crcnn_plain_free(ctx, w1->folded_b); w1->folded_b = nullptr; }
@@ -1244,6 +1248,55 @@ int crcnn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w1, crcnn
         memcpy(w1->folded_key, key, sizeof(key));
     }
     return crcnn_fc_forward(ctx, in, w1->folded_w, w1->folded_b, batch, in_dim, out_dim, out);
+}
+
+// AvgPoolingLayer -> BatchNormLayer -> FullyConnectedLayer -> FullyConnectedLayer (layers 5-8 of the reference's nine-layer networks,
+// cnnBuilder.cpp:118-122): the window sums of the input, then ONE composed fully connected layer that carries the pooling scale, the
+// batch-norm and both weight matrices (compose_fc with the per-channel constants).  Same bytes as the four calls.
+int crcnn_pool_bn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int pxs, int pys, int pxf, int pyf,
+                                crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_plain *w1, crcnn_plain *b1,
+                                crcnn_plain *w2, crcnn_plain *b2, int mid_dim, int out_dim, crcnn_tensor **out) {
+    if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(in && scale && mean && invstd && w1 && b1 && w2 && b2 && out, "null argument");
+    REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && pxs > 0 && pys > 0 && pxf > 0 && pyf > 0 && pxf <= xd && pyf <= yd, "bad pooling geometry");
+    REQUIRE(mid_dim > 0 && out_dim > 0, "bad fully-connected geometry");
+    const int pxo = (xd - pxf) / pxs + 1, pyo = (yd - pyf) / pys + 1, Rp = pxf * pyf;
+    const int in_dim = zd * pxo * pyo;
+    REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
+    REQUIRE(scale->count >= 1 && mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
+    REQUIRE(w1->count == (long)mid_dim * in_dim && b1->count == mid_dim && w2->count == (long)out_dim * mid_dim && b2->count == out_dim,
+            "weight/bias count does not match the layer geometry");
+    CU(cudaSetDevice(ctx->device));
+    const bool composed = pxs <= pxf && pys <= pyf && sum_fits_64(ctx, Rp) &&
+                          (double)out_dim * in_dim < (double)mid_dim * (in_dim + out_dim) && !w1->dense_only && !w2->dense_only &&
+                          ctx->tcn_mode && tcn_planes_for(ctx->hp.d) == 7 && in_dim <= TCN_MAX_R && mid_dim <= TCN_MAX_R &&
+                          tc_mac_available() == cudaSuccess && tcn_w_bytes(7, out_dim, tcn_kpad(in_dim), ctx->K, ctx->n) <= ctx->weight_cache_bytes &&
+                          !getenv("CRCNN_NO_FC_COMPOSE");
+    if (!composed) {
+        crcnn_tensor *mid = nullptr;
+        int rc = crcnn_pool_bn_forward(ctx, in, batch, xd, yd, zd, pxs, pys, pxf, pyf, scale, mean, invstd, &mid);
+        if (rc) return rc;
+        rc = crcnn_fc_fc_forward(ctx, mid, w1, b1, w2, b2, batch, in_dim, mid_dim, out_dim, out);
+        crcnn_tensor_free(ctx, mid);
+        return rc;
+    }
+    int rc = ensure_pool_bn_consts(ctx, scale, mean, invstd);
+    if (rc) return rc;
+    const long key[9] = {b1->serial, w2->serial, b2->serial, (long)mid_dim, (long)out_dim, scale->serial, mean->serial, invstd->serial, (long)(pxo * pyo)};
+    if (!w1->folded_w || memcmp(key, w1->folded_key, sizeof(key)) != 0) {
+        if (w1->folded_w) { crcnn_plain_free(ctx, w1->folded_w); w1->folded_w = nullptr; }
+        if (w1->folded_b) { crcnn_plain_free(ctx, w1->folded_b); w1->folded_b = nullptr; }
+        rc = compose_fc(ctx, w1, b1, w2, b2, in_dim, mid_dim, out_dim, invstd->fused_C, invstd->fused_D, pxo * pyo);
+        if (rc) return rc;
+        memcpy(w1->folded_key, key, sizeof(key));
+    }
+    // window sums (no scale), in the input's domain: the pooling layer's own index table
+    crcnn_tensor *sums = nullptr;
+    rc = crcnn_pool_forward(ctx, in, batch, xd, yd, zd, pxs, pys, pxf, pyf, nullptr, &sums);
+    if (rc) return rc;
+    rc = crcnn_fc_forward(ctx, sums, w1->folded_w, w1->folded_b, batch, in_dim, out_dim, out);
+    crcnn_tensor_free(ctx, sums);
+    return rc;
 }
 
 int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
@@ -1406,7 +1459,7 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
     }
     int rc = ensure_pool_bn_consts(ctx, scale, mean, invstd);
     if (rc) return rc;
-    const long key[5] = {b->serial, scale->serial, mean->serial, invstd->serial, (long)Rp};
+    const long key[9] = {b->serial, scale->serial, mean->serial, invstd->serial, (long)Rp, 0, 0, 0, 0};
     if (!w->folded_w || memcmp(key, w->folded_key, sizeof(key)) != 0) {
         if (w->folded_w) { crcnn_plain_free(ctx, w->folded_w); w->folded_w = nullptr; }
         if (w->folded_b) { crcnn_plain_free(ctx, w->folded_b); w->folded_b = nullptr; }

@@ -701,6 +701,34 @@ cudaError_t launch_fold_affine(const DeviceParams *P, uint64_t *data, long rows,
     return cudaGetLastError();
 }
 
+// Composed fully connected layer behind a per-channel affine map x = P (.) C_c - D_c (pooling scale + batch-norm, NTT domain):
+// Bias[k] -= sum_r W[k][r] (.) D[r / per_channel],  then  W[k][r] (.)= C[r / per_channel].  One thread per (k, residue slot).  Once per network.
+__global__ void __launch_bounds__(256)
+fold_fc_input_affine_kernel(const DeviceParams *__restrict__ P, uint64_t *__restrict__ W, int out_dim, int in_dim, int per_channel,
+                            const uint64_t *__restrict__ C, const uint64_t *__restrict__ D, uint64_t *__restrict__ Bias) {
+    const long pw = (long)P->K * P->n;
+    const long id = (long)blockIdx.x * 256 + threadIdx.x;
+    if (id >= (long)out_dim * pw) return;
+    const long k = id / pw, lw = id - k * pw;
+    const Mod mod = P->tab[lw / P->n].mod;
+    uint64_t acc = Bias[k * pw + lw];
+    for (int r = 0; r < in_dim; r++) {
+        const long cw = (long)(r / per_channel) * pw + lw;
+        uint64_t *wp = W + ((long)k * in_dim + r) * pw + lw;
+        const uint64_t w = *wp;
+        acc = submod(acc, mulmod(w, __ldg(D + cw), mod), mod.q);
+        *wp = mulmod(w, __ldg(C + cw), mod);
+    }
+    Bias[k * pw + lw] = acc;
+}
+
+cudaError_t launch_fold_fc_input_affine(const DeviceParams *P, uint64_t *W, int out_dim, int in_dim, long poly_words, int per_channel,
+                                        const uint64_t *C, const uint64_t *D, uint64_t *Bias, cudaStream_t stream) {
+    if (out_dim <= 0 || in_dim <= 0) return cudaSuccess;
+    fold_fc_input_affine_kernel<<<(unsigned)((out_dim * poly_words + 255) / 256), 256, 0, stream>>>(P, W, out_dim, in_dim, per_channel, C, D, Bias);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scale_small(const DeviceParams *P, uint64_t *data, long words, int times, cudaStream_t stream) {
     if (words <= 0) return cudaSuccess;
     scale_small_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream>>>(P, data, words, times);

@@ -73,6 +73,9 @@ cudaError_t launch_tapmul(const DeviceParams *P, int n, int K, const TapMulArgs 
 // data[row] = data[row] (.) C[row / group] - D[row / group] over rows of poly_words residues (D may be null)
 cudaError_t launch_fold_affine(const DeviceParams *P, uint64_t *data, long rows, long poly_words, int group, const uint64_t *C,
                                const uint64_t *D, cudaStream_t stream);
+// Bias[k] -= sum_r W[k][r] (.) D[r / per_channel]; W[k][r] (.)= C[r / per_channel]   (W: [out_dim][in_dim][poly_words], NTT form)
+cudaError_t launch_fold_fc_input_affine(const DeviceParams *P, uint64_t *W, int out_dim, int in_dim, long poly_words, int per_channel,
+                                        const uint64_t *C, const uint64_t *D, uint64_t *Bias, cudaStream_t stream);
 cudaError_t launch_scale_small(const DeviceParams *P, uint64_t *data, long words, int times, cudaStream_t stream);   // data *= times (mod q), times small
 cudaError_t launch_shoup_companion(const DeviceParams *P, const uint64_t *data, long words, uint64_t *out, cudaStream_t stream);
 

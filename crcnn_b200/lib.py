@@ -65,6 +65,7 @@ SYMBOLS = [
     ("crcnn_pool_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp, _vpp]),
     ("crcnn_bn_forward", _I, [_vp, _vp, _I, _I, _I, _I, _vp, _vp, _vpp]),
     ("crcnn_pool_bn_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp, _vp, _vp, _vpp]),
+    ("crcnn_pool_bn_fc_fc_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp] * 7 + [_I, _I, _vpp]),
     ("crcnn_fc_fc_forward", _I, [_vp, _vp, _vp, _vp, _vp, _vp, _I, _I, _I, _I, _vpp]),
     ("crcnn_conv_pool_bn_forward", _I, [_vp, _vp, _vp, _vp] + [_I] * 13 + [_vp, _vp, _vp, _vpp]),
     ("crcnn_square_forward", _I, [_vp, _vp, _vp, _vpp]),
@@ -366,6 +367,11 @@ class Engine:
         """Convolution + average pooling + batch-norm on the pooled grid (crcnn_conv_pool_bn_forward)."""
         return self._new(self.lib.crcnn_conv_pool_bn_forward, "tensor", x.ptr, w.ptr, b.ptr, batch, xd, yd, zd, xs, ys, xf, yf, nf,
                          pxs, pys, pxf, pyf, scale.ptr, mean.ptr, invstd.ptr)
+
+    def pool_bn_fc_fc(self, x, batch, xd, yd, zd, pxs, pys, pxf, pyf, scale, mean, invstd, w1, b1, w2, b2, mid_dim, out_dim):
+        """avg-pool + batch-norm + two fully connected layers as window sums + one composed layer (crcnn_pool_bn_fc_fc_forward)."""
+        return self._new(self.lib.crcnn_pool_bn_fc_fc_forward, "tensor", x.ptr, batch, xd, yd, zd, pxs, pys, pxf, pyf, scale.ptr, mean.ptr,
+                         invstd.ptr, w1.ptr, b1.ptr, w2.ptr, b2.ptr, mid_dim, out_dim)
 
     def fc_fc(self, x, w1, b1, w2, b2, batch, in_dim, mid_dim, out_dim):
         """Two fully connected layers in a row as one composed layer (crcnn_fc_fc_forward)."""

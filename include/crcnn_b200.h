@@ -220,6 +220,15 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
  * cache, or without the limb-split GEMM.  Environment CRCNN_NO_FC_COMPOSE=1 forces the two-call path (A/B timing, tests). */
 int crcnn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w1, crcnn_plain *b1, crcnn_plain *w2, crcnn_plain *b2, int batch,
                         int in_dim, int mid_dim, int out_dim, crcnn_tensor **out);
+/* AvgPoolingLayer, BatchNormLayer, FullyConnectedLayer, FullyConnectedLayer::forward in a row (layers 5-8 of the reference's
+ * nine-layer networks, CrCNN/src/cnnBuilder.cpp:118-122), producing the last layer's output ciphertexts -- the same bytes as the four
+ * calls: the pooling windows are summed, then ONE composed fully connected layer carries the pooling scale, the batch-norm and both
+ * weight matrices (crcnn_fc_fc_forward's composition with W[k,r] (.)= scale (.) invstd_c(r) and B_k -= sum_r W[k,r] (.) mean_c(r) (.) invstd_c(r)).
+ * (xd,yd,zd): input of the pooling layer; the first fully connected layer has zd * pooled positions inputs.  Falls back to
+ * crcnn_pool_bn_forward + crcnn_fc_fc_forward under the conditions stated there. */
+int crcnn_pool_bn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int pxs, int pys, int pxf, int pyf,
+                                crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_plain *w1, crcnn_plain *b1,
+                                crcnn_plain *w2, crcnn_plain *b2, int mid_dim, int out_dim, crcnn_tensor **out);
 /* Replaces SquareLayer::forward (CrCNN/src/squareLayer.cpp:22-71): Evaluator::square + relinearize. */
 int crcnn_square_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_evk *evk, crcnn_tensor **out);
 

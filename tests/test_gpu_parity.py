@@ -431,6 +431,60 @@ def test_two_fc_layers_as_one_composed_layer(env):
         assert np.array_equal(eng.download(eng.fc(eng.upload(x), packs[0], packs[1], batch, in_dim, mid)).reshape(want1.shape), want1)
 
 
+def test_pool_bn_fc_fc_as_window_sums_and_one_composed_layer(env):
+    """crcnn_pool_bn_fc_fc_forward == AvgPoolingLayer, BatchNormLayer, FullyConnectedLayer x2 ::forward in a row (cnnBuilder.cpp:118-122),
+    for coefficient-form (after a square layer) and NTT-form activations, batch > 1, 2x2 stride-1 and 3x3 stride-2 windows."""
+    n, primes, t, eng, orc, rng = env
+    for (xd, yd, zd, pxs, pys, pxf, pyf, mid, out, batch) in [(4, 4, 3, 1, 1, 2, 2, 8, 3, 2), (5, 7, 2, 2, 2, 3, 3, 5, 2, 1)]:
+        pxo, pyo = (xd - pxf) // pxs + 1, (yd - pyf) // pys + 1
+        in_dim = zd * pxo * pyo
+        mv, mp = _layer_params(orc, rng, zd)
+        vv = rng.uniform(-3, 3, size=zd).astype(np.float32)
+        vp = orc.encode_many(vv)
+        d, cc = orc.encode(1.0 / (pxf * pyf))
+        w1v, w1p = _layer_params(orc, rng, mid * in_dim)
+        b1v, b1p = _layer_params(orc, rng, mid)
+        w2v, w2p = _layer_params(orc, rng, out * mid)
+        b2v, b2p = _layer_params(orc, rng, out)
+        per = zd * xd * yd
+        x = random_cts(rng, n, primes, batch * per)
+        ct = x.shape[1:]
+
+        def ref_one(xi):
+            y = orc.bn(orc.pool(xi, xd, yd, zd, pxs, pys, pxf, pyf, d, cc), zd, pxo, pyo, mp, vp).reshape(in_dim, *ct)
+            return orc.fc(orc.fc(y, in_dim, mid, w1p, b1p).reshape(mid, *ct), mid, out, w2p, b2p).reshape(out, *ct)
+        want = np.concatenate([ref_one(x[b * per:(b + 1) * per]) for b in range(batch)])
+        packs = [eng.plain_encode_f64([1.0 / (pxf * pyf)]), eng.plain_encode(mv), eng.plain_encode(vv)] + [eng.plain_encode(v) for v in (w1v, b1v, w2v, b2v)]
+        geo = (batch, xd, yd, zd, pxs, pys, pxf, pyf)
+
+        def run(t_in):
+            eng.prof_reset(); eng.prof_enable(True)
+            y = eng.download(eng.pool_bn_fc_fc(t_in, *geo, *packs, mid, out))
+            work = eng.prof_work()
+            eng.prof_enable(False)
+            return y, work
+        eng.set_tensor_core_mode(0)
+        try:
+            got, _ = run(eng.upload(x))
+            got2, work = run(eng.upload(x))
+            tn = eng.upload(x)
+            eng.to_ntt(tn)
+            got_n, _ = run(tn)
+            os.environ["CRCNN_NO_FC_COMPOSE"] = "1"
+            got_l, work_l = run(eng.upload(x))
+        finally:
+            os.environ.pop("CRCNN_NO_FC_COMPOSE", None)
+            eng.set_tensor_core_mode(1)
+        for y in (got, got2, got_n, got_l):
+            assert np.array_equal(y.reshape(want.shape), want), geo
+        macs = lambda wk: sum(v[1] for k, v in wk.items() if k.startswith("weighted_sum"))
+        assert macs(work) < macs(work_l), (work, work_l)
+        # the composed layer with the affine map must not be mistaken for the plain composition of the same two layers (and back)
+        y_in = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, pxs, pys, pxf, pyf, d, cc), zd, pxo, pyo, mp, vp).reshape(in_dim, *ct) for b in range(batch)])
+        assert np.array_equal(eng.download(eng.fc_fc(eng.upload(y_in), *packs[3:], batch, in_dim, mid, out)).reshape(want.shape), want)
+        assert np.array_equal(eng.download(eng.pool_bn_fc_fc(eng.upload(x), *geo, *packs, mid, out)).reshape(want.shape), want)
+
+
 def test_layer_chain_stays_exact(env):
     """conv -> avgpool -> bn -> square -> fc without leaving the device (lazy NTT domain inside)."""
     n, primes, t, eng, orc, rng = env
