@@ -525,7 +525,7 @@ public:
         return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
     }
     // avg-pool + batch-norm + this layer + the next one (crcnn_pool_bn_fc_fc_forward): layers 5-8 of the nine-layer networks
-    DeviceTensor forward_after_avgpool_bn_then(DeviceTensor in, class AvgPoolingLayer &pool, class BatchNormLayer &bn, FullyConnectedLayer &next);
+    DeviceTensor forward_after_avgpool_bn_then(DeviceTensor in, class PoolingLayer &pool, class BatchNormLayer &bn, FullyConnectedLayer &next);
     // Output rows [o0, o0+oc) only: this GPU's share of the reference's row split (fullyConnectedLayer.cpp:148-158)
     DeviceTensor forward_shard(const DeviceTensor &in, int o0, int oc) {
         Runtime &rt = Runtime::get();
@@ -589,6 +589,7 @@ public:
     }
     void savePlaintextParameters(std::ostream *) override {}
     void loadPlaintextParameters(std::istream *) override {}
+    crcnn_plain *scale_or_null() { return scale(); }     // the 1/(xf*yf) pack of an AvgPoolingLayer, nullptr for a plain window sum
 protected:
     virtual crcnn_plain *scale() { return nullptr; }
 };
@@ -666,10 +667,10 @@ public:
     }
     // avg-pool + this batch-norm in one pass over NTT-form activations (crcnn_pool_bn_forward): what Network::forward_dev calls when an
     // AvgPoolingLayer is directly followed by a BatchNormLayer (layers 1+2 and 5+6 of the reference's nine-layer blocks, cnnBuilder.cpp:115-134)
-    DeviceTensor forward_after_avgpool(DeviceTensor in, class AvgPoolingLayer &pool);
+    DeviceTensor forward_after_avgpool(DeviceTensor in, PoolingLayer &pool);
     // convolution + avg-pool + this batch-norm (crcnn_conv_pool_bn_forward): layers 0-2 of those blocks; a stride-1 convolution is then
     // evaluated on the pooled grid (window sums of its input, convolution at the pooling stride) -- same bytes, a quarter of the columns
-    DeviceTensor forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, class AvgPoolingLayer &pool);
+    DeviceTensor forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, PoolingLayer &pool);
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
         ensure_packs();
@@ -697,33 +698,33 @@ private:
     int s0_ = -1, sc_ = -1;
 };
 
-inline DeviceTensor BatchNormLayer::forward_after_avgpool(DeviceTensor in, AvgPoolingLayer &pool) {
+inline DeviceTensor BatchNormLayer::forward_after_avgpool(DeviceTensor in, PoolingLayer &pool) {
     Runtime &rt = Runtime::get();
     ensure_packs();
     if (in.zd != num_channels) throw std::invalid_argument("channel count of the pooled tensor does not match the batch-norm layer");
     crcnn_tensor *o = nullptr;
-    rt.check(crcnn_pool_bn_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(), m_.p, v_.p, &o));
+    rt.check(crcnn_pool_bn_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_or_null(), m_.p, v_.p, &o));
     return DeviceTensor(o, in.zd, pool.xo, pool.yo, in.batch);
 }
 
-inline DeviceTensor BatchNormLayer::forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, AvgPoolingLayer &pool) {
+inline DeviceTensor BatchNormLayer::forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, PoolingLayer &pool) {
     Runtime &rt = Runtime::get();
     ensure_packs();
     if (conv.nf != num_channels || pool.xd != conv.xo || pool.yd != conv.yo)
         throw std::invalid_argument("convolution / pooling / batch-norm shapes do not chain");
     crcnn_tensor *o = nullptr;
     rt.check(crcnn_conv_pool_bn_forward(rt.ctx(), in.t, conv.weight_pack(), conv.bias_pack(), in.batch, conv.xd, conv.yd, conv.zd, conv.xs, conv.ys,
-                                        conv.xf, conv.yf, conv.nf, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(), m_.p, v_.p, &o));
+                                        conv.xf, conv.yf, conv.nf, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_or_null(), m_.p, v_.p, &o));
     return DeviceTensor(o, conv.nf, pool.xo, pool.yo, in.batch);
 }
 
-inline DeviceTensor FullyConnectedLayer::forward_after_avgpool_bn_then(DeviceTensor in, AvgPoolingLayer &pool, BatchNormLayer &bn, FullyConnectedLayer &next) {
+inline DeviceTensor FullyConnectedLayer::forward_after_avgpool_bn_then(DeviceTensor in, PoolingLayer &pool, BatchNormLayer &bn, FullyConnectedLayer &next) {
     Runtime &rt = Runtime::get();
     ensure_packs(); next.ensure_packs();
     if (next.in_dim != out_dim || bn.num_channels != in.zd || in.zd * pool.xo * pool.yo != in_dim)
         throw std::invalid_argument("pooling / batch-norm / fully connected shapes do not chain");
     crcnn_tensor *o = nullptr;
-    rt.check(crcnn_pool_bn_fc_fc_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_pack(),
+    rt.check(crcnn_pool_bn_fc_fc_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_or_null(),
                                          bn.mean_pack(), bn.invstd_pack(), w_.p, b_.p, next.w_.p, next.b_.p, out_dim, next.out_dim, &o));
     return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
 }
@@ -864,7 +865,7 @@ public:
             // ConvolutionalLayer + AvgPoolingLayer + BatchNormLayer: the convolution on the pooled grid (same bytes; crcnn_conv_pool_bn_forward)
             if (fuse_conv_pool_bn && i + 2 < last) {
                 auto *conv = dynamic_cast<ConvolutionalLayer *>(layers[i].get());
-                auto *pool = conv ? dynamic_cast<AvgPoolingLayer *>(layers[i + 1].get()) : nullptr;
+                auto *pool = conv ? dynamic_cast<PoolingLayer *>(layers[i + 1].get()) : nullptr;
                 auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 2].get()) : nullptr;
                 if (bn) {
                     x = bn->forward_after_conv_avgpool(std::move(x), *conv, *pool);
@@ -875,7 +876,7 @@ public:
             }
             // AvgPoolingLayer + BatchNormLayer + two FullyConnectedLayers: window sums + one composed layer (same bytes; crcnn_pool_bn_fc_fc_forward)
             if (fuse_fc_fc && fuse_pool_bn && i + 3 < last) {
-                auto *pool = dynamic_cast<AvgPoolingLayer *>(layers[i].get());
+                auto *pool = dynamic_cast<PoolingLayer *>(layers[i].get());
                 auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 1].get()) : nullptr;
                 auto *f1 = bn ? dynamic_cast<FullyConnectedLayer *>(layers[i + 2].get()) : nullptr;
                 auto *f2 = f1 ? dynamic_cast<FullyConnectedLayer *>(layers[i + 3].get()) : nullptr;
@@ -899,7 +900,7 @@ public:
             }
             // AvgPoolingLayer directly followed by BatchNormLayer: one pass instead of two (same bytes; crcnn_pool_bn_forward)
             if (fuse_pool_bn && i + 1 < last) {
-                auto *pool = dynamic_cast<AvgPoolingLayer *>(layers[i].get());
+                auto *pool = dynamic_cast<PoolingLayer *>(layers[i].get());
                 auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 1].get()) : nullptr;
                 if (bn) {
                     x = bn->forward_after_avgpool(std::move(x), *pool);

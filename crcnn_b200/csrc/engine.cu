@@ -318,11 +318,13 @@ int ensure_shoup(crcnn_ctx *ctx, crcnn_plain *p) {
 // Per-channel constants of "pooling scale, then batch-norm" in NTT form, kept in the batch-norm factor pack:
 // C[z] = scale (.) invstd[z] (with Shoup companions), D[z] = mean[z] (.) invstd[z];  x -> x (.) C[z] - D[z] (D on polynomial 0 only).
 int ensure_pool_bn_consts(crcnn_ctx *ctx, crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd) {
-    int rc = ensure_form(ctx, scale, PF_NTT_MUL);
+    // scale == nullptr: sum pooling (PoolingLayer, the WoPad topology) -- C[z] = invstd[z]
+    int rc = scale ? ensure_form(ctx, scale, PF_NTT_MUL) : CRCNN_OK;
     if (!rc) rc = ensure_form(ctx, mean, PF_NTT_ADD);
     if (!rc) rc = ensure_form(ctx, invstd, PF_NTT_MUL);
     if (rc) return rc;
-    if (invstd->fused_C && invstd->fused_scale == scale->serial && invstd->fused_mean == mean->serial) return CRCNN_OK;
+    const long scale_id = scale ? scale->serial : -1;
+    if (invstd->fused_C && invstd->fused_scale == scale_id && invstd->fused_mean == mean->serial) return CRCNN_OK;
     const size_t words = (size_t)invstd->count * poly_words(ctx);
     dev_free(ctx, invstd->fused_C); dev_free(ctx, invstd->fused_Csh); dev_free(ctx, invstd->fused_D);
     invstd->fused_C = invstd->fused_Csh = invstd->fused_D = nullptr;
@@ -330,9 +332,9 @@ int ensure_pool_bn_consts(crcnn_ctx *ctx, crcnn_plain *scale, crcnn_plain *mean,
     if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_Csh);
     if (!rc) rc = dev_alloc(ctx, words * 8, (void **)&invstd->fused_D);
     if (rc) return rc;
-    CU(launch_pool_bn_consts(ctx->dP, scale->ntt_mul, invstd->ntt_mul, mean->ntt_add, (long)words, invstd->fused_C, invstd->fused_D, ctx->stream));
+    CU(launch_pool_bn_consts(ctx->dP, scale ? scale->ntt_mul : nullptr, invstd->ntt_mul, mean->ntt_add, (long)words, invstd->fused_C, invstd->fused_D, ctx->stream));
     CU(launch_shoup_companion(ctx->dP, invstd->fused_C, (long)words, invstd->fused_Csh, ctx->stream));
-    invstd->fused_scale = scale->serial; invstd->fused_mean = mean->serial;
+    invstd->fused_scale = scale_id; invstd->fused_mean = mean->serial;
     return CRCNN_OK;
 }
 
@@ -1257,13 +1259,13 @@ int crcnn_pool_bn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int
                                 crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_plain *w1, crcnn_plain *b1,
                                 crcnn_plain *w2, crcnn_plain *b2, int mid_dim, int out_dim, crcnn_tensor **out) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
-    REQUIRE(in && scale && mean && invstd && w1 && b1 && w2 && b2 && out, "null argument");
+    REQUIRE(in && mean && invstd && w1 && b1 && w2 && b2 && out, "null argument");      // scale == NULL: PoolingLayer
     REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && pxs > 0 && pys > 0 && pxf > 0 && pyf > 0 && pxf <= xd && pyf <= yd, "bad pooling geometry");
     REQUIRE(mid_dim > 0 && out_dim > 0, "bad fully-connected geometry");
     const int pxo = (xd - pxf) / pxs + 1, pyo = (yd - pyf) / pys + 1, Rp = pxf * pyf;
     const int in_dim = zd * pxo * pyo;
     REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
-    REQUIRE(scale->count >= 1 && mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
+    REQUIRE((!scale || scale->count >= 1) && mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
     REQUIRE(w1->count == (long)mid_dim * in_dim && b1->count == mid_dim && w2->count == (long)out_dim * mid_dim && b2->count == out_dim,
             "weight/bias count does not match the layer geometry");
     CU(cudaSetDevice(ctx->device));
@@ -1282,7 +1284,7 @@ int crcnn_pool_bn_fc_fc_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int
     }
     int rc = ensure_pool_bn_consts(ctx, scale, mean, invstd);
     if (rc) return rc;
-    const long key[9] = {b1->serial, w2->serial, b2->serial, (long)mid_dim, (long)out_dim, scale->serial, mean->serial, invstd->serial, (long)(pxo * pyo)};
+    const long key[9] = {b1->serial, w2->serial, b2->serial, (long)mid_dim, (long)out_dim, scale ? scale->serial : -1, mean->serial, invstd->serial, (long)(pxo * pyo)};
     if (!w1->folded_w || memcmp(key, w1->folded_key, sizeof(key)) != 0) {
         if (w1->folded_w) { crcnn_plain_free(ctx, w1->folded_w); w1->folded_w = nullptr; }
         if (w1->folded_b) { crcnn_plain_free(ctx, w1->folded_b); w1->folded_b = nullptr; }
@@ -1369,8 +1371,8 @@ int crcnn_pool_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int 
 int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
                           crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
-    REQUIRE(in && scale && mean && invstd && out, "null argument");
-    REQUIRE(scale->count >= 1 && mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
+    REQUIRE(in && mean && invstd && out, "null argument");      // scale == NULL: PoolingLayer (window sum without a factor)
+    REQUIRE((!scale || scale->count >= 1) && mean->count == zd && invstd->count == zd, "mean/var count does not match the channel count");
     const int xo = (xd - xf) / xs + 1, yo = (yd - yf) / ys + 1;
     const int R = xf * yf;
     if (!in->ntt || !sum_fits_64(ctx, R)) {      // not the fused kernel's case: the two layers one after the other
@@ -1433,7 +1435,7 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
                                int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
                                crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
-    REQUIRE(in && w && b && scale && mean && invstd && out, "null argument");
+    REQUIRE(in && w && b && mean && invstd && out, "null argument");      // scale == NULL: PoolingLayer (window sum without a factor)
     REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && nf > 0 && xf <= xd && yf <= yd,
             "bad convolution geometry");
     const int cxo = (xd - xf) / xs + 1, cyo = (yd - yf) / ys + 1;          // convolution output (convolutionalLayer.cpp:24)
@@ -1442,7 +1444,7 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
     const int Rp = pxf * pyf, R = zd * xf * yf;
     REQUIRE(in->size == 2 && in->count == (long)batch * zd * xd * yd, "input tensor does not match the layer geometry");
     REQUIRE(w->count == (long)nf * R && b->count == nf, "kernel/bias count does not match the layer geometry");
-    REQUIRE(scale->count >= 1 && mean->count == nf && invstd->count == nf, "mean/var count does not match the channel count");
+    REQUIRE((!scale || scale->count >= 1) && mean->count == nf && invstd->count == nf, "mean/var count does not match the channel count");
     CU(cudaSetDevice(ctx->device));
     // the pooled grid needs: strides that leave no output the reference skips (computeBoundaries), window sums below 2^64, and the
     // limb-split weighted sum (any NTT-form weights) with the folded weight planes resident
@@ -1459,7 +1461,7 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
     }
     int rc = ensure_pool_bn_consts(ctx, scale, mean, invstd);
     if (rc) return rc;
-    const long key[9] = {b->serial, scale->serial, mean->serial, invstd->serial, (long)Rp, 0, 0, 0, 0};
+    const long key[9] = {b->serial, scale ? scale->serial : -1, mean->serial, invstd->serial, (long)Rp, 0, 0, 0, 0};
     if (!w->folded_w || memcmp(key, w->folded_key, sizeof(key)) != 0) {
         if (w->folded_w) { crcnn_plain_free(ctx, w->folded_w); w->folded_w = nullptr; }
         if (w->folded_b) { crcnn_plain_free(ctx, w->folded_b); w->folded_b = nullptr; }

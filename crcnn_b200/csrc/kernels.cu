@@ -1049,7 +1049,7 @@ pool_bn_consts_kernel(const DeviceParams *__restrict__ P, const uint64_t *__rest
     const long pw = (long)P->K * P->n, lw = w % pw;
     const Mod mod = P->tab[lw / P->n].mod;
     const uint64_t v = __ldg(V + w);
-    C[w] = mulmod(__ldg(S + lw), v, mod);
+    C[w] = S ? mulmod(__ldg(S + lw), v, mod) : v;      // no pooling factor (sum pooling): C = V
     D[w] = mulmod(__ldg(M + w), v, mod);
 }
 cudaError_t launch_pool_bn_consts(const DeviceParams *P, const uint64_t *S, const uint64_t *V, const uint64_t *M, long words,

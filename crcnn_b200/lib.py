@@ -366,11 +366,11 @@ class Engine:
     def conv_pool_bn(self, x, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf, scale, mean, invstd):
         """Convolution + average pooling + batch-norm on the pooled grid (crcnn_conv_pool_bn_forward)."""
         return self._new(self.lib.crcnn_conv_pool_bn_forward, "tensor", x.ptr, w.ptr, b.ptr, batch, xd, yd, zd, xs, ys, xf, yf, nf,
-                         pxs, pys, pxf, pyf, scale.ptr, mean.ptr, invstd.ptr)
+                         pxs, pys, pxf, pyf, scale.ptr if scale is not None else None, mean.ptr, invstd.ptr)
 
     def pool_bn_fc_fc(self, x, batch, xd, yd, zd, pxs, pys, pxf, pyf, scale, mean, invstd, w1, b1, w2, b2, mid_dim, out_dim):
         """avg-pool + batch-norm + two fully connected layers as window sums + one composed layer (crcnn_pool_bn_fc_fc_forward)."""
-        return self._new(self.lib.crcnn_pool_bn_fc_fc_forward, "tensor", x.ptr, batch, xd, yd, zd, pxs, pys, pxf, pyf, scale.ptr, mean.ptr,
+        return self._new(self.lib.crcnn_pool_bn_fc_fc_forward, "tensor", x.ptr, batch, xd, yd, zd, pxs, pys, pxf, pyf, scale.ptr if scale is not None else None, mean.ptr,
                          invstd.ptr, w1.ptr, b1.ptr, w2.ptr, b2.ptr, mid_dim, out_dim)
 
     def fc_fc(self, x, w1, b1, w2, b2, batch, in_dim, mid_dim, out_dim):
@@ -385,7 +385,7 @@ class Engine:
 
     def pool_bn(self, x, batch, xd, yd, zd, xs, ys, xf, yf, scale, mean, invstd):
         """Average pooling + batch-norm in one pass (crcnn_pool_bn_forward)."""
-        return self._new(self.lib.crcnn_pool_bn_forward, "tensor", x.ptr, batch, xd, yd, zd, xs, ys, xf, yf, scale.ptr, mean.ptr, invstd.ptr)
+        return self._new(self.lib.crcnn_pool_bn_forward, "tensor", x.ptr, batch, xd, yd, zd, xs, ys, xf, yf, scale.ptr if scale is not None else None, mean.ptr, invstd.ptr)
 
     def square_layer(self, x, evk):
         return self._new(self.lib.crcnn_square_forward, "tensor", x.ptr, evk.ptr)

@@ -194,7 +194,9 @@ int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd
 /* AvgPoolingLayer::forward immediately followed by BatchNormLayer::forward (CrCNN/src/avgPoolingLayer.cpp:16-45,
  * batchNormLayer.cpp:29-40 -- layers 1+2 and 5+6 of the reference's nine-layer networks, cnnBuilder.cpp:115-134) in one pass over
  * NTT-form activations: out = (window sum) * (scale (.) invstd_z) - mean_z (.) invstd_z, the same canonical residues as the two
- * calls.  Coefficient-form activations run the two layers one after the other.  The result has the batch-norm layer's shape. */
+ * calls.  Coefficient-form activations run the two layers one after the other.  The result has the batch-norm layer's shape.
+ * scale = NULL: PoolingLayer (window sum without a factor, poolingLayer.cpp:23-47 -- the WoPad topology) in place of AvgPoolingLayer;
+ * the same holds for crcnn_conv_pool_bn_forward and crcnn_pool_bn_fc_fc_forward. */
 int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, int yd, int zd, int xs, int ys, int xf, int yf,
                           crcnn_plain *scale, crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out);
 /* ConvolutionalLayer::forward, AvgPoolingLayer::forward and BatchNormLayer::forward in a row (layers 0-2 of the reference's

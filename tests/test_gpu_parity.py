@@ -316,6 +316,13 @@ def test_pool_bn_fused(env):
         want2 = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, d, cc), zd, xo, yo, mp2, vp) for b in range(batch)])
         got2 = eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, packs[0], eng.plain_encode(mv2), packs[2]))
         assert np.array_equal(got2.reshape(want2.shape), want2)
+        # PoolingLayer (window sum, no factor -- the WoPad topology, cnnBuilder.cpp:136-155) followed by the batch-norm
+        want3 = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf), zd, xo, yo, mp, vp) for b in range(batch)])
+        got3 = eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, None, packs[1], packs[2]))
+        assert np.array_equal(got3.reshape(want3.shape), want3)
+        got3c = eng.download(eng.pool_bn(eng.upload(x), batch, xd, yd, zd, xs, ys, xf, yf, None, packs[1], packs[2]))
+        assert np.array_equal(got3c.reshape(want3.shape), want3)
+        assert np.array_equal(eng.download(eng.pool_bn(tn, batch, xd, yd, zd, xs, ys, xf, yf, *packs)).reshape(want.shape), want)   # and back to the scaled constants
 
 
 def test_conv_pool_bn_on_the_pooled_grid(env):
@@ -375,6 +382,13 @@ def test_conv_pool_bn_on_the_pooled_grid(env):
         eng.to_ntt(tn)      # NTT-form input
         got_n = eng.download(eng.conv_pool_bn(tn, w, bias, *geo, *packs))
         assert np.array_equal(got_n.reshape(want.shape), want), geo
+        # sum pooling (no factor) in the middle: same path, C = invstd
+        want_s = np.concatenate([
+            orc.bn(orc.pool(orc.conv(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, nf, wp, bp).reshape(nf * cxo * cyo, *x.shape[1:]),
+                            cxo, cyo, nf, pxs, pys, pxf, pyf), nf, pxo, pyo, mp, vp) for b in range(batch)])
+        got_s = eng.download(eng.conv_pool_bn(eng.upload(x), w, bias, *geo, None, packs[1], packs[2]))
+        assert np.array_equal(got_s.reshape(want_s.shape), want_s), geo
+        assert np.array_equal(eng.download(eng.conv_pool_bn(eng.upload(x), w, bias, *geo, *packs)).reshape(want.shape), want), geo
         # the bias pack still adds ONE bias in a plain convolution afterwards (the repeated form lives in a derived pack)
         want_c = np.concatenate([orc.conv(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, nf, wp, bp).reshape(nf * cxo * cyo, *x.shape[1:]) for b in range(batch)])
         got_c = eng.download(eng.conv(eng.upload(x), w, bias, batch, xd, yd, zd, xs, ys, xf, yf, nf))
@@ -479,6 +493,12 @@ def test_pool_bn_fc_fc_as_window_sums_and_one_composed_layer(env):
             assert np.array_equal(y.reshape(want.shape), want), geo
         macs = lambda wk: sum(v[1] for k, v in wk.items() if k.startswith("weighted_sum"))
         assert macs(work) < macs(work_l), (work, work_l)
+        def ref_sum(xi):
+            y = orc.bn(orc.pool(xi, xd, yd, zd, pxs, pys, pxf, pyf), zd, pxo, pyo, mp, vp).reshape(in_dim, *ct)
+            return orc.fc(orc.fc(y, in_dim, mid, w1p, b1p).reshape(mid, *ct), mid, out, w2p, b2p).reshape(out, *ct)
+        want_s = np.concatenate([ref_sum(x[b * per:(b + 1) * per]) for b in range(batch)])
+        got_s = eng.download(eng.pool_bn_fc_fc(eng.upload(x), *geo, None, *packs[1:], mid, out))
+        assert np.array_equal(got_s.reshape(want_s.shape), want_s), geo
         # the composed layer with the affine map must not be mistaken for the plain composition of the same two layers (and back)
         y_in = np.concatenate([orc.bn(orc.pool(x[b * per:(b + 1) * per], xd, yd, zd, pxs, pys, pxf, pyf, d, cc), zd, pxo, pyo, mp, vp).reshape(in_dim, *ct) for b in range(batch)])
         assert np.array_equal(eng.download(eng.fc_fc(eng.upload(y_in), *packs[3:], batch, in_dim, mid, out)).reshape(want.shape), want)

@@ -27,8 +27,30 @@ def main():
     ap.add_argument("--model", default=bench.MODEL)
     ap.add_argument("--first", type=int, default=0)
     ap.add_argument("--last", type=int, default=None)
+    ap.add_argument("--path", default="host", choices=("host", "layers"),
+                    help="host: the C++17 host path bench.py times (crcnn_b200::Network::forward_dev with its layer fusion); "
+                         "layers: one C-ABI call per reference layer (crcnn_b200/nets.py), any sub-range with --first/--last")
     args = ap.parse_args()
     n, primes, t = bench.N_POLY, bench.PRIMES, bench.T_PLAIN
+    if args.path == "host" and args.first == 0 and args.last is None:
+        from crcnn_b200 import host
+        rng = np.random.default_rng(5)
+        evk = bench.synth_evk(rng, primes, n)
+        net = host.HostNetwork(n, primes, t, args.model, device=0, evk=evk)
+        per_image = net.zd * net.xd * net.yd
+        K = len(primes)
+        pin, own = host.pinned_array(args.batch * per_image * 2 * K * (n + 1))
+        bench.synth_residues(rng, (args.batch * per_image, 2), primes, n, out=pin.reshape(args.batch * per_image, 2, K, n + 1))
+        net.resident_begin(own.ptr, args.batch)
+        net.resident_run(2)
+        cuda = ctypes.CDLL("libcuda.so.1")
+        cuda.cuProfilerStart()
+        net.resident_run(1)
+        cuda.cuProfilerStop()
+        net.resident_end()
+        print("profiled one forward of the C++ host path, batch %d" % args.batch)
+        net.close()
+        return
     eng = Engine(n, primes, t, device=0)
     rng = np.random.default_rng(5)
     evk_words, sizes, dbc = bench.synth_evk(rng, primes, n)
