@@ -671,6 +671,9 @@ public:
     // convolution + avg-pool + this batch-norm (crcnn_conv_pool_bn_forward): layers 0-2 of those blocks; a stride-1 convolution is then
     // evaluated on the pooled grid (window sums of its input, convolution at the pooling stride) -- same bytes, a quarter of the columns
     DeviceTensor forward_after_conv_avgpool(DeviceTensor in, ConvolutionalLayer &conv, PoolingLayer &pool);
+    // output channels [k0, k0+kc) of the same (ShardedNetwork); returns false -- and leaves `in` alone -- where the engine has no pooled-grid
+    // path for this geometry (the caller then runs the three layers one by one on its shard)
+    bool forward_after_conv_avgpool_shard(const DeviceTensor &in, ConvolutionalLayer &conv, PoolingLayer &pool, int k0, int kc, DeviceTensor *out);
     DeviceTensor forward_dev(DeviceTensor in) override {
         Runtime &rt = Runtime::get();
         ensure_packs();
@@ -727,6 +730,22 @@ inline DeviceTensor FullyConnectedLayer::forward_after_avgpool_bn_then(DeviceTen
     rt.check(crcnn_pool_bn_fc_fc_forward(rt.ctx(), in.t, in.batch, pool.xd, pool.yd, in.zd, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_or_null(),
                                          bn.mean_pack(), bn.invstd_pack(), w_.p, b_.p, next.w_.p, next.b_.p, out_dim, next.out_dim, &o));
     return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
+}
+
+inline bool BatchNormLayer::forward_after_conv_avgpool_shard(const DeviceTensor &in, ConvolutionalLayer &conv, PoolingLayer &pool, int k0, int kc,
+                                                             DeviceTensor *out) {
+    Runtime &rt = Runtime::get();
+    ensure_packs();
+    if (conv.nf != num_channels || pool.xd != conv.xo || pool.yd != conv.yo)
+        throw std::invalid_argument("convolution / pooling / batch-norm shapes do not chain");
+    crcnn_tensor *o = nullptr;
+    const int rc = crcnn_conv_pool_bn_forward_shard(rt.ctx(), in.t, conv.weight_pack(), conv.bias_pack(), in.batch, conv.xd, conv.yd, conv.zd, conv.xs,
+                                                    conv.ys, conv.xf, conv.yf, conv.nf, pool.xs, pool.ys, pool.xf, pool.yf, pool.scale_or_null(), m_.p,
+                                                    v_.p, k0, kc, &o);
+    if (rc == CRCNN_ERR_UNSUPPORTED) return false;
+    rt.check(rc);
+    *out = DeviceTensor(o, kc, pool.xo, pool.yo, in.batch);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1073,10 +1092,33 @@ public:
             if (auto *c = dynamic_cast<ConvolutionalLayer *>(l)) {
                 if (sharded) x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);
                 int k0, kc; shard_range(c->nf, world_, rank_, &k0, &kc);
+                // conv + pool + batch-norm: this rank's channels of the composed layer (§4.5 of DESIGN.md), when the engine has it for the geometry
+                if (fuse_conv_pool_bn && i + 2 < last) {
+                    auto *pool = dynamic_cast<PoolingLayer *>(layers[i + 1].get());
+                    auto *bn = pool ? dynamic_cast<BatchNormLayer *>(layers[i + 2].get()) : nullptr;
+                    DeviceTensor y;
+                    if (bn && bn->forward_after_conv_avgpool_shard(x, *c, *pool, k0, kc, &y)) {
+                        x = std::move(y);
+                        channels = c->nf; sharded = true; rows = false;
+                        if (after_layer) { after_layer(i); after_layer(i + 1); after_layer(i + 2); }
+                        i += 2;
+                        continue;
+                    }
+                }
                 x = c->forward_shard(x, k0, kc);
                 channels = c->nf; sharded = true; rows = false;
             } else if (auto *f = dynamic_cast<FullyConnectedLayer *>(l)) {
                 if (sharded) x = all_gather(x, channels, x.xd * x.yd, x.xd, x.yd);
+                // fc -> fc whose composed layer has only a handful of rows (fc3 * fc4: 10): every rank evaluates the composed layer on the gathered
+                // input -- no split of fc3's rows, no second exchange
+                auto *f2 = (fuse_fc_fc && i + 1 < last) ? dynamic_cast<FullyConnectedLayer *>(layers[i + 1].get()) : nullptr;
+                if (f2 && f2->out_dim < min_sharded_outputs && (double)f2->out_dim * f->in_dim < (double)f->out_dim * (f->in_dim + f2->out_dim)) {
+                    x = f->forward_then(std::move(x), *f2);
+                    channels = 1; sharded = false; rows = false;
+                    if (after_layer) { after_layer(i); after_layer(i + 1); }
+                    i++;
+                    continue;
+                }
                 if (f->out_dim < min_sharded_outputs) {
                     // a handful of output rows (fc4: 10): the layer's cost is transforming and staging its INPUT, which every rank has in
                     // full after the gather -- splitting the rows saves nothing and costs another exchange; every rank computes them all

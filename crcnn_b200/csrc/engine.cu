@@ -1431,10 +1431,11 @@ int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, i
 //     W'[k,r] = W[k,r] (.) C_k,      B'_k = |window| * B_k (.) C_k - D_k        (NTT domain, computed once per network).
 // One weighted sum with (pooled positions / convolution positions) of the columns replaces three layers and two full-size
 // intermediates; the residues are the canonical ones of the same ring elements, hence the reference's bytes.
-int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
-                               int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
-                               crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out) {
+int crcnn_conv_pool_bn_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
+                                     int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
+                                     crcnn_plain *mean, crcnn_plain *invstd, int k0, int kc, crcnn_tensor **out) {
     if (!ctx) return CRCNN_ERR_INVALID_ARGUMENT;
+    REQUIRE(k0 >= 0 && kc >= 0 && k0 + kc <= nf, "bad output-channel shard");
     REQUIRE(in && w && b && mean && invstd && out, "null argument");      // scale == NULL: PoolingLayer (window sum without a factor)
     REQUIRE(batch > 0 && xd > 0 && yd > 0 && zd > 0 && xs > 0 && ys > 0 && xf > 0 && yf > 0 && nf > 0 && xf <= xd && yf <= yd,
             "bad convolution geometry");
@@ -1452,6 +1453,8 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
                              ctx->tcn_mode && tcn_planes_for(ctx->hp.d) == 7 && R <= TCN_MAX_R && tc_mac_available() == cudaSuccess &&
                              tcn_w_bytes(7, nf, tcn_kpad(R), ctx->K, ctx->n) <= ctx->weight_cache_bytes && !getenv("CRCNN_NO_POOLED_CONV");
     if (!pooled_grid) {   // the three layers one after the other (the last two in one pass when the activations are in NTT form)
+        if (k0 != 0 || kc != nf)    // a channel shard of the layer-by-layer path is the caller's: conv shard, then pool and batch-norm on its channels
+            return fail(ctx, CRCNN_ERR_UNSUPPORTED, "channel shards of conv + pool + batch-norm need the pooled-grid path");
         crcnn_tensor *mid = nullptr;
         int rc = crcnn_conv_forward(ctx, in, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, &mid);
         if (rc) return rc;
@@ -1511,15 +1514,21 @@ int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w,
         cudaError_t e = launch_pool(ctx->dP, ctx->n, ctx->K, in->d, d_index, Nsum, Rp, nullptr, nullptr, true, sums->d, ctx->stream);
         if (e != cudaSuccess) { crcnn_tensor_free(ctx, sums); return fail(ctx, CRCNN_ERR_CUDA, cudaGetErrorString(e)); }
     }
-    rc = crcnn_conv_forward(ctx, sums, w->folded_w, w->folded_b, batch, sxd, syd, zd, pxs * xs, pys * ys, xf, yf, nf, &pooled);
+    rc = crcnn_conv_forward_shard(ctx, sums, w->folded_w, w->folded_b, batch, sxd, syd, zd, pxs * xs, pys * ys, xf, yf, nf, k0, kc, &pooled);
     crcnn_tensor_free(ctx, sums);
     if (rc) return rc;
-    if (pooled->count != (long)batch * nf * pxo * pyo || !pooled->ntt) {
+    if (pooled->count != (long)batch * kc * pxo * pyo || !pooled->ntt) {
         crcnn_tensor_free(ctx, pooled);
         return fail(ctx, CRCNN_ERR_UNSUPPORTED, "pooled-grid convolution produced an unexpected shape");
     }
     *out = pooled;
     return CRCNN_OK;
+}
+
+int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
+                               int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
+                               crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out) {
+    return crcnn_conv_pool_bn_forward_shard(ctx, in, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf, scale, mean, invstd, 0, nf, out);
 }
 
 int crcnn_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int zd, int xd, int yd, crcnn_plain *mean,

@@ -68,6 +68,7 @@ SYMBOLS = [
     ("crcnn_pool_bn_fc_fc_forward", _I, [_vp, _vp] + [_I] * 8 + [_vp] * 7 + [_I, _I, _vpp]),
     ("crcnn_fc_fc_forward", _I, [_vp, _vp, _vp, _vp, _vp, _vp, _I, _I, _I, _I, _vpp]),
     ("crcnn_conv_pool_bn_forward", _I, [_vp, _vp, _vp, _vp] + [_I] * 13 + [_vp, _vp, _vp, _vpp]),
+    ("crcnn_conv_pool_bn_forward_shard", _I, [_vp, _vp, _vp, _vp] + [_I] * 13 + [_vp, _vp, _vp, _I, _I, _vpp]),
     ("crcnn_square_forward", _I, [_vp, _vp, _vp, _vpp]),
     ("crcnn_transform_to_ntt", _I, [_vp, _vp]),
     ("crcnn_transform_from_ntt", _I, [_vp, _vp]),
@@ -363,8 +364,11 @@ class Engine:
     def bn(self, x, batch, zd, xd, yd, mean, invstd):
         return self._new(self.lib.crcnn_bn_forward, "tensor", x.ptr, batch, zd, xd, yd, mean.ptr, invstd.ptr)
 
-    def conv_pool_bn(self, x, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf, scale, mean, invstd):
-        """Convolution + average pooling + batch-norm on the pooled grid (crcnn_conv_pool_bn_forward)."""
+    def conv_pool_bn(self, x, w, b, batch, xd, yd, zd, xs, ys, xf, yf, nf, pxs, pys, pxf, pyf, scale, mean, invstd, shard=None):
+        """Convolution + average pooling + batch-norm on the pooled grid (crcnn_conv_pool_bn_forward[_shard])."""
+        if shard is not None:
+            return self._new(self.lib.crcnn_conv_pool_bn_forward_shard, "tensor", x.ptr, w.ptr, b.ptr, batch, xd, yd, zd, xs, ys, xf, yf, nf,
+                             pxs, pys, pxf, pyf, scale.ptr if scale is not None else None, mean.ptr, invstd.ptr, shard[0], shard[1])
         return self._new(self.lib.crcnn_conv_pool_bn_forward, "tensor", x.ptr, w.ptr, b.ptr, batch, xd, yd, zd, xs, ys, xf, yf, nf,
                          pxs, pys, pxf, pyf, scale.ptr if scale is not None else None, mean.ptr, invstd.ptr)
 

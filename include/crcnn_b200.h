@@ -213,6 +213,11 @@ int crcnn_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, int batch, int xd, i
 int crcnn_conv_pool_bn_forward(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
                                int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
                                crcnn_plain *mean, crcnn_plain *invstd, crcnn_tensor **out);
+/* Output channels [k0, k0+kc) of the same (one GPU's share of the reference's filter split, convolutionalLayer.cpp:177-187; pooling and
+ * batch-norm are per channel).  Only on the pooled grid: CRCNN_ERR_UNSUPPORTED where the whole-layer call would fall back. */
+int crcnn_conv_pool_bn_forward_shard(crcnn_ctx *ctx, crcnn_tensor *in, crcnn_plain *w, crcnn_plain *b, int batch, int xd, int yd, int zd,
+                                     int xs, int ys, int xf, int yf, int nf, int pxs, int pys, int pxf, int pyf, crcnn_plain *scale,
+                                     crcnn_plain *mean, crcnn_plain *invstd, int k0, int kc, crcnn_tensor **out);
 /* Two FullyConnectedLayer::forward calls in a row with no layer between them (fc3 -> fc4, the tail of every reference topology:
  * CrCNN/src/cnnBuilder.cpp:121-122, 132-133, 153-154; fullyConnectedLayer.cpp:96-166), producing the second layer's output
  * ciphertexts -- the same bytes as the two calls.  fc2(fc1(x)) = (W2 W1) x + (W2 Delta b1 + Delta b2) over Z_q[x]/(x^n+1): the composed

@@ -382,6 +382,14 @@ def test_conv_pool_bn_on_the_pooled_grid(env):
         eng.to_ntt(tn)      # NTT-form input
         got_n = eng.download(eng.conv_pool_bn(tn, w, bias, *geo, *packs))
         assert np.array_equal(got_n.reshape(want.shape), want), geo
+        # output-channel shard [1, nf) (ShardedNetwork): the same channels of the full result; only on the pooled grid
+        if pooled_grid:
+            got_sh = eng.download(eng.conv_pool_bn(eng.upload(x), w, bias, *geo, *packs, shard=(1, nf - 1)))
+            want_sh = want.reshape(batch, nf, pxo * pyo, *x.shape[1:])[:, 1:]
+            assert np.array_equal(got_sh.reshape(want_sh.shape), want_sh), geo
+        else:
+            with pytest.raises(Exception):
+                eng.conv_pool_bn(eng.upload(x), w, bias, *geo, *packs, shard=(1, nf - 1))
         # sum pooling (no factor) in the middle: same path, C = invstd
         want_s = np.concatenate([
             orc.bn(orc.pool(orc.conv(x[b * per:(b + 1) * per], xd, yd, zd, xs, ys, xf, yf, nf, wp, bp).reshape(nf * cxo * cyo, *x.shape[1:]),
