@@ -25,6 +25,7 @@
 #include <fstream>
 #include <functional>
 #include <istream>
+#include <map>
 #include <memory>
 #include <ostream>
 #include <stdexcept>
@@ -893,6 +894,24 @@ public:
                     continue;
                 }
             }
+            // ConvolutionalLayer + (Avg)PoolingLayer with no batch-norm behind it (the Tiny topology, cnnBuilder.cpp:157-169): the same pooled-grid
+            // layer with an identity batch-norm (mean 0, factor 1: C = the pooling scale, D = 0)
+            if (fuse_conv_pool_bn && i + 1 < last) {
+                auto *conv = dynamic_cast<ConvolutionalLayer *>(layers[i].get());
+                auto *pool = conv ? dynamic_cast<PoolingLayer *>(layers[i + 1].get()) : nullptr;
+                if (pool && pool->xd == conv->xo && pool->yd == conv->yo) {
+                    IdentityBn &id = identity_bn(conv->nf);
+                    Runtime &rt = Runtime::get();
+                    crcnn_tensor *o = nullptr;
+                    rt.check(crcnn_conv_pool_bn_forward(rt.ctx(), x.t, conv->weight_pack(), conv->bias_pack(), x.batch, conv->xd, conv->yd, conv->zd,
+                                                        conv->xs, conv->ys, conv->xf, conv->yf, conv->nf, pool->xs, pool->ys, pool->xf, pool->yf,
+                                                        pool->scale_or_null(), id.mean.p, id.invstd.p, &o));
+                    x = DeviceTensor(o, conv->nf, pool->xo, pool->yo, x.batch);
+                    if (after_layer) { after_layer(i); after_layer(i + 1); }
+                    i++;
+                    continue;
+                }
+            }
             // AvgPoolingLayer + BatchNormLayer + two FullyConnectedLayers: window sums + one composed layer (same bytes; crcnn_pool_bn_fc_fc_forward)
             if (fuse_fc_fc && fuse_pool_bn && i + 3 < last) {
                 auto *pool = dynamic_cast<PoolingLayer *>(layers[i].get());
@@ -933,6 +952,18 @@ public:
         }
         return x;
     }
+    // mean 0 / factor 1 packs per channel count, for chains that have no batch-norm of their own
+    struct IdentityBn { PlainPack mean, invstd; };
+    IdentityBn &identity_bn(int channels) {
+        auto &slot = identity_bn_[channels];
+        if (!slot) {
+            slot = std::make_shared<IdentityBn>();
+            slot->mean.encode(std::vector<float>((size_t)channels, 0.f));
+            slot->invstd.encode(std::vector<float>((size_t)channels, 1.f));
+        }
+        return *slot;
+    }
+    std::map<int, std::shared_ptr<IdentityBn>> identity_bn_;
     bool fuse_fc_fc = !(std::getenv("CRCNN_FC_FC") && std::atoi(std::getenv("CRCNN_FC_FC")) == 0);   // A/B switch, same bytes
     bool fuse_conv_pool_bn = !(std::getenv("CRCNN_CONV_POOL_BN") && std::atoi(std::getenv("CRCNN_CONV_POOL_BN")) == 0);   // A/B switch, same bytes
     bool fuse_pool_bn = !(std::getenv("CRCNN_POOL_BN") && std::atoi(std::getenv("CRCNN_POOL_BN")) == 0);   // A/B switch, same bytes
