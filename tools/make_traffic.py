@@ -9,7 +9,7 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CLASS_OF = {"ntt_fwd_digits_kernel": "relinearize", "r32_digits_kernel": "relinearize_u32", "ntt_inv_tensor_kernel": "ntt_inverse", "ntt_inv_kernel": "ntt_inverse_plain", "ntt_fwd_kernel": "ntt_forward",
+CLASS_OF = {"ntt_fwd_digits_kernel": "relinearize", "r32_digits_kernel": "relinearize_u32", "ntt_inv_tensor_kernel": "square_tensor", "ntt_inv_kernel": "ntt_inverse", "ntt_fwd_kernel": "ntt_forward",
             "tc_mac_kernel": "weighted_sum_tc_i8", "tcn2_mac_kernel": "weighted_sum_tcn_i8", "tcn_mac_kernel": "weighted_sum_tcn_i8_rowmajor", "tcn_split_kernel": "tcn_plane_split",
             "behz_floor_kernel": "behz_floor_sk", "pool_kernel": "pool_sum", "bn_kernel": "batch_norm", "mac_kernel": "weighted_sum_mac"}
 # ncu counters bench.py prints next to every roofline fraction (percent of peak while the kernel was active)
