@@ -616,8 +616,11 @@ def main_b200(args, rank, world, local_rank):
                     "frac": d["hbm_frac"], "peak_source": peak_src}
         if "int_pipe_frac" in d:
             roofline["int_pipe"] = {"frac": d["int_pipe_frac"], "imad_wide_ginstr_s": wide_rate / 1e9,
-                                    "note": "the binding resource of this kernel: the IMAD pipe; peak = independent IMAD.WIDE.U32 chains "
-                                            "measured in this run; counted IMAD-pipe slots per operation: %r" % (IMAD_SLOTS,)}
+                                    "note": "the binding resource of this kernel: the IMAD (FMA-heavy) pipe; frac = NECESSARY multiplier slots of the counted "
+                                            "operations / the IMAD.WIDE.U32 issue rate measured in this run (slots per operation: %r); the pipe's "
+                                            "actual busy share, overhead instructions included, is ncu.pipe_fmaheavy_cycles_pct" % (IMAD_SLOTS,)}
+    if dname in counters:
+        roofline["ncu"] = counters[dname]    # hardware counters of this kernel from the committed capture: pipe_fmaheavy_cycles_pct is the multiplier pipe's busy share
     roofline.update({"traffic": traffic.get(dname), "avg_launch_ms": avg_launch_ms, "launches_per_step": d["launches_per_step"],
                      "share_of_step": d["share_of_step"], "alg_bytes_per_launch": d["alg_gb_per_step"] * 1e9 / d["launches_per_step"],
                      "int_pipe_probe_gmac_s": probe_rate / 1e9, "imad_wide_probe_ginstr_s": wide_rate / 1e9,

@@ -15,6 +15,8 @@ CLASS_OF = {"ntt_fwd_digits_kernel": "relinearize", "r32_digits_kernel": "reline
 # ncu counters bench.py prints next to every roofline fraction (percent of peak while the kernel was active)
 COUNTERS = {"pipe_tensor_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
             "pipe_fma_pct": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+            "pipe_fmaheavy_cycles_pct": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",   # IMAD runs here: the binding pipe of the transforms
+            "sm_throughput_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "pipe_alu_pct": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
             "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active",
             "warps_active_pct": "sm__warps_active.avg.pct_of_peak_sustained_active",
