@@ -358,6 +358,8 @@ public:
 // ------------------------------------------------------------------------------------------------
 // ConvolutionalLayer (CrCNN/src/convolutionalLayer.h:9-58)
 // ------------------------------------------------------------------------------------------------
+class PoolingLayer;      // declared here so that member signatures below name THESE classes, not same-named ones of an including program
+class BatchNormLayer;
 class ConvolutionalLayer : public Layer {
 public:
     int xd, yd, zd, xs, ys, xf, yf, nf, th_count;  // th_count is accepted and ignored (the GPU schedules the work)
@@ -526,7 +528,7 @@ public:
         return DeviceTensor(o, 1, next.out_dim, 1, in.batch);
     }
     // avg-pool + batch-norm + this layer + the next one (crcnn_pool_bn_fc_fc_forward): layers 5-8 of the nine-layer networks
-    DeviceTensor forward_after_avgpool_bn_then(DeviceTensor in, class PoolingLayer &pool, class BatchNormLayer &bn, FullyConnectedLayer &next);
+    DeviceTensor forward_after_avgpool_bn_then(DeviceTensor in, PoolingLayer &pool, BatchNormLayer &bn, FullyConnectedLayer &next);
     // Output rows [o0, o0+oc) only: this GPU's share of the reference's row split (fullyConnectedLayer.cpp:148-158)
     DeviceTensor forward_shard(const DeviceTensor &in, int o0, int oc) {
         Runtime &rt = Runtime::get();

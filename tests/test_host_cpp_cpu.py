@@ -67,3 +67,13 @@ def test_shard_split_and_reencryption_policy(tmp_path):
             total, world, r, first, count = map(int, f)
             assert nets.shard_range(total, world, r) == (first, count), ln
     assert "refused 1 needs 1" in lines and "six_layers_need 0" in lines and "shape 1 32 32 10" in lines
+
+
+def test_reference_harness_is_not_stale():
+    """oracle/_ref/dropin_seal_test (the reference's own classes next to the drop-in ones, run by tests/test_gpu_cpp_dropin.py on the GPU box,
+    where /root/reference does not exist) must have been rebuilt after the last change to the headers it compiles: `make -q` on the recipe."""
+    import subprocess
+    if not os.path.isdir("/root/reference") or not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "dropin_seal_test")):
+        pytest.skip("no reference tree / harness not built here")
+    rc = subprocess.run(["make", "-q", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref"], capture_output=True).returncode
+    assert rc == 0, "oracle/_ref is older than its sources: run `python -c 'import __graft_entry__ as g; g.build()'`"
