@@ -610,6 +610,63 @@ r32_crt_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__restri
     *reinterpret_cast<ulonglong2 *>(out + (ct * 2 + pi) * (long)K * n + w) = res;
 }
 
+// r32_intt_kernel and r32_crt_kernel in one: one CTA = (ciphertext, output o = p*K + j) transforms the S3 auxiliary-prime residues of its
+// polynomial back in shared memory and reconstructs from there -- the 2 x S3 x n 32-bit words per output that the two-kernel form writes to
+// and reads back from HBM (45 GB per step of the headline network) never leave the SM.  S3 * 36 KB of shared memory: two CTAs per SM at n = 8192.
+template <int LOGN, int S3>
+__global__ void __launch_bounds__(Plan32<LOGN>::THREADS, 2)
+r32_intt_crt_kernel(const DeviceParams *__restrict__ P, const Relin32Consts *__restrict__ cp, const uint32_t *__restrict__ acc,
+                    const uint64_t *__restrict__ in3, uint64_t *__restrict__ out) {
+    extern __shared__ uint4 sm32v[];
+    uint32_t *sm32 = reinterpret_cast<uint32_t *>(sm32v);
+    constexpr int N = 1 << LOGN, SW = Plan32<LOGN>::SMEM_WORDS;
+    const int K = P->K;
+    const long b = blockIdx.x;                       // ct * 2K + o
+    const int o = (int)(b % (2 * K));
+    const long ct = b / (2 * K);
+    const int pi = o / K, j = o % K;
+#pragma unroll
+    for (int s = 0; s < S3; s++) {
+        const uint32_t *poly = acc + (b * S3 + s) * N;
+        for (int i = threadIdx.x * 4; i < N; i += Plan32<LOGN>::THREADS * 4)
+            *reinterpret_cast<uint4 *>(sm32 + s * SW + pad32(i)) = __ldg(reinterpret_cast<const uint4 *>(poly + i));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < S3; s++) ntt32_inverse<LOGN>(sm32 + s * SW, cp->iw[s], cp->iwl[s], cp->p[s]);   // ends with a barrier
+    CrtConsts k;
+#pragma unroll
+    for (int s = 0; s < S3; s++) {
+        k.p[s] = cp->p[s];
+        k.half[s] = cp->half[s];
+        k.c[s] = cp->cmodq[j][s];
+        k.csh[s] = cp->cmodq_sh[j][s];
+#pragma unroll
+        for (int i = 0; i < s; i++) {
+            k.ginv[s][i] = cp->ginv[s][i];
+            k.ginvp[s][i] = cp->ginvp[s][i];
+        }
+    }
+    k.Pmodq = cp->Pmodq[j];
+    k.q = P->tab[j].mod.q;
+    const uint64_t *cin = in3 + (ct * 3 + pi) * (long)K * N + (long)j * N;
+    uint64_t *dst = out + (ct * 2 + pi) * (long)K * N + (long)j * N;
+    for (int e = threadIdx.x * 2; e < N; e += Plan32<LOGN>::THREADS * 2) {
+        uint32_t r0[R32_MAXP], r1[R32_MAXP];
+#pragma unroll
+        for (int s = 0; s < S3; s++) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(sm32 + s * SW + pad32(e));   // inverse output in [0, 2p): canonical first
+            r0[s] = csub(v.x, k.p[s]);
+            r1[s] = csub(v.y, k.p[s]);
+        }
+        const ulonglong2 c = __ldg(reinterpret_cast<const ulonglong2 *>(cin + e));
+        ulonglong2 res;
+        res.x = addmod(c.x, crt_one<S3>(r0, k), k.q);
+        res.y = addmod(c.y, crt_one<S3>(r1, k), k.q);
+        *reinterpret_cast<ulonglong2 *>(dst + e) = res;
+    }
+}
+
 template <int LOGN>
 void configure32() {
     static DeviceOnce once;
@@ -678,6 +735,21 @@ cudaError_t run_t(const DeviceParams *dP, int K, const Relin32 &r, const uint64_
             default: e = cudaErrorInvalidValue;  // relin32_applicable admits K = 1, 2, 4, 8 only
         }
         if (e != cudaSuccess) return e;
+    }
+    if constexpr (LOGN <= 13) {
+        // fused inverse transform + reconstruction: 43.1 -> 41.4 ms per step of the headline network (two CTAs of 8 warps per SM hold it back);
+        // CRCNN_R32_FUSED=0 selects the two-kernel form (same bytes)
+        static const bool fused = !(std::getenv("CRCNN_R32_FUSED") && std::atoi(std::getenv("CRCNN_R32_FUSED")) == 0);
+        if (fused && c.S3 == 3) {
+            static DeviceOnce once3;
+            const int smem3 = 3 * Pl::SMEM_WORDS * 4;
+            if (once3.first()) {
+                cudaFuncSetAttribute(r32_intt_crt_kernel<LOGN, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3);
+                cudaFuncSetAttribute(r32_intt_crt_kernel<LOGN, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            }
+            r32_intt_crt_kernel<LOGN, 3><<<(unsigned)(count * 2 * K), Pl::THREADS, smem3, stream>>>(dP, r.dc, acc, in3, out);
+            return cudaGetLastError();
+        }
     }
     r32_intt_kernel<LOGN><<<(unsigned)(count * 2 * K * c.S3), Pl::THREADS, smem, stream>>>(r.dc, acc);
     const dim3 gc((unsigned)(count * 2 * K), (unsigned)(N / 512));
